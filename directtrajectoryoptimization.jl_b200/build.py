@@ -1,0 +1,38 @@
+"""Builds libdto.so (the C-ABI host runtime, csrc/dto_runtime.cpp) in-tree."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB = os.path.join(PKG_DIR, "libdto.so")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    srcs = [os.path.join(CSRC, "dto_runtime.cpp"), os.path.join(CSRC, "dto_model_abi.h"),
+            os.path.join(PKG_DIR, "..", "include", "dto.h")]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build_runtime(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function",
+           "-I", os.path.join(CUDA_HOME, "include"), os.path.join(CSRC, "dto_runtime.cpp"),
+           "-o", LIB + ".tmp", "-L", os.path.join(CUDA_HOME, "lib64"), "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libdto.so failed:\n" + r.stderr[-4000:])
+    os.replace(LIB + ".tmp", LIB)
+    if verbose:
+        print("[dto] built", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build_runtime(force=True, verbose=True)

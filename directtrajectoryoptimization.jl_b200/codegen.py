@@ -1,0 +1,487 @@
+"""Code generator: element expressions -> CUDA device functions -> model library (.so).
+
+This is the "new codegen stage" of the north star: it takes the symbolic expressions the
+element constructors build (what /root/reference/src/dynamics.jl:24-35, src/costs.jl:19-27,
+src/constraints.jl:28-40, src/general_constraint.jl:24-36 feed to `build_function`) and,
+instead of `eval`-ing one un-shared closure per output, lowers ALL outputs that are
+evaluated at the same knot in the same pass (e.g. Jacobian + Hessian of one dynamics
+element) through one common-subexpression-eliminated straight-line FP64 program, emitted as
+a `__device__` function that the hand-written kernels of csrc/dto_kernels.cuh inline.
+
+One model library = one translation unit = generated `struct DtoModel` + dto_kernels.cuh,
+compiled by nvcc for sm_100a and exporting `dto_model_entry()` (csrc/dto_model_abi.h).
+Libraries are content-addressed (the reference's "#TODO: option to load/save methods",
+src/dynamics.jl:22) and cached in-tree under _models/.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import sympy as sp
+
+CODEGEN_VERSION = "2"
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+MODEL_DIR = os.path.join(PKG_DIR, "_models")
+NVCC = os.environ.get("DTO_NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+# ----------------------------------------------------------------------------- specs
+@dataclass
+class ElementSpec:
+    """One element kind. `args` maps C argument name -> list of symbols (in order)."""
+    role: str                      # 'dyn' | 'cost' | 'stage'
+    n_out: int
+    nx: int
+    nu: int
+    nw: int
+    args: Dict[str, Sequence[sp.Symbol]]
+    evaluate: List[sp.Expr]
+    jac_rows: List[int]
+    jac_cols: List[int]
+    jac: List[sp.Expr]             # cost: dense gradient
+    has_hess: bool
+    hess_rows: List[int] = field(default_factory=list)
+    hess_cols: List[int] = field(default_factory=list)
+    hess: List[sp.Expr] = field(default_factory=list)
+    ineq: List[int] = field(default_factory=list)
+
+
+@dataclass
+class GeneralSpec:
+    num_variables: int
+    num_parameter: int
+    args: Dict[str, Sequence[sp.Symbol]]   # 'z', 'w', 'lam'
+    evaluate: List[sp.Expr]
+    jac_rows: List[int]
+    jac_cols: List[int]
+    jac: List[sp.Expr]
+    has_hess: bool
+    hess_rows: List[int] = field(default_factory=list)
+    hess_cols: List[int] = field(default_factory=list)
+    hess: List[sp.Expr] = field(default_factory=list)
+    ineq: List[int] = field(default_factory=list)
+
+
+@dataclass
+class ModelSpec:
+    name: str
+    dyn: List[ElementSpec]
+    cost: List[ElementSpec]
+    stage: List[ElementSpec]
+    general: Optional[GeneralSpec] = None
+
+
+# ----------------------------------------------------------------------------- C printing
+_CFUN = {"sin": "sin", "cos": "cos", "tan": "tan", "exp": "exp", "log": "log", "atan": "atan", "asin": "asin",
+         "acos": "acos", "sinh": "sinh", "cosh": "cosh", "tanh": "tanh", "Abs": "fabs", "atan2": "atan2",
+         "sign": "dto_sign"}
+
+
+def _lit(v: float) -> str:
+    r = repr(float(v))
+    if "e" not in r and "." not in r and "inf" not in r and "nan" not in r:
+        r += ".0"
+    return r
+
+
+def cstr(e: sp.Expr, names: Dict[sp.Symbol, str]) -> str:
+    """Fully parenthesised C for one expression; numbers printed with repr (17 digits)."""
+    if e.is_Symbol:
+        return names[e]
+    if e.is_Number or e.is_NumberSymbol:
+        v = float(e)
+        return _lit(v) if v >= 0 else f"({_lit(v)})"
+    if e.is_Add:
+        return "(" + " + ".join(cstr(a, names) for a in e.args) + ")"
+    if e.is_Mul:
+        num, den = [], []
+        for a in e.args:
+            if a.is_Pow and a.args[1].is_Integer and int(a.args[1]) < 0:
+                den.append(_pow_c(a.args[0], -int(a.args[1]), names))
+            else:
+                num.append(cstr(a, names))
+        n = "*".join(num) if num else "1.0"
+        if den:
+            d = "*".join(den)
+            return f"(({n})/({d}))" if len(den) > 1 or len(num) > 1 else f"({n}/{d})"
+        return "(" + n + ")"
+    if e.is_Pow:
+        b, p = e.args
+        if p.is_Integer:
+            k = int(p)
+            if k < 0:
+                return f"(1.0/{_pow_c(b, -k, names)})"
+            return _pow_c(b, k, names)
+        if p == sp.Rational(1, 2) or (p.is_Float and float(p) == 0.5):
+            return f"sqrt({cstr(b, names)})"
+        if p.is_Float and float(p) == int(float(p)):
+            k = int(float(p))
+            return f"(1.0/{_pow_c(b, -k, names)})" if k < 0 else _pow_c(b, k, names)
+        return f"pow({cstr(b, names)}, {cstr(p, names)})"
+    if e.is_Function:
+        fn = _CFUN.get(e.func.__name__)
+        if fn is None:
+            raise NotImplementedError(f"no CUDA lowering for function {e.func}")
+        return fn + "(" + ", ".join(cstr(a, names) for a in e.args) + ")"
+    raise NotImplementedError(f"no CUDA lowering for node {type(e)}")
+
+
+def _pow_c(b: sp.Expr, k: int, names) -> str:
+    bs = cstr(b, names)
+    if k == 1:
+        return bs
+    return f"dto_powi<{k}>({bs})"
+
+
+# ----------------------------------------------------------------------------- lowering
+def lower(outputs: List[Tuple[str, sp.Expr]], names: Dict[sp.Symbol, str], loads: Dict[sp.Symbol, str],
+          indent: str = "    ") -> Tuple[List[str], int]:
+    """outputs: [(lhs, expr)] -> C statements of one CSE'd straight-line program, op count.
+    `loads` maps input symbols to their memory expression (e.g. x[1]); each used input is
+    loaded into a register once."""
+    exprs = [sp.sympify(e) for _, e in outputs]
+    if not exprs:
+        return [], 0
+    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("t_"), order="none")
+    used = set()
+    for _, e in repl:
+        used |= e.free_symbols
+    for e in red:
+        used |= e.free_symbols
+    local = dict(names)
+    lines: List[str] = []
+    for s in sorted((s for s in used if s in loads), key=lambda s: loads[s]):
+        lines.append(f"{indent}const double {names[s]} = {loads[s]};")
+    ops = 0
+    for s, e in repl:
+        local[s] = str(s)
+        lines.append(f"{indent}const double {s} = {cstr(e, local)};")
+        ops += int(sp.count_ops(e))
+    for (lhs, _), e in zip(outputs, red):
+        lines.append(f"{indent}{lhs} = {cstr(e, local)};")
+        ops += int(sp.count_ops(e))
+    return lines, ops
+
+
+# ----------------------------------------------------------------------------- emission
+_PREAMBLE = r"""// GENERATED by directtrajectoryoptimization.jl_b200/codegen.py -- do not edit.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "dto_model_abi.h"
+
+template <int K>
+__device__ __forceinline__ double dto_powi(double x)
+{
+    if constexpr (K == 0) return 1.0;
+    else if constexpr (K == 1) return x;
+    else if constexpr (K % 2 == 0) { const double h = dto_powi<K / 2>(x); return h * h; }
+    else return x * dto_powi<K - 1>(x);
+}
+__device__ __forceinline__ double dto_sign(double x) { return (x > 0.0) - (x < 0.0); }
+"""
+
+
+def _names_loads(args: Dict[str, Sequence[sp.Symbol]]):
+    names, loads = {}, {}
+    for cname, syms in args.items():
+        for i, s in enumerate(syms):
+            names[s] = f"{cname}_{i}"
+            loads[s] = f"{cname}[{i}]"
+    return names, loads
+
+
+_SIG = {
+    "dyn": "const double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ w",
+    "cost": "const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ w",
+    "stage": "const double* __restrict__ x, const double* __restrict__ u, const double* __restrict__ w",
+}
+_CALL = {"dyn": "y, x, u, w", "cost": "x, u, w", "stage": "x, u, w"}
+
+
+def _emit_element(el: ElementSpec, k: int, out: List[str], stats: dict) -> None:
+    names, loads = _names_loads(el.args)
+    pre = f"{el.role}{k}"
+    sig = _SIG[el.role]
+    LAM = ", const double* __restrict__ lam"
+
+    def fn(name, extra_sig, outputs):
+        body, ops = lower(outputs, names, loads)
+        stats[f"{pre}_{name}"] = ops
+        out.append(f"__device__ __forceinline__ void {pre}_{name}({sig}{extra_sig})\n{{")
+        out.extend(body)
+        out.append("}\n")
+
+    if el.role == "cost":
+        body, ops = lower([("const double v", el.evaluate[0])], names, loads)
+        stats[f"{pre}_val"] = ops
+        out.append(f"__device__ __forceinline__ double {pre}_val({sig})\n{{")
+        out.extend(body)
+        out.append("    return v;\n}\n")
+        fn("grad", ", double* __restrict__ G", [(f"G[{i}]", e) for i, e in enumerate(el.jac)])
+        sigma = sp.Symbol("sigma")
+        names[sigma] = "sigma"
+        fn("hess", ", const double sigma, double* __restrict__ H",
+           [(f"H[{i}]", sigma * e) for i, e in enumerate(el.hess)] if el.has_hess else [])
+        return
+    fn("res", ", double* __restrict__ R", [(f"R[{i}]", e) for i, e in enumerate(el.evaluate)])
+    jo = [(f"J[{i}]", e) for i, e in enumerate(el.jac)]
+    ho = [(f"H[{i}]", e) for i, e in enumerate(el.hess)] if el.has_hess else []
+    fn("jac", ", double* __restrict__ J", jo)
+    fn("hess", LAM + ", double* __restrict__ H", ho)
+    fn("jac_hess", LAM + ", double* __restrict__ J, double* __restrict__ H", jo + ho)
+
+
+def _dispatch(role: str, n: int, name: str, ret: str, extra_sig: str, extra_call: str) -> List[str]:
+    sig = _SIG[role]
+    call = _CALL[role]
+    lines = [f"    __device__ __forceinline__ static {ret} {role}_{name}(int k, {sig}{extra_sig})", "    {",
+             "        switch (k) {"]
+    for k in range(n):
+        r = "return " if ret != "void" else ""
+        tail = "" if ret != "void" else " break;"
+        lines.append(f"        case {k}: {r}{role}{k}_{name}({call}{extra_call});{tail}")
+    lines.append("        default: break;")
+    lines.append("        }")
+    if ret != "void":
+        lines.append("        return 0.0;")
+    lines.append("    }")
+    return lines
+
+
+def _int_array(name: str, vals: Sequence[int]) -> str:
+    body = ", ".join(str(int(v)) for v in vals) if len(vals) else "0"
+    return f"static const int32_t {name}[] = {{{body}}};"
+
+
+def _general_templates(gen: GeneralSpec):
+    """De-duplicate general-constraint outputs by index shift: an output expression whose z,
+    w and lambda indices are renumbered relative to their minima is a TEMPLATE; outputs with
+    identical templates share one device function (SURVEY: rolled codegen)."""
+    zi = {s: i for i, s in enumerate(gen.args["z"])}
+    wi = {s: i for i, s in enumerate(gen.args["w"])}
+    li = {s: i for i, s in enumerate(gen.args.get("lam", []))}
+    canon_z = [sp.Symbol(f"gz{i}") for i in range(len(zi) + 1)]
+    canon_w = [sp.Symbol(f"gw{i}") for i in range(len(wi) + 1)]
+    canon_l = [sp.Symbol(f"gl{i}") for i in range(len(li) + 1)]
+    templates: List[List[sp.Expr]] = [[], [], []]
+    lookup: List[Dict[sp.Expr, int]] = [{}, {}, {}]
+    inst = [[], [], []]  # per class: (tmpl, zbase, wbase, lbase)
+    for cls, exprs in enumerate([gen.evaluate, gen.jac, gen.hess if gen.has_hess else []]):
+        for e in exprs:
+            e = sp.sympify(e)
+            fs = e.free_symbols
+            zs = [zi[s] for s in fs if s in zi]
+            ws = [wi[s] for s in fs if s in wi]
+            ls = [li[s] for s in fs if s in li]
+            zb, wb, lb = (min(zs) if zs else 0), (min(ws) if ws else 0), (min(ls) if ls else 0)
+            sub = {}
+            for s in fs:
+                if s in zi:
+                    sub[s] = canon_z[zi[s] - zb]
+                elif s in wi:
+                    sub[s] = canon_w[wi[s] - wb]
+                elif s in li:
+                    sub[s] = canon_l[li[s] - lb]
+            ce = e.xreplace(sub)
+            t = lookup[cls].get(ce)
+            if t is None:
+                t = len(templates[cls])
+                templates[cls].append(ce)
+                lookup[cls][ce] = t
+            inst[cls].append((t, zb, wb, lb))
+    names, loads = {}, {}
+    for i, s in enumerate(canon_z):
+        names[s], loads[s] = f"z_{i}", f"z[{i}]"
+    for i, s in enumerate(canon_w):
+        names[s], loads[s] = f"w_{i}", f"w[{i}]"
+    for i, s in enumerate(canon_l):
+        names[s], loads[s] = f"lam_{i}", f"lam[{i}]"
+    return templates, inst, names, loads
+
+
+def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
+    out: List[str] = [_PREAMBLE]
+    stats: dict = {}
+    for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
+        for k, el in enumerate(els):
+            _emit_element(el, k, out, stats)
+
+    # general constraint templates
+    gen = spec.general
+    gen_inst = None
+    if gen is not None:
+        templates, gen_inst, gnames, gloads = _general_templates(gen)
+        for cls in range(3):
+            for t, e in enumerate(templates[cls]):
+                body, ops = lower([("const double v", e)], gnames, gloads)
+                stats[f"gen{cls}_{t}"] = ops
+                out.append(f"__device__ __forceinline__ double gen{cls}_{t}(const double* __restrict__ z, "
+                           "const double* __restrict__ w, const double* __restrict__ lam)\n{")
+                out.extend(body)
+                out.append("    return v;\n}\n")
+        stats["gen_templates"] = [len(t) for t in templates]
+
+    halo = 0
+    for el in spec.dyn:
+        if el.has_hess and any(r > el.nx + el.nu for r in el.hess_rows):
+            halo = 1
+
+    # ---- struct DtoModel
+    # the struct name is unique per model: several model libraries live in one process and C++
+    # template instantiations / inline statics with equal mangled names may be shared across them
+    m: List[str] = [f"struct DtoModel_{source_hash} {{", f"    static constexpr int HESS_HALO = {halo};"]
+    for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
+        m.append(f"    __device__ __forceinline__ static int {role}_nh(int k)")
+        m.append("    {")
+        m.append("        switch (k) {")
+        for k, el in enumerate(els):
+            m.append(f"        case {k}: return {len(el.hess) if el.has_hess else 0};")
+        m.append("        default: return 0;")
+        m.append("        }")
+        m.append("    }")
+    LAM = ", const double* __restrict__ lam"
+    m += _dispatch("cost", len(spec.cost), "val", "double", "", "")
+    m += _dispatch("cost", len(spec.cost), "grad", "void", ", double* __restrict__ G", ", G")
+    m += _dispatch("cost", len(spec.cost), "hess", "void", ", const double sigma, double* __restrict__ H", ", sigma, H")
+    for role, n in (("dyn", len(spec.dyn)), ("stage", len(spec.stage))):
+        m += _dispatch(role, n, "res", "void", ", double* __restrict__ R", ", R")
+        m += _dispatch(role, n, "jac", "void", ", double* __restrict__ J", ", J")
+        m += _dispatch(role, n, "hess", "void", LAM + ", double* __restrict__ H", ", lam, H")
+        m += _dispatch(role, n, "jac_hess", "void", LAM + ", double* __restrict__ J, double* __restrict__ H",
+                       ", lam, J, H")
+    m.append("    __device__ __forceinline__ static double gen_eval(int cls, int tmpl, const double* __restrict__ z, "
+             "const double* __restrict__ w, const double* __restrict__ lam)")
+    m.append("    {")
+    if gen is not None:
+        for cls in range(3):
+            m.append(f"        if (cls == {cls}) {{")
+            m.append("            switch (tmpl) {")
+            for t in range(stats["gen_templates"][cls]):
+                m.append(f"            case {t}: return gen{cls}_{t}(z, w, lam);")
+            m.append("            default: break;")
+            m.append("            }")
+            m.append("        }")
+    m.append("        return 0.0;")
+    m.append("    }")
+    m.append("};")
+    m.append(f"using DtoModel = DtoModel_{source_hash};\n")
+    out.extend(m)
+    out.append('#include "dto_kernels.cuh"\n')
+
+    # ---- descriptors
+    d: List[str] = []
+
+    def elem_desc(role: str, k: int, el: ElementSpec) -> str:
+        p = f"{role}{k}"
+        d.append(_int_array(f"{p}_jr", el.jac_rows))
+        d.append(_int_array(f"{p}_jc", el.jac_cols))
+        d.append(_int_array(f"{p}_hr", el.hess_rows if el.has_hess else []))
+        d.append(_int_array(f"{p}_hc", el.hess_cols if el.has_hess else []))
+        d.append(_int_array(f"{p}_iq", el.ineq))
+        nj = len(el.jac)
+        nh = len(el.hess) if el.has_hess else 0
+        return (f"{{{el.n_out}, {el.nx}, {el.nu}, {el.nw}, {nj}, {p}_jr, {p}_jc, {int(el.has_hess)}, {nh}, "
+                f"{p}_hr, {p}_hc, {len(el.ineq)}, {p}_iq}}")
+
+    for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
+        rows = [elem_desc(role, k, el) for k, el in enumerate(els)]
+        if not rows:
+            rows = ["{0, 0, 0, 0, 0, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr}"]
+        d.append(f"static const dto_element_desc {role}_descs[] = {{\n    " + ",\n    ".join(rows) + "\n};")
+    if gen is not None:
+        d.append(_int_array("gen_jr", gen.jac_rows))
+        d.append(_int_array("gen_jc", gen.jac_cols))
+        d.append(_int_array("gen_hr", gen.hess_rows if gen.has_hess else []))
+        d.append(_int_array("gen_hc", gen.hess_cols if gen.has_hess else []))
+        d.append(_int_array("gen_iq", gen.ineq))
+        for cls in range(3):
+            for j, nm in enumerate(("tmpl", "zbase", "wbase", "lbase")):
+                d.append(_int_array(f"gen_{nm}{cls}", [t[j] for t in gen_inst[cls]]))
+        nh = len(gen.hess) if gen.has_hess else 0
+        d.append("static const dto_general_desc gen_desc = {"
+                 f"{gen.num_variables}, {gen.num_parameter}, {len(gen.evaluate)}, {len(gen.jac)}, gen_jr, gen_jc, "
+                 f"{int(gen.has_hess)}, {nh}, gen_hr, gen_hc, {len(gen.ineq)}, gen_iq, "
+                 "{gen_tmpl0, gen_tmpl1, gen_tmpl2}, {gen_zbase0, gen_zbase1, gen_zbase2}, "
+                 "{gen_wbase0, gen_wbase1, gen_wbase2}, {gen_lbase0, gen_lbase1, gen_lbase2}};")
+    fused = 0
+    for k in range(len(spec.dyn)):
+        fused = max(fused, stats.get(f"dyn{k}_jac_hess", 0))
+    stats["ops_fused_per_knot"] = fused
+    d.append(f"""
+static int model_launch(int kernel_id, const dto_launch_args* a, void* stream) {{ return dto::launch<DtoModel>(kernel_id, a, stream); }}
+static int64_t model_smem(int kernel_id, const dto_launch_args* a) {{ return dto::smem_bytes(kernel_id, a); }}
+static const dto_model_vtable model_vtable = {{
+    DTO_MODEL_ABI_VERSION, "{spec.name}", "{source_hash}",
+    {len(spec.dyn)}, {len(spec.cost)}, {len(spec.stage)},
+    dyn_descs, cost_descs, stage_descs, {"&gen_desc" if gen is not None else "nullptr"},
+    {halo}, DTO_WARPS, {fused},
+    model_launch, model_smem
+}};
+extern "C" __attribute__((visibility("default"))) const dto_model_vtable* dto_model_entry(void) {{ return &model_vtable; }}
+""")
+    out.extend(d)
+    return "\n".join(out), stats
+
+
+# ----------------------------------------------------------------------------- build
+def spec_hash(spec: ModelSpec) -> str:
+    h = hashlib.sha256()
+    h.update(CODEGEN_VERSION.encode())
+    for fname in ("dto_kernels.cuh", "dto_model_abi.h"):
+        with open(os.path.join(CSRC_DIR, fname), "rb") as f:
+            h.update(f.read())
+
+    def feed_el(el):
+        h.update(repr((el.role, el.n_out, el.nx, el.nu, el.nw, el.jac_rows, el.jac_cols, el.has_hess, el.hess_rows,
+                       el.hess_cols, el.ineq)).encode())
+        for e in list(el.evaluate) + list(el.jac) + (list(el.hess) if el.has_hess else []):
+            h.update(sp.srepr(e).encode())
+
+    for els in (spec.dyn, spec.cost, spec.stage):
+        h.update(b"|")
+        for el in els:
+            feed_el(el)
+    if spec.general is not None:
+        g = spec.general
+        h.update(repr((g.num_variables, g.num_parameter, g.jac_rows, g.jac_cols, g.has_hess, g.hess_rows, g.hess_cols,
+                       g.ineq)).encode())
+        for e in list(g.evaluate) + list(g.jac) + (list(g.hess) if g.has_hess else []):
+            h.update(sp.srepr(e).encode())
+    return h.hexdigest()[:16]
+
+
+def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> str:
+    """Generate + compile (or reuse) the model library; returns the path of the .so."""
+    os.makedirs(MODEL_DIR, exist_ok=True)
+    hsh = spec_hash(spec)
+    base = os.path.join(MODEL_DIR, f"{spec.name}_{hsh}")
+    so, cu = base + ".so", base + ".cu"
+    if os.path.exists(so) and not force:
+        return so
+    t0 = time.time()
+    src, stats = emit_model(spec, hsh)
+    with open(cu, "w") as f:
+        f.write(src)
+    if not os.path.exists(NVCC):
+        raise RuntimeError(f"nvcc not found at {NVCC}: the CUDA model library cannot be built (no CPU fallback exists)")
+    cmd = [NVCC, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+           "-I", CSRC_DIR, "-o", so + ".tmp", cu]
+    t1 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(base + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr + f"\ncodegen {t1 - t0:.1f}s nvcc {time.time() - t1:.1f}s\n"
+                + repr(stats) + "\n")
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {cu}:\n{r.stderr[-4000:]}")
+    os.replace(so + ".tmp", so)
+    if verbose:
+        print(f"[dto codegen] built {so} (codegen {t1 - t0:.1f}s, nvcc {time.time() - t1:.1f}s) ops={stats.get('ops_fused_per_knot')}")
+    return so

@@ -1,0 +1,939 @@
+// libdto.so -- host runtime behind include/dto.h.
+//
+//  * loads generated model libraries (dlopen) and checks their ABI;
+//  * assembles a problem shape: z-layout, constraint rows, Jacobian COO structure, sorted-unique
+//    Hessian structure and every per-knot slot table, in O(nnz log nnz) -- the restatement of
+//    /root/reference/src/data.jl:61-104,150-220 and the *_indices / sparsity_* helpers of
+//    src/dynamics.jl:129-204, src/costs.jl:75-104, src/constraints.jl:106-183,
+//    src/general_constraint.jl:93-139 (which are O(T^2)/O(nnz^2) there);
+//  * owns device memory, streams and the contiguous batch shards (one per listed device, no
+//    collective); keeps z / lambda / sigma / w resident between callbacks
+//    (replaces trajectory!/duals!, src/data.jl:258-278);
+//  * enqueues the model library's kernels for the five MOI callbacks (src/moi.jl:1-120).
+//
+// No CPU evaluation path exists in this file by design.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/dto.h"
+#include "dto_model_abi.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DTO_CUDA(call)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return fail(e__ == cudaErrorMemoryAllocation ? DTO_ERR_OOM : DTO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                          \
+    } while (0)
+
+#define DTO_REQUIRE(cond, ...)                                \
+    do {                                                      \
+        if (!(cond)) return fail(DTO_ERR_BAD_ARG, __VA_ARGS__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct dto_model {
+    void* handle = nullptr;
+    const dto_model_vtable* vt = nullptr;
+    std::string path;
+};
+
+struct dto_shape {
+    dto_model* model = nullptr;
+    int32_t T = 0;
+    bool use_general = false;
+    int64_t N_z = 0, N_c = 0, N_w = 0, nnz_J = 0, nnz_H = 0, nnz_H_nonunique = 0;
+    int64_t n_dyn_rows = 0, n_stage_rows = 0, n_gen_rows = 0;
+    int64_t n_dyn_jac = 0, n_stage_jac = 0, n_gen_jac = 0;
+    bool hessian_available = true;
+    std::vector<int32_t> nx, nu;                 // [T]
+    std::vector<dto_knot_entry> knot;            // [T+1]
+    std::vector<int64_t> jac_row, jac_col;       // 1-based
+    std::vector<int64_t> hess_row, hess_col;     // 1-based, sorted unique
+    std::vector<int32_t> hptr, hsrc;             // CSR slot -> term ids (knot elements only)
+    std::vector<int32_t> gen_inst[3];            // [n][4]
+    std::vector<int32_t> gen_hslot;
+    std::vector<double> c_lower, c_upper;
+    int32_t seg_cap[6] = {0, 0, 0, 0, 0, 0};
+    int32_t seg_pad[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct dto_shard {
+    int device = 0;
+    int64_t begin = 0, size = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    double* arr[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    dto_knot_entry* d_knot = nullptr;
+    int32_t* d_hptr = nullptr;
+    int32_t* d_hsrc = nullptr;
+    int32_t* d_gen_inst[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_gen_hslot = nullptr;
+};
+
+struct dto_batch {
+    dto_shape* shape = nullptr;
+    int64_t B = 0;
+    std::vector<dto_shard> shards;
+    bool have_x = false, have_duals = false;
+    int64_t launches = 0;
+};
+
+static int64_t array_width(const dto_shape* s, int array)
+{
+    switch (array) {
+    case DTO_ARRAY_Z: return s->N_z;
+    case DTO_ARRAY_LAMBDA: return s->N_c;
+    case DTO_ARRAY_SIGMA: return 1;
+    case DTO_ARRAY_W: return s->N_w;
+    case DTO_ARRAY_F: return 1;
+    case DTO_ARRAY_G: return s->N_z;
+    case DTO_ARRAY_C: return s->N_c;
+    case DTO_ARRAY_J: return s->nnz_J;
+    case DTO_ARRAY_H: return s->nnz_H;
+    default: return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------
+extern "C" int dto_abi_version(void) { return DTO_ABI_VERSION; }
+extern "C" const char* dto_last_error(void) { return g_err; }
+extern "C" const char* dto_status_string(int status)
+{
+    switch (status) {
+    case DTO_OK: return "ok";
+    case DTO_ERR_BAD_ARG: return "bad argument";
+    case DTO_ERR_CUDA: return "CUDA error";
+    case DTO_ERR_OOM: return "out of memory";
+    case DTO_ERR_MODEL: return "model library error";
+    case DTO_ERR_NO_HESSIAN: return "Hessian not available";
+    case DTO_ERR_STATE: return "invalid state";
+    default: return "unknown status";
+    }
+}
+extern "C" int dto_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+extern "C" int dto_model_load(const char* path, dto_model** out)
+{
+    if (!path || !out) return fail(DTO_ERR_BAD_ARG, "dto_model_load: null argument");
+    *out = nullptr;
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) return fail(DTO_ERR_MODEL, "dto_model_load: dlopen(%s) failed: %s", path, dlerror());
+    typedef const dto_model_vtable* (*entry_fn)(void);
+    entry_fn entry = (entry_fn)dlsym(h, "dto_model_entry");
+    if (!entry) {
+        dlclose(h);
+        return fail(DTO_ERR_MODEL, "dto_model_load: %s does not export dto_model_entry", path);
+    }
+    const dto_model_vtable* vt = entry();
+    if (!vt || vt->abi_version != DTO_MODEL_ABI_VERSION) {
+        int got = vt ? vt->abi_version : -1;
+        dlclose(h);
+        return fail(DTO_ERR_MODEL, "dto_model_load: %s has model ABI %d, runtime expects %d (rebuild the model)", path, got,
+                    DTO_MODEL_ABI_VERSION);
+    }
+    dto_model* m = new (std::nothrow) dto_model();
+    if (!m) {
+        dlclose(h);
+        return fail(DTO_ERR_OOM, "dto_model_load: out of host memory");
+    }
+    m->handle = h;
+    m->vt = vt;
+    m->path = path;
+    *out = m;
+    return DTO_OK;
+}
+
+extern "C" void dto_model_destroy(dto_model* m)
+{
+    if (!m) return;
+    // the library stays mapped: CUDA module teardown at dlclose time is not worth the risk
+    delete m;
+}
+extern "C" const char* dto_model_name(const dto_model* m) { return m ? m->vt->name : ""; }
+extern "C" const char* dto_model_hash(const dto_model* m) { return m ? m->vt->source_hash : ""; }
+
+static const dto_element_desc* kind_desc(const dto_model* m, int role, int kind)
+{
+    const dto_model_vtable* vt = m->vt;
+    int n = role == 0 ? vt->n_dyn : role == 1 ? vt->n_cost : role == 2 ? vt->n_stage : 0;
+    if (kind < 0 || kind >= n) return nullptr;
+    return (role == 0 ? vt->dyn : role == 1 ? vt->cost : vt->stage) + kind;
+}
+
+extern "C" int dto_model_num_kinds(const dto_model* m, int role)
+{
+    if (!m) return fail(DTO_ERR_BAD_ARG, "dto_model_num_kinds: null model");
+    switch (role) {
+    case 0: return m->vt->n_dyn;
+    case 1: return m->vt->n_cost;
+    case 2: return m->vt->n_stage;
+    default: return fail(DTO_ERR_BAD_ARG, "dto_model_num_kinds: role %d", role);
+    }
+}
+
+extern "C" int dto_model_kind_dims(const dto_model* m, int role, int kind, int32_t dims[6])
+{
+    if (!m || !dims) return fail(DTO_ERR_BAD_ARG, "dto_model_kind_dims: null argument");
+    const dto_element_desc* d = kind_desc(m, role, kind);
+    if (!d) return fail(DTO_ERR_BAD_ARG, "dto_model_kind_dims: no kind %d for role %d", kind, role);
+    dims[0] = d->n_out;
+    dims[1] = d->nx;
+    dims[2] = d->nu;
+    dims[3] = d->nw;
+    dims[4] = d->nnz_jac;
+    dims[5] = d->has_hess ? d->nnz_hess : 0;
+    return DTO_OK;
+}
+extern "C" int dto_model_has_general(const dto_model* m) { return (m && m->vt->general) ? 1 : 0; }
+
+// ------------------------------------------------------------------------------------------
+// shape assembly
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Term {
+    int64_t row, col;  // 1-based global
+    int32_t id;        // term id (knot elements) or general index
+};
+
+int32_t cyclic_window_max(const std::vector<int32_t>& size, int W)
+{
+    const int T = (int)size.size();
+    int32_t best = 0;
+    for (int t0 = 0; t0 < T; ++t0) {
+        int64_t s = 0;
+        for (int i = 0; i < W; ++i) s += size[(t0 + i) % T];
+        best = std::max<int64_t>(best, s);
+    }
+    return best;
+}
+}  // namespace
+
+extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape** out)
+{
+    if (!m || !d || !out) return fail(DTO_ERR_BAD_ARG, "dto_shape_create: null argument");
+    *out = nullptr;
+    const int T = d->T;
+    DTO_REQUIRE(T >= 2, "dto_shape_create: T=%d, need at least 2 knots", T);
+    DTO_REQUIRE(d->dynamics_kind && d->cost_kind && d->stage_kind, "dto_shape_create: null kind array");
+    const dto_general_desc* gen = nullptr;
+    if (d->use_general) {
+        gen = m->vt->general;
+        if (!gen) return fail(DTO_ERR_MODEL, "dto_shape_create: use_general=1 but model '%s' has no general constraint", m->vt->name);
+    }
+    dto_shape* s = new (std::nothrow) dto_shape();
+    if (!s) return fail(DTO_ERR_OOM, "dto_shape_create: out of host memory");
+    struct Guard {
+        dto_shape* s;
+        ~Guard() { delete s; }
+    } guard{s};
+    s->model = m;
+    s->T = T;
+    s->use_general = gen != nullptr;
+
+    // ---- dims (src/dynamics.jl:206-211) and kinds
+    std::vector<const dto_element_desc*> dyn(T, nullptr), cost(T, nullptr), stage(T, nullptr);
+    for (int t = 0; t < T; ++t) {
+        if (t < T - 1) {
+            dyn[t] = kind_desc(m, 0, d->dynamics_kind[t]);
+            DTO_REQUIRE(dyn[t], "dto_shape_create: dynamics_kind[%d]=%d out of range", t, d->dynamics_kind[t]);
+        }
+        cost[t] = kind_desc(m, 1, d->cost_kind[t]);
+        DTO_REQUIRE(cost[t], "dto_shape_create: cost_kind[%d]=%d out of range", t, d->cost_kind[t]);
+        if (d->stage_kind[t] >= 0) {
+            stage[t] = kind_desc(m, 2, d->stage_kind[t]);
+            DTO_REQUIRE(stage[t], "dto_shape_create: stage_kind[%d]=%d out of range", t, d->stage_kind[t]);
+        }
+    }
+    s->nx.resize(T);
+    s->nu.resize(T);
+    for (int t = 0; t < T - 1; ++t) {
+        s->nx[t] = dyn[t]->nx;
+        s->nu[t] = dyn[t]->nu;
+        if (t > 0)
+            DTO_REQUIRE(dyn[t - 1]->n_out == dyn[t]->nx, "dto_shape_create: dynamics[%d].num_next_state=%d != dynamics[%d].num_state=%d",
+                        t - 1, dyn[t - 1]->n_out, t, dyn[t]->nx);
+    }
+    s->nx[T - 1] = dyn[T - 2]->n_out;
+    s->nu[T - 1] = 0;
+    for (int t = 0; t < T; ++t) {
+        DTO_REQUIRE(cost[t]->nx + cost[t]->nu == s->nx[t] + s->nu[t],
+                    "dto_shape_create: objective[%d] has %d+%d variables, knot has %d+%d (gradient slice would not fit, "
+                    "src/costs.jl:61)", t, cost[t]->nx, cost[t]->nu, s->nx[t], s->nu[t]);
+        if (stage[t])
+            DTO_REQUIRE(stage[t]->nx == s->nx[t], "dto_shape_create: constraints[%d].num_state=%d != %d", t, stage[t]->nx, s->nx[t]);
+        if (!cost[t]->has_hess) s->hessian_available = false;
+    }
+
+    // ---- prefix tables
+    s->knot.resize(T + 1);
+    std::vector<int32_t> hterm_cost(T, 0), hterm_dyn(T, 0), hterm_stage(T, 0);
+    {
+        int64_t zofs = 0, rdyn = 0, jdyn = 0, hterm = 0, wsum = 0;
+        for (int t = 0; t < T; ++t) {
+            dto_knot_entry& k = s->knot[t];
+            k.zofs = (int32_t)zofs;
+            k.nx = s->nx[t];
+            const int32_t pdim = d->parameter_dim ? d->parameter_dim[t] : 0;
+            DTO_REQUIRE(pdim >= 0, "dto_shape_create: parameter_dim[%d] negative", t);
+            k.wofs = d->parameter_offset ? d->parameter_offset[t] : (int32_t)wsum;
+            wsum += pdim;
+            if (d->parameter_offset)
+                DTO_REQUIRE(k.wofs >= 0 && k.wofs + pdim <= d->num_parameter, "dto_shape_create: parameter slice of knot %d outside [0,%d)", t,
+                            d->num_parameter);
+            const dto_element_desc* els[3] = {dyn[t], cost[t], stage[t]};
+            for (const dto_element_desc* e : els)
+                if (e) DTO_REQUIRE(e->nw <= pdim, "dto_shape_create: an element at knot %d reads %d parameters, w_t has %d", t, e->nw, pdim);
+            k.kdyn = t < T - 1 ? d->dynamics_kind[t] : -1;
+            k.kcost = d->cost_kind[t];
+            k.kstage = stage[t] ? d->stage_kind[t] : -1;
+            k.rdyn = (int32_t)rdyn;
+            k.jdyn = (int32_t)jdyn;
+            k.hterm = (int32_t)hterm;
+            hterm_cost[t] = cost[t]->has_hess ? cost[t]->nnz_hess : 0;
+            hterm_dyn[t] = (dyn[t] && dyn[t]->has_hess) ? dyn[t]->nnz_hess : 0;
+            hterm_stage[t] = (stage[t] && stage[t]->has_hess) ? stage[t]->nnz_hess : 0;
+            hterm += hterm_cost[t] + hterm_dyn[t] + hterm_stage[t];
+            zofs += s->nx[t] + s->nu[t];
+            if (dyn[t]) {
+                rdyn += dyn[t]->n_out;
+                jdyn += dyn[t]->nnz_jac;
+            }
+        }
+        s->N_z = zofs;
+        s->N_w = d->parameter_offset ? d->num_parameter : wsum;
+        s->n_dyn_rows = rdyn;
+        s->n_dyn_jac = jdyn;
+        int64_t rstage = rdyn, jstage = jdyn;
+        for (int t = 0; t < T; ++t) {
+            s->knot[t].rstage = (int32_t)rstage;
+            s->knot[t].jstage = (int32_t)jstage;
+            if (stage[t]) {
+                rstage += stage[t]->n_out;
+                jstage += stage[t]->nnz_jac;
+            }
+        }
+        s->n_stage_rows = rstage - rdyn;
+        s->n_stage_jac = jstage - jdyn;
+        dto_knot_entry& e = s->knot[T];
+        e.zofs = (int32_t)zofs;
+        e.nx = 0;
+        e.wofs = 0;
+        e.kdyn = e.kcost = e.kstage = -1;
+        e.rdyn = (int32_t)rdyn;
+        e.rstage = (int32_t)rstage;
+        e.jdyn = (int32_t)jdyn;
+        e.jstage = (int32_t)jstage;
+        e.hterm = (int32_t)hterm;
+        e.hslot = 0;  // filled below
+    }
+    if (gen) {
+        DTO_REQUIRE(gen->num_variables == s->N_z, "dto_shape_create: general constraint built for %d variables, shape has %lld",
+                    gen->num_variables, (long long)s->N_z);
+        DTO_REQUIRE(gen->num_parameter <= s->N_w, "dto_shape_create: general constraint reads %d parameters, problems carry %lld",
+                    gen->num_parameter, (long long)s->N_w);
+        s->n_gen_rows = gen->num_constraint;
+        s->n_gen_jac = gen->nnz_jac;
+    }
+    s->N_c = s->n_dyn_rows + s->n_stage_rows + s->n_gen_rows;
+    s->nnz_J = s->n_dyn_jac + s->n_stage_jac + s->n_gen_jac;
+    DTO_REQUIRE(s->N_z < (1ll << 30) && s->nnz_J < (1ll << 30), "dto_shape_create: shape too large for 32-bit tables");
+
+    // ---- constraint bounds (src/data.jl:135-148)
+    s->c_lower.assign(s->N_c, 0.0);
+    s->c_upper.assign(s->N_c, 0.0);
+    for (int t = 0; t < T; ++t)
+        if (stage[t])
+            for (int i = 0; i < stage[t]->n_ineq; ++i) {
+                const int r = stage[t]->ineq[i];
+                DTO_REQUIRE(r >= 1 && r <= stage[t]->n_out, "dto_shape_create: constraints[%d] inequality index %d out of range", t, r);
+                s->c_lower[s->knot[t].rstage + r - 1] = -std::numeric_limits<double>::infinity();
+            }
+    if (gen)
+        for (int i = 0; i < gen->n_ineq; ++i) {
+            const int r = gen->ineq[i];
+            DTO_REQUIRE(r >= 1 && r <= gen->num_constraint, "dto_shape_create: general inequality index %d out of range", r);
+            s->c_lower[s->n_dyn_rows + s->n_stage_rows + r - 1] = -std::numeric_limits<double>::infinity();
+        }
+
+    // ---- Jacobian COO structure (src/data.jl:170-175, Q3)
+    s->jac_row.reserve(s->nnz_J);
+    s->jac_col.reserve(s->nnz_J);
+    for (int t = 0; t < T - 1; ++t)
+        for (int k = 0; k < dyn[t]->nnz_jac; ++k) {
+            s->jac_row.push_back(s->knot[t].rdyn + dyn[t]->jac_row[k]);
+            s->jac_col.push_back(s->knot[t].zofs + dyn[t]->jac_col[k]);
+        }
+    for (int t = 0; t < T; ++t)
+        if (stage[t])
+            for (int k = 0; k < stage[t]->nnz_jac; ++k) {
+                s->jac_row.push_back(s->knot[t].rstage + stage[t]->jac_row[k]);
+                s->jac_col.push_back(s->knot[t].zofs + stage[t]->jac_col[k]);
+            }
+    if (gen)
+        for (int k = 0; k < gen->nnz_jac; ++k) {
+            s->jac_row.push_back(s->n_dyn_rows + s->n_stage_rows + gen->jac_row[k]);
+            s->jac_col.push_back(gen->jac_col[k]);
+        }
+
+    // ---- Hessian terms in the reference's concatenation order (src/data.jl:178-182, Q4)
+    std::vector<Term> terms;       // knot-element terms: id = smem term id
+    std::vector<Term> gen_terms;   // general terms: id = index into the general nzval
+    for (int t = 0; t < T; ++t)    // objective
+        for (int k = 0; k < hterm_cost[t]; ++k)
+            terms.push_back({s->knot[t].zofs + cost[t]->hess_row[k], s->knot[t].zofs + cost[t]->hess_col[k], s->knot[t].hterm + k});
+    for (int t = 0; t < T - 1; ++t)  // dynamics
+        for (int k = 0; k < hterm_dyn[t]; ++k)
+            terms.push_back({s->knot[t].zofs + dyn[t]->hess_row[k], s->knot[t].zofs + dyn[t]->hess_col[k],
+                             s->knot[t].hterm + hterm_cost[t] + k});
+    for (int t = 0; t < T; ++t)  // stage
+        for (int k = 0; k < hterm_stage[t]; ++k)
+            terms.push_back({s->knot[t].zofs + stage[t]->hess_row[k], s->knot[t].zofs + stage[t]->hess_col[k],
+                             s->knot[t].hterm + hterm_cost[t] + hterm_dyn[t] + k});
+    if (gen && gen->has_hess)
+        for (int k = 0; k < gen->nnz_hess; ++k) gen_terms.push_back({gen->hess_row[k], gen->hess_col[k], k});
+    s->nnz_H_nonunique = (int64_t)terms.size() + (int64_t)gen_terms.size();
+
+    // key = sort(unique(list)): lexicographic on (row, col) (src/data.jl:184)
+    std::vector<std::pair<int64_t, int64_t>> key;
+    key.reserve(terms.size() + gen_terms.size());
+    for (const Term& t : terms) key.emplace_back(t.row, t.col);
+    for (const Term& t : gen_terms) key.emplace_back(t.row, t.col);
+    std::sort(key.begin(), key.end());
+    key.erase(std::unique(key.begin(), key.end()), key.end());
+    s->nnz_H = (int64_t)key.size();
+    DTO_REQUIRE(s->nnz_H < (1ll << 30), "dto_shape_create: Hessian too large for 32-bit tables");
+    s->hess_row.resize(key.size());
+    s->hess_col.resize(key.size());
+    for (size_t i = 0; i < key.size(); ++i) {
+        s->hess_row[i] = key[i].first;
+        s->hess_col[i] = key[i].second;
+        DTO_REQUIRE(key[i].first >= 1 && key[i].first <= s->N_z && key[i].second >= 1 && key[i].second <= s->N_z,
+                    "dto_shape_create: Hessian entry (%lld,%lld) outside the %lld variables", (long long)key[i].first,
+                    (long long)key[i].second, (long long)s->N_z);
+    }
+    auto slot_of = [&](int64_t r, int64_t c) -> int32_t {
+        return (int32_t)(std::lower_bound(key.begin(), key.end(), std::make_pair(r, c)) - key.begin());
+    };
+    // first slot owned by each knot (rows are variables of knot t)
+    for (int t = 0; t <= T; ++t)
+        s->knot[t].hslot = (int32_t)(std::lower_bound(key.begin(), key.end(), std::make_pair((int64_t)s->knot[t].zofs + 1, (int64_t)0)) - key.begin());
+    // CSR slot -> contributing term ids, in reference += order (stable counting sort)
+    s->hptr.assign(s->nnz_H + 1, 0);
+    std::vector<int32_t> tslot(terms.size());
+    for (size_t i = 0; i < terms.size(); ++i) {
+        tslot[i] = slot_of(terms[i].row, terms[i].col);
+        s->hptr[tslot[i] + 1]++;
+    }
+    for (int64_t i = 0; i < s->nnz_H; ++i) s->hptr[i + 1] += s->hptr[i];
+    s->hsrc.resize(terms.size());
+    {
+        std::vector<int32_t> fill(s->hptr.begin(), s->hptr.end() - 1);
+        for (size_t i = 0; i < terms.size(); ++i) s->hsrc[fill[tslot[i]]++] = terms[i].id;
+    }
+    // locality check: a slot owned by knot t may only draw from knot t and dynamics[t-1]
+    for (int t = 0; t < T; ++t) {
+        const int32_t lo = t > 0 ? s->knot[t - 1].hterm + hterm_cost[t - 1] : s->knot[t].hterm;
+        const int32_t lo_end = t > 0 ? lo + hterm_dyn[t - 1] : lo;
+        const int32_t own0 = s->knot[t].hterm, own1 = s->knot[t + 1].hterm;
+        for (int32_t sl = s->knot[t].hslot; sl < s->knot[t + 1].hslot; ++sl)
+            for (int32_t p = s->hptr[sl]; p < s->hptr[sl + 1]; ++p) {
+                const int32_t id = s->hsrc[p];
+                const bool ok = (id >= own0 && id < own1) || (id >= lo && id < lo_end);
+                DTO_REQUIRE(ok, "dto_shape_create: Hessian slot %d (row %lld) draws from an element outside knots %d..%d; "
+                                "element reaches beyond its [x;u;y] window", sl, (long long)s->hess_row[sl], t - 1, t);
+            }
+    }
+    s->gen_hslot.resize(gen_terms.size());
+    for (size_t i = 0; i < gen_terms.size(); ++i) s->gen_hslot[i] = slot_of(gen_terms[i].row, gen_terms[i].col);
+    if (gen) {
+        const int n[3] = {gen->num_constraint, gen->nnz_jac, gen->has_hess ? gen->nnz_hess : 0};
+        for (int cls = 0; cls < 3; ++cls) {
+            s->gen_inst[cls].resize((size_t)n[cls] * 4);
+            for (int i = 0; i < n[cls]; ++i) {
+                s->gen_inst[cls][4 * i + 0] = gen->inst_tmpl[cls][i];
+                s->gen_inst[cls][4 * i + 1] = gen->inst_zbase[cls][i];
+                s->gen_inst[cls][4 * i + 2] = gen->inst_wbase[cls][i];
+                s->gen_inst[cls][4 * i + 3] = gen->inst_lbase[cls][i];
+            }
+        }
+    }
+
+    // ---- shared-memory segment capacities: max flat extent of 32 consecutive (b,t) items
+    {
+        std::vector<int32_t> sz[6];
+        for (int k = 0; k < 6; ++k) sz[k].resize(T);
+        for (int t = 0; t < T; ++t) {
+            sz[DTO_SEG_G][t] = s->nx[t] + s->nu[t];
+            sz[DTO_SEG_CDYN][t] = dyn[t] ? dyn[t]->n_out : 0;
+            sz[DTO_SEG_CSTAGE][t] = stage[t] ? stage[t]->n_out : 0;
+            sz[DTO_SEG_JDYN][t] = dyn[t] ? dyn[t]->nnz_jac : 0;
+            sz[DTO_SEG_JSTAGE][t] = stage[t] ? stage[t]->nnz_jac : 0;
+            sz[DTO_SEG_HTERM][t] = hterm_cost[t] + hterm_dyn[t] + hterm_stage[t];
+        }
+        for (int k = 0; k < 6; ++k) {
+            s->seg_cap[k] = cyclic_window_max(sz[k], 32);
+            s->seg_pad[k] = 0;
+        }
+        if (m->vt->hess_halo) {
+            s->seg_pad[DTO_SEG_JDYN] = *std::max_element(sz[DTO_SEG_JDYN].begin(), sz[DTO_SEG_JDYN].end());
+            s->seg_pad[DTO_SEG_HTERM] = *std::max_element(sz[DTO_SEG_HTERM].begin(), sz[DTO_SEG_HTERM].end());
+        }
+    }
+    guard.s = nullptr;
+    *out = s;
+    return DTO_OK;
+}
+
+extern "C" void dto_shape_destroy(dto_shape* s) { delete s; }
+extern "C" int64_t dto_num_variables(const dto_shape* s) { return s ? s->N_z : -1; }
+extern "C" int64_t dto_num_constraint(const dto_shape* s) { return s ? s->N_c : -1; }
+extern "C" int64_t dto_num_jacobian(const dto_shape* s) { return s ? s->nnz_J : -1; }
+extern "C" int64_t dto_num_hessian(const dto_shape* s) { return s ? s->nnz_H : -1; }
+extern "C" int64_t dto_num_hessian_nonunique(const dto_shape* s) { return s ? s->nnz_H_nonunique : -1; }
+extern "C" int64_t dto_num_parameter(const dto_shape* s) { return s ? s->N_w : -1; }
+extern "C" int dto_hessian_available(const dto_shape* s) { return (s && s->hessian_available) ? 1 : 0; }
+
+extern "C" int dto_jacobian_structure(const dto_shape* s, int64_t* rows, int64_t* cols)
+{
+    if (!s || !rows || !cols) return fail(DTO_ERR_BAD_ARG, "dto_jacobian_structure: null argument");
+    std::copy(s->jac_row.begin(), s->jac_row.end(), rows);
+    std::copy(s->jac_col.begin(), s->jac_col.end(), cols);
+    return DTO_OK;
+}
+extern "C" int dto_hessian_lagrangian_structure(const dto_shape* s, int64_t* rows, int64_t* cols)
+{
+    if (!s || !rows || !cols) return fail(DTO_ERR_BAD_ARG, "dto_hessian_lagrangian_structure: null argument");
+    std::copy(s->hess_row.begin(), s->hess_row.end(), rows);
+    std::copy(s->hess_col.begin(), s->hess_col.end(), cols);
+    return DTO_OK;
+}
+extern "C" int dto_constraint_bounds(const dto_shape* s, double* lower, double* upper)
+{
+    if (!s || !lower || !upper) return fail(DTO_ERR_BAD_ARG, "dto_constraint_bounds: null argument");
+    std::copy(s->c_lower.begin(), s->c_lower.end(), lower);
+    std::copy(s->c_upper.begin(), s->c_upper.end(), upper);
+    return DTO_OK;
+}
+extern "C" int dto_knot_layout(const dto_shape* s, int64_t* state_start, int32_t* num_state, int64_t* action_start, int32_t* num_action)
+{
+    if (!s) return fail(DTO_ERR_BAD_ARG, "dto_knot_layout: null shape");
+    for (int t = 0; t < s->T; ++t) {
+        if (state_start) state_start[t] = s->knot[t].zofs + 1;
+        if (num_state) num_state[t] = s->nx[t];
+        if (action_start) action_start[t] = s->knot[t].zofs + s->nx[t] + 1;
+        if (num_action) num_action[t] = s->nu[t];
+    }
+    return DTO_OK;
+}
+extern "C" int64_t dto_algorithmic_bytes_per_problem(const dto_shape* s)
+{
+    return s ? 8 * (s->N_z + s->N_c + s->N_w + s->nnz_J + s->nnz_H) + 8 : -1;
+}
+
+static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* a)
+{
+    memset(a, 0, sizeof(*a));
+    a->B = sh ? sh->size : 0;
+    a->T = s->T;
+    a->N_z = (int32_t)s->N_z;
+    a->N_c = (int32_t)s->N_c;
+    a->N_w = (int32_t)s->N_w;
+    a->nnz_J = (int32_t)s->nnz_J;
+    a->nnz_H = (int32_t)s->nnz_H;
+    if (sh) {
+        a->z = sh->arr[DTO_ARRAY_Z];
+        a->lam = sh->arr[DTO_ARRAY_LAMBDA];
+        a->sigma = sh->arr[DTO_ARRAY_SIGMA];
+        a->w = sh->arr[DTO_ARRAY_W];
+        a->f = sh->arr[DTO_ARRAY_F];
+        a->g = sh->arr[DTO_ARRAY_G];
+        a->c = sh->arr[DTO_ARRAY_C];
+        a->J = sh->arr[DTO_ARRAY_J];
+        a->H = sh->arr[DTO_ARRAY_H];
+        a->knot = sh->d_knot;
+        a->hptr = sh->d_hptr;
+        a->hsrc = sh->d_hsrc;
+        for (int k = 0; k < 3; ++k) a->gen_inst[k] = sh->d_gen_inst[k];
+        a->gen_hslot = sh->d_gen_hslot;
+    }
+    a->gen_nrow = (int32_t)s->n_gen_rows;
+    a->gen_njac = (int32_t)s->n_gen_jac;
+    a->gen_nhess = (int32_t)s->gen_hslot.size();
+    a->gen_row0 = (int32_t)(s->n_dyn_rows + s->n_stage_rows);
+    a->gen_jac0 = (int32_t)(s->n_dyn_jac + s->n_stage_jac);
+    for (int k = 0; k < 6; ++k) {
+        a->seg_cap[k] = s->seg_cap[k];
+        a->seg_pad[k] = s->seg_pad[k];
+    }
+}
+
+extern "C" int64_t dto_kernel_smem_bytes(const dto_shape* s, int kernel_id)
+{
+    if (!s) return -1;
+    dto_launch_args a;
+    fill_args(s, nullptr, &a);
+    return s->model->vt->smem_bytes(kernel_id, &a);
+}
+
+// ------------------------------------------------------------------------------------------
+// batch
+// ------------------------------------------------------------------------------------------
+template <class V>
+static int upload(V** dst, const std::vector<V>& src, cudaStream_t st)
+{
+    *dst = nullptr;
+    if (src.empty()) return DTO_OK;
+    DTO_CUDA(cudaMalloc((void**)dst, src.size() * sizeof(V)));
+    DTO_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(V), cudaMemcpyHostToDevice, st));
+    return DTO_OK;
+}
+
+static int ensure_array(dto_batch* b, dto_shard& sh, int array)
+{
+    if (sh.arr[array]) return DTO_OK;
+    const int64_t n = std::max<int64_t>(1, array_width(b->shape, array) * sh.size);
+    DTO_CUDA(cudaSetDevice(sh.device));
+    DTO_CUDA(cudaMalloc((void**)&sh.arr[array], (size_t)n * sizeof(double)));
+    if (array == DTO_ARRAY_SIGMA) {
+        std::vector<double> ones((size_t)n, 1.0);
+        DTO_CUDA(cudaMemcpy(sh.arr[array], ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        DTO_CUDA(cudaMemsetAsync(sh.arr[array], 0, (size_t)n * sizeof(double), sh.stream));
+    }
+    return DTO_OK;
+}
+
+extern "C" void dto_batch_destroy(dto_batch* b)
+{
+    if (!b) return;
+    for (dto_shard& sh : b->shards) {
+        cudaSetDevice(sh.device);
+        if (sh.stream) cudaStreamSynchronize(sh.stream);
+        for (double*& p : sh.arr)
+            if (p) cudaFree(p);
+        if (sh.d_knot) cudaFree(sh.d_knot);
+        if (sh.d_hptr) cudaFree(sh.d_hptr);
+        if (sh.d_hsrc) cudaFree(sh.d_hsrc);
+        for (int32_t*& p : sh.d_gen_inst)
+            if (p) cudaFree(p);
+        if (sh.d_gen_hslot) cudaFree(sh.d_gen_hslot);
+        if (sh.stream && sh.own_stream) cudaStreamDestroy(sh.stream);
+    }
+    cudaGetLastError();
+    delete b;
+}
+
+extern "C" int dto_batch_create(dto_shape* s, int64_t B, const int* devices, int ndev, dto_batch** out)
+{
+    if (!s || !out) return fail(DTO_ERR_BAD_ARG, "dto_batch_create: null argument");
+    *out = nullptr;
+    DTO_REQUIRE(B >= 1, "dto_batch_create: B=%lld", (long long)B);
+    DTO_REQUIRE(ndev >= 0 && (ndev == 0 || devices), "dto_batch_create: bad device list");
+    int count = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            return fail(DTO_ERR_CUDA, "dto_batch_create: no CUDA device available (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        }
+    }
+    std::vector<int> devs;
+    if (ndev == 0) {
+        int cur = 0;
+        DTO_CUDA(cudaGetDevice(&cur));
+        devs.push_back(cur);
+    } else {
+        devs.assign(devices, devices + ndev);
+    }
+    for (int dv : devs) DTO_REQUIRE(dv >= 0 && dv < count, "dto_batch_create: device %d not in [0,%d)", dv, count);
+    DTO_REQUIRE(B * std::max<int64_t>(s->nnz_J, s->nnz_H) < (1ll << 40), "dto_batch_create: batch too large");
+
+    dto_batch* b = new (std::nothrow) dto_batch();
+    if (!b) return fail(DTO_ERR_OOM, "dto_batch_create: out of host memory");
+    b->shape = s;
+    b->B = B;
+    const int64_t chunk = (B + (int64_t)devs.size() - 1) / (int64_t)devs.size();
+    for (size_t i = 0; i < devs.size(); ++i) {
+        dto_shard sh;
+        sh.device = devs[i];
+        sh.begin = std::min<int64_t>(B, (int64_t)i * chunk);
+        sh.size = std::min<int64_t>(chunk, B - sh.begin);
+        b->shards.push_back(sh);
+    }
+    int rc = DTO_OK;
+    for (dto_shard& sh : b->shards) {
+        auto setup = [&]() -> int {
+            DTO_CUDA(cudaSetDevice(sh.device));
+            DTO_CUDA(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+            int r;
+            if ((r = upload(&sh.d_knot, s->knot, sh.stream))) return r;
+            if ((r = upload(&sh.d_hptr, s->hptr, sh.stream))) return r;
+            if ((r = upload(&sh.d_hsrc, s->hsrc, sh.stream))) return r;
+            for (int k = 0; k < 3; ++k)
+                if ((r = upload(&sh.d_gen_inst[k], s->gen_inst[k], sh.stream))) return r;
+            if ((r = upload(&sh.d_gen_hslot, s->gen_hslot, sh.stream))) return r;
+            // inputs are allocated eagerly, outputs on first use
+            for (int arr : {DTO_ARRAY_Z, DTO_ARRAY_LAMBDA, DTO_ARRAY_SIGMA, DTO_ARRAY_W})
+                if ((r = ensure_array(b, sh, arr))) return r;
+            DTO_CUDA(cudaStreamSynchronize(sh.stream));
+            return DTO_OK;
+        };
+        if ((rc = setup())) break;
+    }
+    if (rc) {
+        std::string msg = g_err;
+        dto_batch_destroy(b);
+        snprintf(g_err, sizeof(g_err), "%s", msg.c_str());
+        return rc;
+    }
+    *out = b;
+    return DTO_OK;
+}
+
+extern "C" int64_t dto_batch_size(const dto_batch* b) { return b ? b->B : -1; }
+extern "C" int dto_batch_num_shards(const dto_batch* b) { return b ? (int)b->shards.size() : -1; }
+extern "C" int64_t dto_shard_begin(const dto_batch* b, int shard)
+{
+    return (b && shard >= 0 && shard < (int)b->shards.size()) ? b->shards[shard].begin : -1;
+}
+extern "C" int64_t dto_shard_size(const dto_batch* b, int shard)
+{
+    return (b && shard >= 0 && shard < (int)b->shards.size()) ? b->shards[shard].size : -1;
+}
+extern "C" int dto_shard_device(const dto_batch* b, int shard)
+{
+    return (b && shard >= 0 && shard < (int)b->shards.size()) ? b->shards[shard].device : -1;
+}
+
+static int sync_all(dto_batch* b)
+{
+    for (dto_shard& sh : b->shards) {
+        DTO_CUDA(cudaSetDevice(sh.device));
+        DTO_CUDA(cudaStreamSynchronize(sh.stream));
+    }
+    return DTO_OK;
+}
+
+static int h2d(dto_batch* b, int array, const double* host)
+{
+    const int64_t wdt = array_width(b->shape, array);
+    if (wdt == 0) return DTO_OK;
+    if (!host) return fail(DTO_ERR_BAD_ARG, "null host pointer for input array %d", array);
+    for (dto_shard& sh : b->shards) {
+        if (sh.size == 0) continue;
+        int r;
+        if ((r = ensure_array(b, sh, array))) return r;
+        DTO_CUDA(cudaSetDevice(sh.device));
+        DTO_CUDA(cudaMemcpyAsync(sh.arr[array], host + sh.begin * wdt, (size_t)(sh.size * wdt) * sizeof(double), cudaMemcpyHostToDevice,
+                                 sh.stream));
+    }
+    return DTO_OK;
+}
+
+static int d2h(dto_batch* b, int array, double* host)
+{
+    const int64_t wdt = array_width(b->shape, array);
+    if (wdt == 0 || !host) return DTO_OK;
+    for (dto_shard& sh : b->shards) {
+        if (sh.size == 0) continue;
+        DTO_CUDA(cudaSetDevice(sh.device));
+        DTO_CUDA(cudaMemcpyAsync(host + sh.begin * wdt, sh.arr[array], (size_t)(sh.size * wdt) * sizeof(double), cudaMemcpyDeviceToHost,
+                                 sh.stream));
+    }
+    return DTO_OK;
+}
+
+extern "C" int dto_set_parameters(dto_batch* b, const double* w)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_set_parameters: null batch");
+    int r;
+    if ((r = h2d(b, DTO_ARRAY_W, w))) return r;
+    return sync_all(b);
+}
+extern "C" int dto_set_x(dto_batch* b, const double* z)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_set_x: null batch");
+    int r;
+    if ((r = h2d(b, DTO_ARRAY_Z, z))) return r;
+    if ((r = sync_all(b))) return r;
+    b->have_x = true;
+    return DTO_OK;
+}
+extern "C" int dto_set_duals(dto_batch* b, const double* sigma, const double* lambda)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_set_duals: null batch");
+    int r;
+    if ((r = h2d(b, DTO_ARRAY_SIGMA, sigma))) return r;
+    if ((r = h2d(b, DTO_ARRAY_LAMBDA, lambda))) return r;
+    if ((r = sync_all(b))) return r;
+    b->have_duals = true;
+    return DTO_OK;
+}
+
+static int launch_all(dto_batch* b, int kernel_id)
+{
+    const dto_shape* s = b->shape;
+    if (kernel_id < 0 || kernel_id >= DTO_K_COUNT) return fail(DTO_ERR_BAD_ARG, "dto_launch: kernel id %d", kernel_id);
+    if (!b->have_x) return fail(DTO_ERR_STATE, "evaluation requested before dto_set_x");
+    const bool hess = kernel_id == DTO_K_HESSIAN || kernel_id == DTO_K_JAC_HESS;
+    if (hess && !s->hessian_available)
+        return fail(DTO_ERR_NO_HESSIAN, "Hessian requested but a Cost was built without evaluate_hessian (reference throws at src/costs.jl:68)");
+    if (hess && !b->have_duals) return fail(DTO_ERR_STATE, "Hessian requested before dto_set_duals");
+    for (dto_shard& sh : b->shards) {
+        if (sh.size == 0) continue;
+        int r;
+        std::vector<int> outs;
+        switch (kernel_id) {
+        case DTO_K_OBJECTIVE: outs = {DTO_ARRAY_F}; break;
+        case DTO_K_GRADIENT: outs = {DTO_ARRAY_G}; break;
+        case DTO_K_CONSTRAINT: outs = {DTO_ARRAY_C}; break;
+        case DTO_K_JACOBIAN: outs = {DTO_ARRAY_J}; break;
+        case DTO_K_HESSIAN: outs = {DTO_ARRAY_H}; break;
+        default: outs = {DTO_ARRAY_J, DTO_ARRAY_H}; break;
+        }
+        for (int o : outs)
+            if ((r = ensure_array(b, sh, o))) return r;
+        DTO_CUDA(cudaSetDevice(sh.device));
+        dto_launch_args a;
+        fill_args(s, &sh, &a);
+        const int e = s->model->vt->launch(kernel_id, &a, (void*)sh.stream);
+        if (e != 0) return fail(DTO_ERR_CUDA, "kernel launch (id %d) failed: %s", kernel_id, cudaGetErrorString((cudaError_t)e));
+        int64_t n = 1;
+        if (kernel_id == DTO_K_CONSTRAINT) n += a.gen_nrow > 0;
+        if (kernel_id == DTO_K_JACOBIAN || kernel_id == DTO_K_JAC_HESS) n += a.gen_njac > 0;
+        if (kernel_id == DTO_K_HESSIAN || kernel_id == DTO_K_JAC_HESS) n += a.gen_nhess > 0;
+        b->launches += n;
+    }
+    return DTO_OK;
+}
+
+static int eval_to_host(dto_batch* b, int kernel_id, int array, double* host)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "null batch");
+    if (!host && array_width(b->shape, array) > 0) return fail(DTO_ERR_BAD_ARG, "null output pointer");
+    int r;
+    if ((r = launch_all(b, kernel_id))) return r;
+    if ((r = d2h(b, array, host))) return r;
+    return sync_all(b);
+}
+
+extern "C" int dto_eval_objective(dto_batch* b, double* f) { return eval_to_host(b, DTO_K_OBJECTIVE, DTO_ARRAY_F, f); }
+extern "C" int dto_eval_objective_gradient(dto_batch* b, double* g) { return eval_to_host(b, DTO_K_GRADIENT, DTO_ARRAY_G, g); }
+extern "C" int dto_eval_constraint(dto_batch* b, double* c) { return eval_to_host(b, DTO_K_CONSTRAINT, DTO_ARRAY_C, c); }
+extern "C" int dto_eval_constraint_jacobian(dto_batch* b, double* J) { return eval_to_host(b, DTO_K_JACOBIAN, DTO_ARRAY_J, J); }
+extern "C" int dto_eval_hessian_lagrangian(dto_batch* b, double* H) { return eval_to_host(b, DTO_K_HESSIAN, DTO_ARRAY_H, H); }
+extern "C" int dto_eval_jacobian_hessian(dto_batch* b, double* J, double* H)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_eval_jacobian_hessian: null batch");
+    int r;
+    if ((r = launch_all(b, DTO_K_JAC_HESS))) return r;
+    if ((r = d2h(b, DTO_ARRAY_J, J))) return r;
+    if ((r = d2h(b, DTO_ARRAY_H, H))) return r;
+    return sync_all(b);
+}
+
+extern "C" int dto_get_problem(dto_batch* b, int array, int64_t problem, double* out)
+{
+    if (!b || !out) return fail(DTO_ERR_BAD_ARG, "dto_get_problem: null argument");
+    const int64_t wdt = array_width(b->shape, array);
+    DTO_REQUIRE(wdt >= 0, "dto_get_problem: array id %d", array);
+    DTO_REQUIRE(problem >= 0 && problem < b->B, "dto_get_problem: problem %lld not in [0,%lld)", (long long)problem, (long long)b->B);
+    if (wdt == 0) return DTO_OK;
+    for (dto_shard& sh : b->shards) {
+        if (problem < sh.begin || problem >= sh.begin + sh.size) continue;
+        if (!sh.arr[array]) return fail(DTO_ERR_STATE, "dto_get_problem: array %d has not been computed yet", array);
+        DTO_CUDA(cudaSetDevice(sh.device));
+        DTO_CUDA(cudaMemcpyAsync(out, sh.arr[array] + (problem - sh.begin) * wdt, (size_t)wdt * sizeof(double), cudaMemcpyDeviceToHost,
+                                 sh.stream));
+        DTO_CUDA(cudaStreamSynchronize(sh.stream));
+        return DTO_OK;
+    }
+    return fail(DTO_ERR_STATE, "dto_get_problem: problem not found in any shard");
+}
+
+extern "C" int dto_get_last_x(const dto_batch* b, int64_t problem, double* z)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_get_last_x: null batch");
+    if (!b->have_x) return fail(DTO_ERR_STATE, "dto_get_last_x: no z has been set");
+    return dto_get_problem(const_cast<dto_batch*>(b), DTO_ARRAY_Z, problem, z);
+}
+
+extern "C" void* dto_device_pointer(dto_batch* b, int array, int shard)
+{
+    if (!b || shard < 0 || shard >= (int)b->shards.size() || array < 0 || array > DTO_ARRAY_H) {
+        fail(DTO_ERR_BAD_ARG, "dto_device_pointer: bad argument");
+        return nullptr;
+    }
+    if (ensure_array(b, b->shards[shard], array)) return nullptr;
+    if (array == DTO_ARRAY_Z) b->have_x = true;  // caller writes the inputs on the device
+    if (array == DTO_ARRAY_LAMBDA || array == DTO_ARRAY_SIGMA) b->have_duals = true;
+    return b->shards[shard].arr[array];
+}
+extern "C" void* dto_get_stream(dto_batch* b, int shard)
+{
+    return (b && shard >= 0 && shard < (int)b->shards.size()) ? (void*)b->shards[shard].stream : nullptr;
+}
+extern "C" int dto_set_stream(dto_batch* b, int shard, void* cuda_stream)
+{
+    if (!b || shard < 0 || shard >= (int)b->shards.size()) return fail(DTO_ERR_BAD_ARG, "dto_set_stream: bad argument");
+    dto_shard& sh = b->shards[shard];
+    DTO_CUDA(cudaSetDevice(sh.device));
+    DTO_CUDA(cudaStreamSynchronize(sh.stream));
+    if (sh.own_stream && sh.stream) cudaStreamDestroy(sh.stream);
+    sh.stream = (cudaStream_t)cuda_stream;
+    sh.own_stream = false;
+    return DTO_OK;
+}
+extern "C" int dto_launch(dto_batch* b, int kernel_id)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_launch: null batch");
+    return launch_all(b, kernel_id);
+}
+extern "C" int dto_sync(dto_batch* b)
+{
+    if (!b) return fail(DTO_ERR_BAD_ARG, "dto_sync: null batch");
+    return sync_all(b);
+}
+extern "C" int64_t dto_launch_count(const dto_batch* b) { return b ? b->launches : -1; }

