@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- knot-point Jacobian+Hessian evaluations per second (FP64), BASELINE.json metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE configs[1] -- cartpole swing-up, T=101, B=4096 problems PER
+GPU (weak scaling: each rank owns its own contiguous shard of the global batch, no collective on
+the data path), callback evaluation only. One step = one fused Jacobian + Hessian-of-Lagrangian
+pass over the rank's batch.
+
+  value     evals/s with (z, lambda, sigma, w) resident in HBM; timed on the device with CUDA
+            events on the launching stream, max over ranks, 3 rotating input/output sets
+            (387 MB > 126 MB L2) so no step finds its data in L2.
+  e2e       the same metric through the public host API (pinned host buffers -> set_x/set_duals ->
+            eval_jacobian_hessian -> host J/H), copies inside the timed region.
+  roofline  algorithmic bytes (8(N_z+N_c+N_w+nnz_J+nnz_H)+8 per problem) / kernel time vs the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json); plus an FP64-pipe estimate.
+  cpu_baseline  the oracle's C twin (no-CSE, "what Symbolics 0.1.x emits") on the host cores.
+
+--impl reference times that C twin itself (the reference needs Julia + Ipopt, absent here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "knot-point Jac+Hessian evals/sec (FP64)"
+UNIT = "knot-evals/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _fp64_peak():
+    p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["dfma_per_s"])
+    return 16.7e12
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw),
+                "window": "timed region + identical untimed continuation (>=1 s under load)"}
+
+
+def build_c_baseline(T: int, verbose=False):
+    from examples import models as M
+    from oracle import api as O, cgen
+    mo = M.build_cartpole(O, T=T, evaluate_hessian=True, parameterized=True)
+    osolver = O.solver_from(mo, parameters=[np.zeros(8) for _ in range(T)] + [np.zeros(0)])
+    return cgen.build_c_oracle(osolver, f"cartpole{T}", shared_parameters=True, cse=False, verbose=verbose), mo
+
+
+def time_cpu(co, z, lam, sigma, w, threads: int, budget_s: float = 12.0):
+    """Jac+Hess on a bounded sample sized for ~budget_s of wall time; returns (evals/s, sample B)."""
+    T = co.T
+    probe = min(z.shape[0], max(threads, 8))
+    t = time.time()
+    co.eval(8 | 16, z[:probe], lam[:probe], sigma[:probe], w[:probe], threads)
+    dt = max(time.time() - t, 1e-6)
+    Bs = int(min(z.shape[0], max(probe, probe * budget_s / dt)))
+    t = time.time()
+    co.eval(8 | 16, z[:Bs], lam[:Bs], sigma[:Bs], w[:Bs], threads)
+    dt = time.time() - t
+    return Bs * T / dt, Bs, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from util import make_inputs
+    co, mo = build_c_baseline(args.T)
+    threads = co.max_threads()
+    Bs = args.ref_sample
+    z, lam, sigma, w = make_inputs("cartpole", mo, co.NZ, co.NC, co.NW, Bs, config=2, shard=0)
+    what = 8 | 16
+    for _ in range(args.warmup):
+        co.eval(what, z, lam, sigma, w, threads)
+    t0 = time.time()
+    for _ in range(args.steps):
+        co.eval(what, z, lam, sigma, w, threads)
+    dt = time.time() - t0
+    value = Bs * args.T * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cartpole swing-up T={args.T}, B={args.batch} per GPU, fused Jacobian+Hessian callbacks",
+                   "note": "the Julia reference cannot run here (no Julia/Ipopt); this arm times the oracle's C twin of the "
+                           "reference callbacks (no-CSE element code, reference loop structure) on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{Bs} problems x T={args.T} per step (of B={args.batch}), gcc -O2 -fopenmp, no-CSE element code"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import dto_b200 as D
+    from dto_b200.evaluator import A_H, A_J, A_LAMBDA, A_SIGMA, A_W, A_Z, K_JAC_HESS
+    from examples import models as M
+    from util import make_inputs
+
+    B, T = args.batch, args.T
+    model = M.build_cartpole(D, T=T, evaluate_hessian=True, parameterized=True)
+    solver = D.solver_from(model, batch=B, devices=[local])
+    nlp0 = solver.nlp
+    R = 3  # rotating input/output sets: 3 x 129 MB > 126 MB L2
+    nlps = [nlp0] + [nlp0.new_batch() for _ in range(R - 1)]
+    stream = torch.cuda.Stream()
+    host = []
+    for i, n in enumerate(nlps):
+        z, lam, sigma, w = make_inputs("cartpole", model, n.num_variables, n.num_constraint, n.num_parameter, B, config=2,
+                                       shard=rank * R + i)
+        n.set_parameters(w)
+        n.set_x(z)
+        n.set_duals(sigma, lam)
+        n.set_stream(stream.cuda_stream)
+        host.append((z, lam, sigma, w))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for i in range(max(args.warmup, 3)):
+            nlps[i % R].launch(K_JAC_HESS)
+        barrier()
+        n0 = sum(n.launch_count() for n in nlps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start = time.time()
+        e0.record(stream)
+        for i in range(args.steps):
+            nlps[i % R].launch(K_JAC_HESS)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        n1 = sum(n.launch_count() for n in nlps)
+        # identical untimed continuation so the clock sampler sees >= 1 s under the same load
+        t_busy = time.time()
+        while time.time() - t_busy < 1.0:
+            for i in range(50):
+                nlps[i % R].launch(K_JAC_HESS)
+            torch.cuda.synchronize()
+        t_end = time.time()
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = world * B * T / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public host API, pinned host buffers
+    n = nlps[0]
+    z, lam, sigma, w = host[0]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    zp, lp, sp_ = pin(z), pin(lam), pin(sigma)
+    Jp = torch.empty((B, n.num_jacobian), dtype=torch.float64).pin_memory().numpy()
+    Hp = torch.empty((B, n.num_hessian), dtype=torch.float64).pin_memory().numpy()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        n.eval_jacobian_hessian(Jp, Hp, zp, sp_, lp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        n.eval_jacobian_hessian(Jp, Hp, zp, sp_, lp)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tdt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+    dt = float(tdt.item())
+    e2e_value = world * B * T * e2e_steps / dt
+    h2d = 8 * B * (n.num_variables + n.num_constraint + 1)
+    d2h = 8 * B * (n.num_jacobian + n.num_hessian)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = _peaks()
+        bytes_per_launch = n.algorithmic_bytes_per_problem() * B
+        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        ops = None
+        try:
+            ops = int(open(n.model.path.replace(".so", ".log")).read().split("'ops_fused_per_knot': ")[1].split("}")[0].split(",")[0])
+        except Exception:  # noqa: BLE001
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"cartpole swing-up T={T}, B={B} per GPU, fused Jacobian+Hessian callbacks",
+                       "l2": f"{R} rotating input/output sets ({R * bytes_per_launch / 1e6:.0f} MB) > 126 MB L2",
+                       "parallelism": f"{world} independent shards, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps},
+            "gpu_launches": int(n1 - n0),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch},
+        }
+        if ops:
+            fp = _fp64_peak()
+            line["fp64"] = {"codegen_ops_per_knot": ops, "achieved_gops": ops * B * T / (ms_per_step * 1e-3) / 1e9,
+                            "peak_gdfma": fp / 1e9, "note": "cartpole RK3 is FP64-pipe bound (SURVEY 8d); ops = sympy count_ops"}
+        if world == 1 and not args.no_cpu:
+            co, mo = build_c_baseline(T)
+            threads = co.max_threads()
+            v, Bs, dtc = time_cpu(co, z, lam, sigma, w, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{Bs} of {B} problems x T={T}, {dtc:.1f} s, oracle C twin (no-CSE element code, "
+                                              "reference loop structure), gcc -O2 -fopenmp"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--T", type=int, default=101)
+    ap.add_argument("--ref-sample", type=int, default=256, dest="ref_sample")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200:
+            args.steps = 5
+        if args.warmup == 10:
+            args.warmup = 1
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -254,6 +254,41 @@ class BatchedNLPData:
             self.set_duals(1.0 if scaling is None else scaling, duals)
         _lib.check(_lib.lib().dto_eval_jacobian_hessian(self.handle, _p(J), _p(H)))
 
+    # ---- device-resident interface (no host copies)
+    def new_batch(self, batch: Optional[int] = None, devices: Optional[Sequence[int]] = None) -> "BatchedNLPData":
+        """Another batch of the same shape (shares the model library and static tables)."""
+        other = object.__new__(BatchedNLPData)
+        other.__dict__.update(self.__dict__)
+        other._batch = None
+        other.batch = int(batch) if batch is not None else self.batch
+        other.devices = list(devices) if devices is not None else self.devices
+        return other
+
+    def launch(self, kernel_id: int) -> None:
+        """Enqueue one callback on the batch's stream(s) without synchronising."""
+        _lib.check(_lib.lib().dto_launch(self.handle, kernel_id))
+
+    def sync(self) -> None:
+        _lib.check(_lib.lib().dto_sync(self.handle))
+
+    def set_stream(self, cuda_stream: int, shard: int = 0) -> None:
+        _lib.check(_lib.lib().dto_set_stream(self.handle, shard, C.c_void_p(cuda_stream)))
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().dto_launch_count(self.handle))
+
+    def device_pointer(self, array: int, shard: int = 0) -> int:
+        p = _lib.lib().dto_device_pointer(self.handle, array, shard)
+        if not p:
+            raise _lib.DtoError(-1, _lib.lib().dto_last_error().decode(errors="replace"))
+        return int(p)
+
+    def algorithmic_bytes_per_problem(self) -> int:
+        return int(_lib.lib().dto_algorithmic_bytes_per_problem(self.shape))
+
+    def kernel_smem_bytes(self, kernel_id: int) -> int:
+        return int(_lib.lib().dto_kernel_smem_bytes(self.shape, kernel_id))
+
     def last_x(self, problem: int = 0) -> np.ndarray:
         z = np.empty(self.num_variables)
         _lib.check(_lib.lib().dto_get_last_x(self.handle, problem, _p(z)))
