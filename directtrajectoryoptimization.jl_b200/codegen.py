@@ -32,6 +32,18 @@ NVCC = os.environ.get("DTO_NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
+def _tuning() -> Dict[str, int]:
+    """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
+    resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
+    Override with DTO_TUNE="warps=4,min_ctas=3"."""
+    t = {"warps": 4, "min_ctas": 1}
+    for kv in os.environ.get("DTO_TUNE", "").split(","):
+        if "=" in kv:
+            k, v = kv.split("=")
+            t[k.strip()] = int(v)
+    return t
+
+
 # ----------------------------------------------------------------------------- specs
 @dataclass
 class ElementSpec:
@@ -435,6 +447,7 @@ extern "C" __attribute__((visibility("default"))) const dto_model_vtable* dto_mo
 def spec_hash(spec: ModelSpec) -> str:
     h = hashlib.sha256()
     h.update(CODEGEN_VERSION.encode())
+    h.update(repr(sorted(_tuning().items())).encode())
     for fname in ("dto_kernels.cuh", "dto_model_abi.h"):
         with open(os.path.join(CSRC_DIR, fname), "rb") as f:
             h.update(f.read())
@@ -472,7 +485,8 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
         f.write(src)
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}: the CUDA model library cannot be built (no CPU fallback exists)")
-    cmd = [NVCC, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+    tune = _tuning()
+    cmd = [NVCC, *NVCC_ARCH, f"-DDTO_WARPS={tune['warps']}", f"-DDTO_MIN_CTAS={tune['min_ctas']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
            "-I", CSRC_DIR, "-o", so + ".tmp", cu]
     t1 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -29,6 +29,9 @@
 #ifndef DTO_WARPS
 #define DTO_WARPS 4
 #endif
+#ifndef DTO_MIN_CTAS
+#define DTO_MIN_CTAS 1
+#endif
 
 #define DTO_MODE_G 1
 #define DTO_MODE_C 2
@@ -81,7 +84,7 @@ __host__ __device__ inline int smem_doubles_per_warp(const dto_launch_args& a, i
 // per-knot kernel: gradient / residuals / Jacobian / Hessian / fused Jacobian+Hessian
 // ---------------------------------------------------------------------------------------
 template <class M, int MODE>
-__global__ void __launch_bounds__(DTO_WARPS * 32) knot_kernel(const __grid_constant__ dto_launch_args a)
+__global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(const __grid_constant__ dto_launch_args a)
 {
     extern __shared__ __align__(16) double dto_smem[];
     constexpr bool DO_G = (MODE & DTO_MODE_G) != 0, DO_C = (MODE & DTO_MODE_C) != 0;
@@ -183,11 +186,28 @@ __global__ void __launch_bounds__(DTO_WARPS * 32) knot_kernel(const __grid_const
             if (DO_H) {
                 const double* __restrict__ smh = sm + base[DTO_SEG_HTERM] + db * L_h - k0.hterm;
                 double* __restrict__ Hb = a.H + (size_t)b * a.nnz_H;
-                for (int s = ea.hslot + lane; s < eb.hslot; s += 32) {
-                    const int p0 = __ldg(a.hptr + s), p1 = __ldg(a.hptr + s + 1);
-                    double acc = 0.0;
-                    for (int p = p0; p < p1; ++p) acc += smh[__ldg(a.hsrc + p)];
-                    Hb[s] = acc;
+                const int4* __restrict__ src4 = reinterpret_cast<const int4*>(a.hsrc4);
+                int s = ea.hslot + lane;
+                // two slots per lane per trip: both table records are in flight before any use
+                for (; s + 32 < eb.hslot; s += 64) {
+                    const int4 q0 = __ldg(src4 + s), q1 = __ldg(src4 + s + 32);
+                    double a0 = q0.x >= 0 ? smh[q0.x] : 0.0, a1 = q1.x >= 0 ? smh[q1.x] : 0.0;
+                    if (q0.y >= 0) a0 += smh[q0.y];
+                    if (q1.y >= 0) a1 += smh[q1.y];
+                    if (q0.z >= 0) a0 += smh[q0.z];
+                    if (q1.z >= 0) a1 += smh[q1.z];
+                    if (q0.w >= 0) a0 += smh[q0.w];
+                    if (q1.w >= 0) a1 += smh[q1.w];
+                    Hb[s] = a0;
+                    Hb[s + 32] = a1;
+                }
+                if (s < eb.hslot) {
+                    const int4 q0 = __ldg(src4 + s);
+                    double a0 = q0.x >= 0 ? smh[q0.x] : 0.0;
+                    if (q0.y >= 0) a0 += smh[q0.y];
+                    if (q0.z >= 0) a0 += smh[q0.z];
+                    if (q0.w >= 0) a0 += smh[q0.w];
+                    Hb[s] = a0;
                 }
             }
             rem -= cnt;

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 3
+#define DTO_MODEL_ABI_VERSION 4
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -101,8 +101,10 @@ typedef struct dto_launch_args {
     double* J;            /* [B][nnz_J] */
     double* H;            /* [B][nnz_H] */
     const dto_knot_entry* knot; /* [T+1] */
-    const int32_t* hptr;  /* [nnz_H+1] CSR over Hessian slots -> contributing terms   */
-    const int32_t* hsrc;  /* [hptr[nnz_H]] term ids in the reference's += order (Q5)  */
+    /* [nnz_H][4] per Hessian slot: the (at most four: cost_t, dynamics_{t-1}, dynamics_t, stage_t)
+     * contributing term ids in the reference's += order (Q5), -1 = none. One 16-byte record per
+     * slot: the gather issues a single coalesced, independent load per output value. */
+    const int32_t* hsrc4;
     /* general constraint (device copies of the instance tables + output placement) */
     int32_t gen_nrow, gen_njac, gen_nhess;
     int32_t gen_row0;     /* first general row in c / lambda        */

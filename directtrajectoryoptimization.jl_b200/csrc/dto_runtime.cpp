@@ -78,6 +78,7 @@ struct dto_shape {
     std::vector<int64_t> jac_row, jac_col;       // 1-based
     std::vector<int64_t> hess_row, hess_col;     // 1-based, sorted unique
     std::vector<int32_t> hptr, hsrc;             // CSR slot -> term ids (knot elements only)
+    std::vector<int32_t> hsrc4;                  // [nnz_H][4] packed, -1 padded; slot with no knot term: zero term
     std::vector<int32_t> gen_inst[3];            // [n][4]
     std::vector<int32_t> gen_hslot;
     std::vector<double> c_lower, c_upper;
@@ -92,8 +93,7 @@ struct dto_shard {
     bool own_stream = true;
     double* arr[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     dto_knot_entry* d_knot = nullptr;
-    int32_t* d_hptr = nullptr;
-    int32_t* d_hsrc = nullptr;
+    int32_t* d_hsrc4 = nullptr;
     int32_t* d_gen_inst[3] = {nullptr, nullptr, nullptr};
     int32_t* d_gen_hslot = nullptr;
 };
@@ -484,6 +484,13 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
                                 "element reaches beyond its [x;u;y] window", sl, (long long)s->hess_row[sl], t - 1, t);
             }
     }
+    // packed gather table: <= 4 contributors per slot (cost_t, dynamics_{t-1}, dynamics_t, stage_t)
+    s->hsrc4.assign((size_t)s->nnz_H * 4, -1);
+    for (int64_t sl = 0; sl < s->nnz_H; ++sl) {
+        const int32_t n = s->hptr[sl + 1] - s->hptr[sl];
+        DTO_REQUIRE(n <= 4, "dto_shape_create: Hessian slot %lld has %d knot contributors (max 4)", (long long)sl, n);
+        for (int32_t k = 0; k < n; ++k) s->hsrc4[4 * sl + k] = s->hsrc[s->hptr[sl] + k];
+    }
     s->gen_hslot.resize(gen_terms.size());
     for (size_t i = 0; i < gen_terms.size(); ++i) s->gen_hslot[i] = slot_of(gen_terms[i].row, gen_terms[i].col);
     if (gen) {
@@ -592,8 +599,7 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
         a->J = sh->arr[DTO_ARRAY_J];
         a->H = sh->arr[DTO_ARRAY_H];
         a->knot = sh->d_knot;
-        a->hptr = sh->d_hptr;
-        a->hsrc = sh->d_hsrc;
+        a->hsrc4 = sh->d_hsrc4;
         for (int k = 0; k < 3; ++k) a->gen_inst[k] = sh->d_gen_inst[k];
         a->gen_hslot = sh->d_gen_hslot;
     }
@@ -653,8 +659,7 @@ extern "C" void dto_batch_destroy(dto_batch* b)
         for (double*& p : sh.arr)
             if (p) cudaFree(p);
         if (sh.d_knot) cudaFree(sh.d_knot);
-        if (sh.d_hptr) cudaFree(sh.d_hptr);
-        if (sh.d_hsrc) cudaFree(sh.d_hsrc);
+        if (sh.d_hsrc4) cudaFree(sh.d_hsrc4);
         for (int32_t*& p : sh.d_gen_inst)
             if (p) cudaFree(p);
         if (sh.d_gen_hslot) cudaFree(sh.d_gen_hslot);
@@ -709,8 +714,7 @@ extern "C" int dto_batch_create(dto_shape* s, int64_t B, const int* devices, int
             DTO_CUDA(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
             int r;
             if ((r = upload(&sh.d_knot, s->knot, sh.stream))) return r;
-            if ((r = upload(&sh.d_hptr, s->hptr, sh.stream))) return r;
-            if ((r = upload(&sh.d_hsrc, s->hsrc, sh.stream))) return r;
+            if ((r = upload(&sh.d_hsrc4, s->hsrc4, sh.stream))) return r;
             for (int k = 0; k < 3; ++k)
                 if ((r = upload(&sh.d_gen_inst[k], s->gen_inst[k], sh.stream))) return r;
             if ((r = upload(&sh.d_gen_hslot, s->gen_hslot, sh.stream))) return r;

@@ -1,0 +1,508 @@
+"""Expression DAG + derivative synthesis for the code generator.
+
+Why this exists: the reference differentiates every output symbolically and `eval`s one
+un-shared expression per nonzero (/root/reference/src/dynamics.jl:25-34). For cartpole-RK3
+that is ~15 k (Jacobian) + ~138 k (Hessian) operations per knot; tree-level CSE of those
+expanded expressions still leaves ~2 k FP64 instructions and ~600 live temporaries (register
+spills on the GPU). The chain-rule structure is lost by expansion, so the code generator
+does NOT lower the expanded derivatives. It converts the traced RESIDUAL (a ~150-node DAG
+that still has the RK-stage nesting) into a hash-consed DAG and synthesises the first and
+second derivatives on that DAG by sparse second-order forward propagation: every node
+carries a sparse gradient {var: node} and a sparse symmetric Hessian {(v,w): node}; all
+derivative nodes are hash-consed, so equal sub-derivatives (e.g. d/dx_i and d/dy_i through a
+midpoint 0.5(x+y)) are computed once. The values are the same mathematical functions the
+reference evaluates (parity is checked against the oracle at 1e-12).
+
+Node algebra is deliberately small: const, in, add, mul, neg, rcp, powi, unary functions.
+Negations and numeric factors are floated outward so that +/- and scaled variants share nodes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import sympy as sp
+
+UNARY = ("sin", "cos", "tan", "exp", "log", "sqrt", "atan", "sinh", "cosh", "tanh")
+
+
+class Graph:
+    def __init__(self):
+        self.op: List[str] = []
+        self.args: List[tuple] = []
+        self.val: List[object] = []
+        self._memo: Dict[tuple, int] = {}
+        self.ZERO = self.const(0.0)
+        self.ONE = self.const(1.0)
+
+    # ---- raw node creation
+    def _mk(self, op: str, args: tuple = (), val=None) -> int:
+        key = (op, args, val)
+        i = self._memo.get(key)
+        if i is None:
+            i = len(self.op)
+            self.op.append(op)
+            self.args.append(args)
+            self.val.append(val)
+            self._memo[key] = i
+        return i
+
+    def const(self, v: float) -> int:
+        v = float(v)
+        if v == 0.0:
+            v = 0.0  # fold -0.0
+        return self._mk("const", (), v)
+
+    def inp(self, name: str, idx: int) -> int:
+        return self._mk("in", (), (name, idx))
+
+    def is_const(self, a: int) -> bool:
+        return self.op[a] == "const"
+
+    def cval(self, a: int) -> float:
+        return self.val[a]
+
+    # ---- (coefficient, core) view: a = c * core with core free of numeric factor / negation
+    def split(self, a: int) -> Tuple[float, int]:
+        op = self.op[a]
+        if op == "const":
+            return self.val[a], self.ONE
+        if op == "neg":
+            c, x = self.split(self.args[a][0])
+            return -c, x
+        if op == "mul" and self.op[self.args[a][0]] == "const":
+            c, x = self.split(self.args[a][1])
+            return self.val[self.args[a][0]] * c, x
+        return 1.0, a
+
+    def scale(self, c: float, x: int) -> int:
+        """c * x with x a core (non-const, no leading factor)."""
+        if c == 0.0 or (self.is_const(x) and self.val[x] == 0.0):
+            return self.ZERO
+        if self.is_const(x):
+            return self.const(c * self.val[x])
+        if c == 1.0:
+            return x
+        if c == -1.0:
+            return self._mk("neg", (x,))
+        if c < 0:
+            return self._mk("neg", (self._mk("mul", (self.const(-c), x)),))
+        return self._mk("mul", (self.const(c), x))
+
+    # ---- smart constructors
+    def neg(self, a: int) -> int:
+        c, x = self.split(a)
+        return self.scale(-c, x)
+
+    def add(self, a: int, b: int) -> int:
+        if self.is_const(a) and self.is_const(b):
+            return self.const(self.val[a] + self.val[b])
+        if self.is_const(a) and self.val[a] == 0.0:
+            return b
+        if self.is_const(b) and self.val[b] == 0.0:
+            return a
+        ca, xa = self.split(a)
+        cb, xb = self.split(b)
+        if xa == xb and not self.is_const(a) and not self.is_const(b):
+            return self.scale(ca + cb, xa)  # c1*x + c2*x
+        # float a common negation outward: (-p) + (-q) = -(p + q)
+        if ca < 0 and cb < 0 and not self.is_const(a) and not self.is_const(b):
+            return self.neg(self.add(self.neg(a), self.neg(b)))
+        if a > b:
+            a, b = b, a
+        return self._mk("add", (a, b))
+
+    def sub(self, a: int, b: int) -> int:
+        return self.add(a, self.neg(b))
+
+    def mul(self, a: int, b: int) -> int:
+        ca, xa = self.split(a)
+        cb, xb = self.split(b)
+        c = ca * cb
+        if c == 0.0:
+            return self.ZERO
+        if xa == self.ONE:
+            return self.scale(c, xb) if xb != self.ONE else self.const(c)
+        if xb == self.ONE:
+            return self.scale(c, xa)
+        if xa == xb:
+            core = self.powi(xa, 2)
+        else:
+            # x * x^k -> x^(k+1)
+            if self.op[xb] == "powi" and self.args[xb][0] == xa:
+                core = self.powi(xa, self.val[xb] + 1)
+            elif self.op[xa] == "powi" and self.args[xa][0] == xb:
+                core = self.powi(xb, self.val[xa] + 1)
+            else:
+                if xa > xb:
+                    xa, xb = xb, xa
+                core = self._mk("mul", (xa, xb))
+        c2, core2 = self.split(core)
+        return self.scale(c * c2, core2)
+
+    def rcp(self, a: int) -> int:
+        c, x = self.split(a)
+        if x == self.ONE:
+            return self.const(1.0 / c)
+        if self.op[x] == "rcp":
+            return self.scale(1.0 / c, self.args[x][0])
+        return self.scale(1.0 / c, self._mk("rcp", (x,)))
+
+    def div(self, a: int, b: int) -> int:
+        return self.mul(a, self.rcp(b))
+
+    def powi(self, a: int, k: int) -> int:
+        k = int(k)
+        if k == 0:
+            return self.ONE
+        if k < 0:
+            return self.powi(self.rcp(a), -k)
+        if k == 1:
+            return a
+        c, x = self.split(a)
+        if x == self.ONE:
+            return self.const(c ** k)
+        if self.op[x] == "powi":
+            core = self._mk("powi", (self.args[x][0],), self.val[x] * k)
+        else:
+            core = self._mk("powi", (x,), k)
+        return self.scale(c ** k, core)
+
+    def func(self, name: str, a: int) -> int:
+        if self.is_const(a):
+            return self.const(getattr(math, name)(self.val[a]))
+        if name == "sqrt":
+            return self._mk("sqrt", (a,))
+        c, x = self.split(a)
+        if c < 0:  # parity: sin(-x) = -sin(x), cos(-x) = cos(x), tan/atan/sinh/tanh odd, cosh even
+            if name in ("sin", "tan", "atan", "sinh", "tanh"):
+                return self.neg(self._mk(name, (self.neg(a),)))
+            if name in ("cos", "cosh"):
+                return self._mk(name, (self.neg(a),))
+        return self._mk(name, (a,))
+
+    def powc(self, a: int, p: float) -> int:
+        """a ** p for a non-integer constant exponent."""
+        if p == 0.5:
+            return self.func("sqrt", a)
+        if self.is_const(a):
+            return self.const(self.val[a] ** p)
+        return self._mk("powc", (a,), float(p))
+
+    def sum(self, xs: Iterable[int]) -> int:
+        acc = self.ZERO
+        for x in xs:
+            acc = self.add(acc, x)
+        return acc
+
+    # ---- sympy -> DAG
+    def from_sympy(self, e: sp.Expr, sym: Dict[sp.Symbol, int], memo: Optional[dict] = None) -> int:
+        memo = {} if memo is None else memo
+        return self._conv(sp.sympify(e), sym, memo)
+
+    def _conv(self, e, sym, memo) -> int:
+        r = memo.get(e)
+        if r is not None:
+            return r
+        if e.is_Symbol:
+            r = sym[e]
+        elif e.is_Number or e.is_NumberSymbol:
+            r = self.const(float(e))
+        elif e.is_Add:
+            r = self.ZERO
+            for a in e.args:
+                r = self.add(r, self._conv(a, sym, memo))
+        elif e.is_Mul:
+            r = self.ONE
+            for a in e.args:
+                r = self.mul(r, self._conv(a, sym, memo))
+        elif e.is_Pow:
+            b, p = e.args
+            if p.is_Integer:
+                r = self.powi(self._conv(b, sym, memo), int(p))
+            elif p.is_Number and float(p) == int(float(p)):
+                r = self.powi(self._conv(b, sym, memo), int(float(p)))
+            elif p.is_Number:
+                r = self.powc(self._conv(b, sym, memo), float(p))
+            else:
+                # a^b = exp(b log a)
+                r = self.func("exp", self.mul(self._conv(p, sym, memo), self.func("log", self._conv(b, sym, memo))))
+        elif e.is_Function and len(e.args) == 1 and e.func.__name__ in UNARY:
+            r = self.func(e.func.__name__, self._conv(e.args[0], sym, memo))
+        else:
+            raise NotImplementedError(f"no DAG lowering for {e.func}")
+        memo[e] = r
+        return r
+
+    # ---- first/second derivative of a unary function at node c = f(a): returns (f', f'')
+    def _dfun(self, c: int) -> Tuple[int, int]:
+        op, a = self.op[c], self.args[c][0]
+        if op == "sin":
+            return self.func("cos", a), self.neg(c)
+        if op == "cos":
+            return self.neg(self.func("sin", a)), self.neg(c)
+        if op == "tan":
+            d1 = self.add(self.ONE, self.powi(c, 2))
+            return d1, self.mul(self.const(2.0), self.mul(c, d1))
+        if op == "exp":
+            return c, c
+        if op == "log":
+            r = self.rcp(a)
+            return r, self.neg(self.powi(r, 2))
+        if op == "sqrt":
+            r = self.rcp(c)
+            return self.scale(0.5, r) if self.split(r)[0] == 1.0 else self.mul(self.const(0.5), r), \
+                self.mul(self.const(-0.25), self.powi(r, 3))
+        if op == "atan":
+            r = self.rcp(self.add(self.ONE, self.powi(a, 2)))
+            return r, self.mul(self.const(-2.0), self.mul(a, self.powi(r, 2)))
+        if op == "sinh":
+            return self.func("cosh", a), c
+        if op == "cosh":
+            return self.func("sinh", a), c
+        if op == "tanh":
+            d1 = self.sub(self.ONE, self.powi(c, 2))
+            return d1, self.mul(self.const(-2.0), self.mul(c, d1))
+        if op == "rcp":
+            return self.neg(self.powi(c, 2)), self.mul(self.const(2.0), self.powi(c, 3))
+        if op == "powi":
+            k = self.val[c]
+            return self.mul(self.const(float(k)), self.powi(a, k - 1)), \
+                self.mul(self.const(float(k * (k - 1))), self.powi(a, k - 2))
+        if op == "powc":
+            p = self.val[c]
+            d1 = self.mul(self.const(p), self.powc(a, p - 1.0) if (p - 1.0) != int(p - 1.0) else self.powi(a, int(p - 1.0)))
+            p2 = p - 2.0
+            d2 = self.mul(self.const(p * (p - 1.0)), self.powc(a, p2) if p2 != int(p2) else self.powi(a, int(p2)))
+            return d1, d2
+        raise NotImplementedError(f"no derivative rule for {op}")
+
+
+class Derivatives:
+    """Sparse second-order forward propagation over a Graph w.r.t. `wrt` (input node ids)."""
+
+    def __init__(self, g: Graph, wrt: Sequence[int], second: bool = True):
+        self.g = g
+        self.index = {n: i for i, n in enumerate(wrt)}
+        self.second = second
+        self._grad: Dict[int, Dict[int, int]] = {}
+        self._hess: Dict[int, Dict[Tuple[int, int], int]] = {}
+
+    def grad(self, n: int) -> Dict[int, int]:
+        r = self._grad.get(n)
+        if r is None:
+            self._compute(n)
+            r = self._grad[n]
+        return r
+
+    def hess(self, n: int) -> Dict[Tuple[int, int], int]:
+        r = self._hess.get(n)
+        if r is None:
+            self._compute(n)
+            r = self._hess[n]
+        return r
+
+    def _compute(self, root: int) -> None:
+        g = self.g
+        # iterative post-order over not-yet-differentiated ancestors
+        stack = [(root, False)]
+        while stack:
+            n, done = stack.pop()
+            if n in self._grad:
+                continue
+            if not done:
+                stack.append((n, True))
+                for a in g.args[n]:
+                    if a not in self._grad:
+                        stack.append((a, False))
+                continue
+            self._node(n)
+
+    def _acc(self, d: dict, k, v: int) -> None:
+        g = self.g
+        if v == g.ZERO:
+            return
+        cur = d.get(k)
+        d[k] = v if cur is None else g.add(cur, v)
+        if d[k] == g.ZERO:
+            del d[k]
+
+    def _node(self, n: int) -> None:
+        g = self.g
+        op = g.op[n]
+        G: Dict[int, int] = {}
+        H: Dict[Tuple[int, int], int] = {}
+        if op == "const":
+            pass
+        elif op == "in":
+            i = self.index.get(n)
+            if i is not None:
+                G[i] = g.ONE
+        elif op == "neg":
+            a = g.args[n][0]
+            for k, v in self._grad[a].items():
+                G[k] = g.neg(v)
+            if self.second:
+                for k, v in self._hess[a].items():
+                    H[k] = g.neg(v)
+        elif op == "add":
+            a, b = g.args[n]
+            for src in (a, b):
+                for k, v in self._grad[src].items():
+                    self._acc(G, k, v)
+            if self.second:
+                for src in (a, b):
+                    for k, v in self._hess[src].items():
+                        self._acc(H, k, v)
+        elif op == "mul":
+            a, b = g.args[n]
+            ga, gb = self._grad[a], self._grad[b]
+            for k, v in ga.items():
+                self._acc(G, k, g.mul(b, v))
+            for k, v in gb.items():
+                self._acc(G, k, g.mul(a, v))
+            if self.second:
+                for k, v in self._hess[a].items():
+                    self._acc(H, k, g.mul(b, v))
+                for k, v in self._hess[b].items():
+                    self._acc(H, k, g.mul(a, v))
+                for i, vi in ga.items():
+                    for j, vj in gb.items():
+                        t = g.mul(vi, vj)
+                        if i == j:
+                            self._acc(H, (i, i), g.mul(g.const(2.0), t))
+                        else:
+                            self._acc(H, (i, j) if i < j else (j, i), t)
+        else:  # unary function of args[0]
+            a = g.args[n][0]
+            ga = self._grad[a]
+            if ga:
+                d1, d2 = g._dfun(n)
+                for k, v in ga.items():
+                    self._acc(G, k, g.mul(d1, v))
+                if self.second:
+                    for k, v in self._hess[a].items():
+                        self._acc(H, k, g.mul(d1, v))
+                    if d2 != g.ZERO:
+                        items = sorted(ga.items())
+                        # d2 * ga[i] is shared by every pair (i, j)
+                        for x, (i, vi) in enumerate(items):
+                            d2vi = g.mul(d2, vi)
+                            for (j, vj) in items[x:]:
+                                self._acc(H, (i, j), g.mul(d2vi, vj))
+        self._grad[n] = G
+        self._hess[n] = H
+
+
+# ----------------------------------------------------------------------------- emission
+def _lit(v: float) -> str:
+    r = repr(float(v))
+    if "e" not in r and "." not in r and "inf" not in r and "nan" not in r:
+        r += ".0"
+    return r
+
+
+def count_ops(g: Graph, outputs: Sequence[int]) -> Dict[str, int]:
+    seen, stack = set(), list(outputs)
+    while stack:
+        n = stack.pop()
+        if n in seen:
+            continue
+        seen.add(n)
+        stack.extend(g.args[n])
+    c: Dict[str, int] = {}
+    for n in seen:
+        op = g.op[n]
+        if op == "powi":
+            k = g.val[n]
+            c["mul"] = c.get("mul", 0) + (k.bit_length() - 1) + bin(k).count("1") - 1
+        elif op not in ("const", "in", "neg"):
+            c[op] = c.get(op, 0) + 1
+    return c
+
+
+def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], str], indent: str = "    ",
+         prefix: str = "t") -> List[str]:
+    """Straight-line C for the nodes reachable from `outputs` [(lhs, node)], DFS post-order in
+    output order (keeps live ranges short); sin/cos of one argument become one sincos()."""
+    name: Dict[int, str] = {}
+    lines: List[str] = []
+    need = set()
+    stack = [n for _, n in outputs]
+    while stack:
+        n = stack.pop()
+        if n in need:
+            continue
+        need.add(n)
+        stack.extend(g.args[n])
+    # sincos pairing
+    sin_of = {g.args[n][0]: n for n in need if g.op[n] == "sin"}
+    cos_of = {g.args[n][0]: n for n in need if g.op[n] == "cos"}
+    paired = {a for a in sin_of if a in cos_of}
+
+    def ref(n: int) -> str:
+        op = g.op[n]
+        if op == "const":
+            v = g.val[n]
+            return _lit(v) if v >= 0 else f"({_lit(v)})"
+        if op == "neg":
+            return f"(-{ref(g.args[n][0])})"
+        return name[n]
+
+    def define(n: int) -> None:
+        op = g.op[n]
+        if op in ("const", "neg") or n in name:
+            return
+        nm = f"{prefix}{n}"
+        a = g.args[n]
+        if op == "in":
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = {load[g.val[n]]};")
+        elif op == "add":
+            name[n] = nm
+            # print a + (-b) as a - b
+            x, y = a
+            if g.op[y] == "neg":
+                lines.append(f"{indent}const double {nm} = {ref(x)} - {ref(g.args[y][0])};")
+            elif g.op[x] == "neg":
+                lines.append(f"{indent}const double {nm} = {ref(y)} - {ref(g.args[x][0])};")
+            else:
+                lines.append(f"{indent}const double {nm} = {ref(x)} + {ref(y)};")
+        elif op == "mul":
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = {ref(a[0])} * {ref(a[1])};")
+        elif op == "rcp":
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = 1.0 / {ref(a[0])};")
+        elif op == "powi":
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = dto_powi<{g.val[n]}>({ref(a[0])});")
+        elif op == "powc":
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = pow({ref(a[0])}, {_lit(g.val[n])});")
+        elif op in ("sin", "cos") and a[0] in paired:
+            s, c = sin_of[a[0]], cos_of[a[0]]
+            name[s], name[c] = f"{prefix}{s}", f"{prefix}{c}"
+            lines.append(f"{indent}double {name[s]}, {name[c]}; sincos({ref(a[0])}, &{name[s]}, &{name[c]});")
+        else:
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = {op}({ref(a[0])});")
+
+    # iterative DFS post-order
+    for lhs, root in outputs:
+        stack2 = [(root, False)]
+        while stack2:
+            n, done = stack2.pop()
+            if n in name or g.op[n] == "const":
+                continue
+            if g.op[n] == "neg":
+                stack2.append((g.args[n][0], False))
+                continue
+            if not done:
+                stack2.append((n, True))
+                for a in reversed(g.args[n]):
+                    stack2.append((a, False))
+                continue
+            define(n)
+        lines.append(f"{indent}{lhs} = {ref(root)};")
+    return lines
