@@ -24,12 +24,22 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import sympy as sp
 
-CODEGEN_VERSION = "2"
+CODEGEN_VERSION = "3"
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 MODEL_DIR = os.path.join(PKG_DIR, "_models")
 NVCC = os.environ.get("DTO_NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _deriv_mode() -> str:
+    """"dag" (default): derivatives synthesised on the residual DAG (ir.py). "sympy": lower the
+    expanded symbolic derivative expressions (what the reference's Symbolics closures hold)
+    through tree CSE -- the literal drop-in input, kept as a cross-check path. Both are CUDA."""
+    m = os.environ.get("DTO_DERIV", "dag")
+    if m not in ("dag", "sympy"):
+        raise ValueError("DTO_DERIV must be 'dag' or 'sympy'")
+    return m
 
 
 def _tuning() -> Dict[str, int]:
@@ -57,12 +67,46 @@ class ElementSpec:
     evaluate: List[sp.Expr]
     jac_rows: List[int]
     jac_cols: List[int]
-    jac: List[sp.Expr]             # cost: dense gradient
     has_hess: bool
     hess_rows: List[int] = field(default_factory=list)
     hess_cols: List[int] = field(default_factory=list)
-    hess: List[sp.Expr] = field(default_factory=list)
     ineq: List[int] = field(default_factory=list)
+    vars: Sequence[sp.Symbol] = ()         # differentiation variables in order ([x;u;y] or [x;u])
+    lam: Sequence[sp.Symbol] = ()          # multipliers of the element's outputs (not for costs)
+    _jac: Optional[List[sp.Expr]] = None   # expanded symbolic derivatives, built on demand
+    _hess: Optional[List[sp.Expr]] = None  # (only the "sympy" derivative mode lowers these)
+
+    @property
+    def nnz_jac(self) -> int:
+        return len(self.jac_rows)
+
+    @property
+    def nnz_hess(self) -> int:
+        return len(self.hess_rows) if self.has_hess else 0
+
+    @property
+    def lagrangian(self) -> sp.Expr:
+        if self.role == "cost":
+            return self.evaluate[0]
+        acc = sp.Integer(0)
+        for l, e in zip(self.lam, self.evaluate):
+            acc = acc + l * e
+        return acc
+
+    @property
+    def jac(self) -> List[sp.Expr]:
+        if self._jac is None:
+            from . import symbolic as S
+            self._jac = S.jacobian_values(self.evaluate, list(self.vars), self.jac_rows, self.jac_cols)
+        return self._jac
+
+    @property
+    def hess(self) -> List[sp.Expr]:
+        if self._hess is None:
+            from . import symbolic as S
+            self._hess = (S.hessian_values(self.lagrangian, list(self.vars), self.hess_rows, self.hess_cols)
+                          if self.has_hess else [])
+        return self._hess
 
 
 @dataclass
@@ -219,6 +263,90 @@ _CALL = {"dyn": "y, x, u, w", "cost": "x, u, w", "stage": "x, u, w"}
 
 
 def _emit_element(el: ElementSpec, k: int, out: List[str], stats: dict) -> None:
+    if _deriv_mode() == "dag":
+        try:
+            _emit_element_dag(el, k, out, stats)
+            return
+        except NotImplementedError as e:  # a function the DAG has no rule for: lower sympy's derivatives instead
+            stats[f"{el.role}{k}_dag_fallback"] = str(e)
+    _emit_element_sympy(el, k, out, stats)
+
+
+def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict) -> None:
+    """Derivative synthesis on the residual DAG (ir.py): first/second-order sparse forward
+    propagation, all outputs of one pass share one hash-consed graph."""
+    from .ir import Derivatives, Graph, count_ops, emit
+
+    g = Graph()
+    sym: Dict[sp.Symbol, int] = {}
+    load: Dict[Tuple[str, int], str] = {}
+    for cname, syms in el.args.items():
+        for i, s_ in enumerate(syms):
+            sym[s_] = g.inp(cname, i)
+            load[(cname, i)] = f"{cname}[{i}]"
+    memo: dict = {}
+    res = [g.from_sympy(e, sym, memo) for e in el.evaluate]
+    wrt = [sym[v] for v in el.vars]
+    D = Derivatives(g, wrt, second=el.has_hess)
+    pre = f"{el.role}{k}"
+    sig = _SIG[el.role]
+    LAM = ", const double* __restrict__ lam"
+    chunks: List[str] = []
+
+    def fn(name, extra_sig, outputs, ret=None):
+        body = emit(g, outputs, load)
+        c = count_ops(g, [n for _, n in outputs])
+        stats[f"{pre}_{name}"] = sum(v for kk, v in c.items())
+        stats[f"{pre}_{name}_mix"] = c
+        chunks.append(f"__device__ __forceinline__ {'double' if ret else 'void'} {pre}_{name}({sig}{extra_sig})\n{{")
+        chunks.extend(body)
+        if ret:
+            chunks.append(f"    return {ret};")
+        chunks.append("}\n")
+
+    # Jacobian / gradient entries in pattern order; every derivative must sit inside the pattern
+    jac_nodes = []
+    allowed = {}
+    for r, c in zip(el.jac_rows, el.jac_cols):
+        allowed.setdefault(r - 1, set()).add(c - 1)
+    for i, rn in enumerate(res):
+        extra = set(D.grad(rn)) - allowed.get(i, set())
+        if extra:
+            raise RuntimeError(f"{pre}: derivative of output {i} w.r.t. variables {sorted(extra)} is outside the structural "
+                               "Jacobian pattern")
+    for r, c in zip(el.jac_rows, el.jac_cols):
+        jac_nodes.append(D.grad(res[r - 1]).get(c - 1, g.ZERO))
+    hess_nodes = []
+    if el.has_hess:
+        if el.role == "cost":
+            L = res[0]
+        else:
+            L = g.sum(g.mul(sym[l], rn) for l, rn in zip(el.lam, res))
+        Hd = D.hess(L)
+        pat = {(min(r, c) - 1, max(r, c) - 1) for r, c in zip(el.hess_rows, el.hess_cols)}
+        extra = set(Hd) - pat
+        if extra:
+            raise RuntimeError(f"{pre}: second derivatives {sorted(extra)} are outside the structural Hessian pattern")
+        for r, c in zip(el.hess_rows, el.hess_cols):
+            hess_nodes.append(Hd.get((min(r, c) - 1, max(r, c) - 1), g.ZERO))
+
+    if el.role == "cost":
+        fn("val", "", [("const double v", res[0])], ret="v")
+        fn("grad", ", double* __restrict__ G", [(f"G[{i}]", n) for i, n in enumerate(jac_nodes)])
+        sg = g.inp("sigma", 0)
+        load[("sigma", 0)] = "sigma"
+        fn("hess", ", const double sigma, double* __restrict__ H", [(f"H[{i}]", g.mul(sg, n)) for i, n in enumerate(hess_nodes)])
+    else:
+        jo = [(f"J[{i}]", n) for i, n in enumerate(jac_nodes)]
+        ho = [(f"H[{i}]", n) for i, n in enumerate(hess_nodes)]
+        fn("res", ", double* __restrict__ R", [(f"R[{i}]", n) for i, n in enumerate(res)])
+        fn("jac", ", double* __restrict__ J", jo)
+        fn("hess", LAM + ", double* __restrict__ H", ho)
+        fn("jac_hess", LAM + ", double* __restrict__ J, double* __restrict__ H", jo + ho)
+    out.extend(chunks)
+
+
+def _emit_element_sympy(el: ElementSpec, k: int, out: List[str], stats: dict) -> None:
     names, loads = _names_loads(el.args)
     pre = f"{el.role}{k}"
     sig = _SIG[el.role]
@@ -355,7 +483,7 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
         m.append("    {")
         m.append("        switch (k) {")
         for k, el in enumerate(els):
-            m.append(f"        case {k}: return {len(el.hess) if el.has_hess else 0};")
+            m.append(f"        case {k}: return {el.nnz_hess};")
         m.append("        default: return 0;")
         m.append("        }")
         m.append("    }")
@@ -398,8 +526,8 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
         d.append(_int_array(f"{p}_hr", el.hess_rows if el.has_hess else []))
         d.append(_int_array(f"{p}_hc", el.hess_cols if el.has_hess else []))
         d.append(_int_array(f"{p}_iq", el.ineq))
-        nj = len(el.jac)
-        nh = len(el.hess) if el.has_hess else 0
+        nj = el.nnz_jac
+        nh = el.nnz_hess
         return (f"{{{el.n_out}, {el.nx}, {el.nu}, {el.nw}, {nj}, {p}_jr, {p}_jc, {int(el.has_hess)}, {nh}, "
                 f"{p}_hr, {p}_hc, {len(el.ineq)}, {p}_iq}}")
 
@@ -448,6 +576,9 @@ def spec_hash(spec: ModelSpec) -> str:
     h = hashlib.sha256()
     h.update(CODEGEN_VERSION.encode())
     h.update(repr(sorted(_tuning().items())).encode())
+    h.update(_deriv_mode().encode())
+    with open(os.path.join(PKG_DIR, "ir.py"), "rb") as f:
+        h.update(f.read())
     for fname in ("dto_kernels.cuh", "dto_model_abi.h"):
         with open(os.path.join(CSRC_DIR, fname), "rb") as f:
             h.update(f.read())
@@ -455,7 +586,7 @@ def spec_hash(spec: ModelSpec) -> str:
     def feed_el(el):
         h.update(repr((el.role, el.n_out, el.nx, el.nu, el.nw, el.jac_rows, el.jac_cols, el.has_hess, el.hess_rows,
                        el.hess_cols, el.ineq)).encode())
-        for e in list(el.evaluate) + list(el.jac) + (list(el.hess) if el.has_hess else []):
+        for e in list(el.evaluate):
             h.update(sp.srepr(e).encode())
 
     for els in (spec.dyn, spec.cost, spec.stage):

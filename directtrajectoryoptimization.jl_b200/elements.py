@@ -24,19 +24,17 @@ class Cost:
         x, u, w = S.variables("x", num_state), S.variables("u", num_action), S.variables("w", num_parameter)
         evaluate = S.flatten(f(x, u, w))[0]
         xu = list(x) + list(u)
-        grad = [sp.diff(evaluate, v) for v in xu]
         self.num_state, self.num_action, self.num_parameter = num_state, num_action, num_parameter
         self.num_gradient = num_state + num_action
-        hr, hc, hv = [], [], []
+        hr, hc = [], []
         if evaluate_hessian:
             hr, hc = S.hessian_pattern(evaluate, xu)
-            hv = S.hessian_values(evaluate, xu, hr, hc)
-        self.num_hessian = len(hv)
+        self.num_hessian = len(hr)
         self.sparsity = [hr, hc] if evaluate_hessian else [[]]
         self.spec = ElementSpec(role="cost", n_out=1, nx=num_state, nu=num_action, nw=num_parameter,
                                 args={"x": list(x), "u": list(u), "w": list(w)}, evaluate=[evaluate],
-                                jac_rows=[1] * len(xu), jac_cols=list(range(1, len(xu) + 1)), jac=grad,
-                                has_hess=bool(evaluate_hessian), hess_rows=hr, hess_cols=hc, hess=hv)
+                                jac_rows=[1] * len(xu), jac_cols=list(range(1, len(xu) + 1)),
+                                has_hess=bool(evaluate_hessian), hess_rows=hr, hess_cols=hc, vars=xu)
 
 
 class Dynamics:
@@ -61,7 +59,8 @@ class Dynamics:
         xuy = list(x) + list(u) + list(y)
         self.num_next_state, self.num_state, self.num_action = num_next_state, num_state, num_action
         self.num_parameter = num_parameter
-        hr, hc, hv = [], [], []
+        hr, hc = [], []
+        jv = None
         if user_jac is not None:
             nv = len(xuy)
             M = np.zeros((num_next_state, nv), dtype=object)
@@ -72,19 +71,17 @@ class Dynamics:
             evaluate_hessian = False
         else:
             jr, jc = S.jacobian_pattern(evaluate, xuy)
-            jv = S.jacobian_values(evaluate, xuy, jr, jc)
         lam = S.variables("lam", num_next_state)
         if evaluate_hessian:
             lag = S.dot(lam, evaluate)
             hr, hc = S.hessian_pattern(lag, xuy)
-            hv = S.hessian_values(lag, xuy, hr, hc)
-        self.num_jacobian, self.num_hessian = len(jv), len(hv)
+        self.num_jacobian, self.num_hessian = len(jr), len(hr)
         self.jacobian_sparsity = [jr, jc]
         self.hessian_sparsity = [hr, hc] if evaluate_hessian else [[]]
         self.spec = ElementSpec(role="dyn", n_out=num_next_state, nx=num_state, nu=num_action, nw=num_parameter,
                                 args={"y": list(y), "x": list(x), "u": list(u), "w": list(w), "lam": list(lam)},
-                                evaluate=evaluate, jac_rows=jr, jac_cols=jc, jac=jv, has_hess=bool(evaluate_hessian),
-                                hess_rows=hr, hess_cols=hc, hess=hv)
+                                evaluate=evaluate, jac_rows=jr, jac_cols=jc, has_hess=bool(evaluate_hessian),
+                                hess_rows=hr, hess_cols=hc, vars=xuy, lam=list(lam), _jac=jv)
 
 
 class Constraint:
@@ -102,20 +99,18 @@ class Constraint:
         evaluate = S.flatten(f(x, u, w))
         xu = list(x) + list(u)
         jr, jc = S.jacobian_pattern(evaluate, xu)
-        jv = S.jacobian_values(evaluate, xu, jr, jc)
         lam = S.variables("lam", len(evaluate))
-        hr, hc, hv = [], [], []
+        hr, hc = [], []
         if evaluate_hessian:
             lag = S.dot(lam, evaluate)
             hr, hc = S.hessian_pattern(lag, xu)
-            hv = S.hessian_values(lag, xu, hr, hc)
-        self.num_constraint, self.num_jacobian, self.num_hessian = len(evaluate), len(jv), len(hv)
+        self.num_constraint, self.num_jacobian, self.num_hessian = len(evaluate), len(jr), len(hr)
         self.jacobian_sparsity = [jr, jc]
         self.hessian_sparsity = [hr, hc] if evaluate_hessian else [[]]
         self.spec = ElementSpec(role="stage", n_out=len(evaluate), nx=num_state, nu=num_action, nw=num_parameter,
                                 args={"x": list(x), "u": list(u), "w": list(w), "lam": list(lam)}, evaluate=evaluate,
-                                jac_rows=jr, jac_cols=jc, jac=jv, has_hess=bool(evaluate_hessian), hess_rows=hr,
-                                hess_cols=hc, hess=hv, ineq=list(indices_inequality))
+                                jac_rows=jr, jac_cols=jc, has_hess=bool(evaluate_hessian), hess_rows=hr,
+                                hess_cols=hc, ineq=list(indices_inequality), vars=xu, lam=list(lam))
 
 
 class GeneralConstraint:

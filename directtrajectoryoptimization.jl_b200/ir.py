@@ -129,7 +129,9 @@ class Graph:
             core = self.powi(xa, 2)
         else:
             # x * x^k -> x^(k+1)
-            if self.op[xb] == "powi" and self.args[xb][0] == xa:
+            if self.op[xa] == "powi" and self.op[xb] == "powi" and self.args[xa][0] == self.args[xb][0]:
+                core = self.powi(self.args[xa][0], self.val[xa] + self.val[xb])
+            elif self.op[xb] == "powi" and self.args[xb][0] == xa:
                 core = self.powi(xa, self.val[xb] + 1)
             elif self.op[xa] == "powi" and self.args[xa][0] == xb:
                 core = self.powi(xb, self.val[xa] + 1)
@@ -251,8 +253,7 @@ class Graph:
             return r, self.neg(self.powi(r, 2))
         if op == "sqrt":
             r = self.rcp(c)
-            return self.scale(0.5, r) if self.split(r)[0] == 1.0 else self.mul(self.const(0.5), r), \
-                self.mul(self.const(-0.25), self.powi(r, 3))
+            return self.mul(self.const(0.5), r), self.mul(self.const(-0.25), self.powi(r, 3))
         if op == "atan":
             r = self.rcp(self.add(self.ONE, self.powi(a, 2)))
             return r, self.mul(self.const(-2.0), self.mul(a, self.powi(r, 2)))
