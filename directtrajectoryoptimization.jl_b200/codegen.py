@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import sympy as sp
 
-CODEGEN_VERSION = "3"
+CODEGEN_VERSION = "4"
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 MODEL_DIR = os.path.join(PKG_DIR, "_models")
@@ -262,17 +262,17 @@ _SIG = {
 _CALL = {"dyn": "y, x, u, w", "cost": "x, u, w", "stage": "x, u, w"}
 
 
-def _emit_element(el: ElementSpec, k: int, out: List[str], stats: dict) -> None:
+def _emit_element(el: ElementSpec, k: int, out: List[str], stats: dict, cpool: Optional[dict] = None) -> None:
     if _deriv_mode() == "dag":
         try:
-            _emit_element_dag(el, k, out, stats)
+            _emit_element_dag(el, k, out, stats, cpool)
             return
         except NotImplementedError as e:  # a function the DAG has no rule for: lower sympy's derivatives instead
             stats[f"{el.role}{k}_dag_fallback"] = str(e)
     _emit_element_sympy(el, k, out, stats)
 
 
-def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict) -> None:
+def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict, cpool: Optional[dict] = None) -> None:
     """Derivative synthesis on the residual DAG (ir.py): first/second-order sparse forward
     propagation, all outputs of one pass share one hash-consed graph."""
     from .ir import Derivatives, Graph, count_ops, emit
@@ -294,7 +294,7 @@ def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict) -> N
     chunks: List[str] = []
 
     def fn(name, extra_sig, outputs, ret=None):
-        body = emit(g, outputs, load)
+        body = emit(g, outputs, load, cpool=cpool)
         c = count_ops(g, [n for _, n in outputs])
         stats[f"{pre}_{name}"] = sum(v for kk, v in c.items())
         stats[f"{pre}_{name}_mix"] = c
@@ -448,11 +448,16 @@ def _general_templates(gen: GeneralSpec):
 
 
 def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
-    out: List[str] = [_PREAMBLE]
+    out: List[str] = [_PREAMBLE, "/*CPOOL*/"]
     stats: dict = {}
+    cpool: Dict[float, int] = {}
     for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
         for k, el in enumerate(els):
-            _emit_element(el, k, out, stats)
+            _emit_element(el, k, out, stats, cpool)
+    vals = sorted(cpool, key=cpool.get)
+    out[1] = ("// FP64 literals whose low word is non-zero live in the constant bank (direct c[][] operands)\n"
+              "__constant__ double dto_k[] = {" + (", ".join(_lit(v) for v in vals) if vals else "0.0") + "};\n")
+    stats["const_pool"] = len(vals)
 
     # general constraint templates
     gen = spec.general

@@ -422,8 +422,16 @@ def count_ops(g: Graph, outputs: Sequence[int]) -> Dict[str, int]:
     return c
 
 
+def _needs_pool(v: float) -> bool:
+    """FP64 instructions take a 32-bit immediate = the HIGH word of the double; anything with a
+    non-zero low word (0.05, 9.81, 1/6 ...) would be materialised with two UMOVs per use, so it
+    goes to the constant bank instead (read as a direct c[bank][ofs] operand)."""
+    import struct
+    return (struct.unpack("<Q", struct.pack("<d", float(v)))[0] & 0xFFFFFFFF) != 0
+
+
 def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], str], indent: str = "    ",
-         prefix: str = "t") -> List[str]:
+         prefix: str = "t", cpool: Optional[Dict[float, int]] = None, cname: str = "dto_k") -> List[str]:
     """Straight-line C for the nodes reachable from `outputs` [(lhs, node)], DFS post-order in
     output order (keeps live ranges short); sin/cos of one argument become one sincos()."""
     name: Dict[int, str] = {}
@@ -445,6 +453,10 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
         op = g.op[n]
         if op == "const":
             v = g.val[n]
+            if cpool is not None and _needs_pool(v):
+                k = abs(v)
+                idx = cpool.setdefault(k, len(cpool))
+                return f"{cname}[{idx}]" if v >= 0 else f"(-{cname}[{idx}])"
             return _lit(v) if v >= 0 else f"({_lit(v)})"
         if op == "neg":
             return f"(-{ref(g.args[n][0])})"

@@ -19,7 +19,7 @@ from dto_b200.evaluator import K_JAC_HESS
 from examples import models as M
 from util import make_inputs
 build_only = %r
-model = M.build_%s(D, T=%d)
+model = M.BUILDERS[%r](D, **%r)
 s = D.solver_from(model, batch=%d, verbose=build_only)
 if build_only: sys.exit(0)
 import torch
@@ -46,18 +46,25 @@ print(json.dumps({"tune": os.environ.get("DTO_TUNE", ""), "model": %r, "ms": ms,
 
 def main():
     build_only = "--build-only" in sys.argv
-    model = "cartpole"
-    T, B = 101, 4096
+    model, kw, B = "cartpole", dict(T=101), 4096
     for a in sys.argv[1:]:
-        if a.startswith("--model="):
-            model = a.split("=")[1]
+        if a.startswith("--model="):  # e.g. --model=car:T=201,obstacle=general:16384
+            parts = a.split("=", 1)[1].split(":")
+            model = parts[0]
+            kw = {}
+            if len(parts) > 1 and parts[1]:
+                for kv in parts[1].split(","):
+                    k, v = kv.split("=")
+                    kw[k] = int(v) if v.isdigit() else v
+            if len(parts) > 2:
+                B = int(parts[2])
     tunes = TUNES
     for a in sys.argv[1:]:
         if a.startswith("--tunes="):
             tunes = a.split("=", 1)[1].split(";")
     for t in tunes:
         env = dict(os.environ, DTO_TUNE=t)
-        code = CHILD % (ROOT, ROOT, build_only, model, T, B, model, model)
+        code = CHILD % (ROOT, ROOT, build_only, model, kw, B, model, model + repr(kw))
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
         out = (r.stdout.strip().splitlines() or [""])[-1]
         print(out if r.returncode == 0 else f"FAILED {t}: {r.stderr[-500:]}", flush=True)
