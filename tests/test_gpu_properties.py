@@ -1,0 +1,184 @@
+"""GPU tests beyond small-case parity: golden fixtures, full BASELINE sizes against the oracle's C
+twin, size-independent properties (determinism, fused == separate, shard invariance, sigma
+linearity), edge cases and C-ABI state errors. Everything goes through libdto.so."""
+import os
+
+import numpy as np
+import pytest
+
+import dto_b200 as D
+from dto_b200 import _lib
+from dto_b200.evaluator import A_H, A_J, A_Z
+from examples import models as M
+from golden.make_golden import GOLDEN, tag
+from oracle import api as O
+from oracle import cgen
+from util import assert_close, make_inputs
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _eval_all(pn, z, lam, sigma, w):
+    B = z.shape[0]
+    if pn.num_parameter:
+        pn.set_parameters(w)
+    out = dict(f=pn.eval_objective(z), g=np.full((B, pn.num_variables), np.nan), c=np.full((B, pn.num_constraint), np.nan),
+               J=np.full((B, pn.num_jacobian), np.nan), H=np.full((B, pn.num_hessian), np.nan))
+    pn.eval_objective_gradient(out["g"])
+    pn.eval_constraint(out["c"])
+    pn.eval_constraint_jacobian(out["J"])
+    pn.eval_hessian_lagrangian(out["H"], None, sigma, lam)
+    return out
+
+
+@pytest.mark.parametrize("name,kw,B,config", GOLDEN, ids=[tag(g[0], g[1]) for g in GOLDEN])
+def test_cuda_matches_golden(name, kw, B, config):
+    fx = np.load(os.path.join(HERE, tag(name, kw) + ".npz"))
+    pn = D.solver_from(M.BUILDERS[name](D, **kw), batch=B).nlp
+    r, c = pn.jacobian_structure_arrays()
+    assert np.array_equal(np.stack([r, c], 1), fx["jac_structure"])
+    out = _eval_all(pn, fx["z"], fx["lam"], fx["sigma"], fx["w"])
+    for k in ("f", "g", "c", "J", "H"):
+        assert_close(f"{name} {k}", out[k], fx[k])
+    pn.close()
+
+
+FULL = [
+    ("cartpole", dict(T=101), 4096, 2),          # BASELINE configs[1]
+    ("acrobot", dict(T=101), 4096, 3),           # configs[2] (callbacks)
+    ("car", dict(T=201, obstacle="general"), 16384, 4),  # configs[3]
+    ("cartpole", dict(T=1001), 257, 5),          # configs[4] long horizon, ragged batch
+]
+
+
+@pytest.mark.parametrize("name,kw,B,config", FULL, ids=[f"{f[0]}-T{f[1]['T']}-B{f[2]}" for f in FULL])
+def test_full_size_vs_c_oracle_and_properties(name, kw, B, config):
+    mo = M.BUILDERS[name](O, **kw)
+    mp = M.BUILDERS[name](D, **kw)
+    osolver = O.solver_from(mo)
+    shared = bool(mo.get("shared_parameters"))
+    if shared:
+        osolver.set_parameters([np.zeros(8) for _ in range(mo["T"])] + [np.zeros(0)])
+    co = cgen.build_c_oracle(osolver, tag(name, kw), shared_parameters=shared, cse=True)
+    pn = D.solver_from(mp, batch=B).nlp
+    z, lam, sigma, w = make_inputs(name, mp, pn.num_variables, pn.num_constraint, pn.num_parameter, B, config)
+    ref = co.eval(31, z, lam, sigma, w)
+    out = _eval_all(pn, z, lam, sigma, w)
+    for k in ("f", "g", "c", "J", "H"):
+        assert_close(f"{name} {k}", out[k], ref[k])
+    # fused pass == separate passes, bit for bit; and repeatable bit for bit (deterministic gather order)
+    J2, H2 = np.empty_like(out["J"]), np.empty_like(out["H"])
+    pn.eval_jacobian_hessian(J2, H2)
+    assert np.array_equal(J2, out["J"]) and np.array_equal(H2, out["H"])
+    J3, H3 = np.empty_like(J2), np.empty_like(H2)
+    pn.eval_jacobian_hessian(J3, H3)
+    assert np.array_equal(J3, J2) and np.array_equal(H3, H2)
+    # shard invariance: three logical shards on one device give the identical bits (no cross-problem coupling)
+    ps = pn.new_batch(devices=[0, 0, 0])
+    if ps.num_parameter:
+        ps.set_parameters(w)
+    J4, H4 = np.empty_like(J2), np.empty_like(H2)
+    ps.eval_jacobian_hessian(J4, H4, z, sigma, lam)
+    assert _lib.lib().dto_batch_num_shards(ps.handle) == 3
+    assert np.array_equal(J4, J2) and np.array_equal(H4, H2)
+    # one-problem read-back (per-Ipopt driver path) and get_trajectory semantics
+    b = B // 2
+    row = np.empty(pn.num_hessian)
+    _lib.check(_lib.lib().dto_get_problem(pn.handle, A_H, b, row.ctypes.data))
+    assert np.array_equal(row, H2[b])
+    assert np.array_equal(pn.last_x(b), z[b])
+    ps.close()
+    pn.close()
+
+
+def test_sigma_linearity_and_dual_linearity():
+    """H(sigma, lambda) = sigma * H_cost + H_constraints(lambda), linear in each."""
+    mp = M.build_acrobot(D, T=21)
+    B = 37
+    pn = D.solver_from(mp, batch=B).nlp
+    z, lam, sigma, w = make_inputs("acrobot", mp, pn.num_variables, pn.num_constraint, 0, B, 3)
+    H = {}
+    for key, (s, l) in {"00": (0.0, 0 * lam), "10": (1.0, 0 * lam), "20": (2.0, 0 * lam), "01": (0.0, lam), "02": (0.0, 2 * lam),
+                        "11": (1.0, lam)}.items():
+        H[key] = np.empty((B, pn.num_hessian))
+        pn.eval_hessian_lagrangian(H[key], z, s, l)
+    assert np.all(H["00"] == 0.0)
+    assert np.allclose(H["20"], 2 * H["10"], rtol=1e-15, atol=0)
+    assert np.allclose(H["02"], 2 * H["01"], rtol=1e-13, atol=1e-15)
+    assert np.allclose(H["11"], H["10"] + H["01"], rtol=1e-13, atol=1e-15)
+    pn.close()
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 65])
+def test_ragged_batches_and_min_horizon(B):
+    """Warp tiles straddle problem boundaries: every batch size / horizon must give the same rows."""
+    for name, kw in (("pendulum", dict(T=2)), ("pendulum", dict(T=3)), ("cartpole", dict(T=7))):
+        mo, mp = M.BUILDERS[name](O, **kw), M.BUILDERS[name](D, **kw)
+        osolver = O.solver_from(mo)
+        shared = bool(mo.get("shared_parameters"))
+        if shared:
+            osolver.set_parameters([np.zeros(8) for _ in range(mo["T"])] + [np.zeros(0)])
+        co = cgen.build_c_oracle(osolver, tag(name, kw), shared_parameters=shared, cse=True)
+        pn = D.solver_from(mp, batch=B).nlp
+        z, lam, sigma, w = make_inputs(name, mp, pn.num_variables, pn.num_constraint, pn.num_parameter, B, 8)
+        ref = co.eval(31, z, lam, sigma, w)
+        out = _eval_all(pn, z, lam, sigma, w)
+        for k in ("f", "g", "c", "J", "H"):
+            assert_close(f"{name}{kw} B={B} {k}", out[k], ref[k])
+        pn.close()
+
+
+def test_state_errors_and_hessian_switch():
+    mp = M.build_pendulum(D)
+    pn = D.solver_from(mp, batch=2).nlp
+    with pytest.raises(_lib.DtoError) as e:
+        pn.eval_objective()
+    assert e.value.status == -6  # before dto_set_x
+    z = np.zeros((2, pn.num_variables))
+    pn.eval_objective(z)
+    H = np.empty((2, pn.num_hessian))
+    with pytest.raises(_lib.DtoError) as e:
+        pn.eval_hessian_lagrangian(H)
+    assert e.value.status == -6  # before dto_set_duals
+    with pytest.raises(ValueError):
+        pn.set_x(np.zeros((3, pn.num_variables)))
+    pn.close()
+    # a Cost without evaluate_hessian: the reference throws (Q9); we return DTO_ERR_NO_HESSIAN
+    mp = M.build_cartpole(D, T=5, evaluate_hessian=False)
+    pn = D.solver_from(mp, batch=2).nlp
+    pn.set_parameters(np.zeros((2, 8)))
+    pn.set_x(np.zeros((2, pn.num_variables)))
+    pn.set_duals(1.0, np.zeros((2, pn.num_constraint)))
+    with pytest.raises(_lib.DtoError) as e:
+        pn.eval_hessian_lagrangian(np.empty((2, 0)))
+    assert e.value.status == -5
+    J = np.empty((2, pn.num_jacobian))
+    pn.eval_constraint_jacobian(J)  # Jacobian still fine
+    assert np.isfinite(J).all()
+    pn.close()
+
+
+def test_nan_inf_pass_through():
+    """Non-finite values are handed back unchanged, like the reference (no status codes for them)."""
+    mp = M.build_pendulum(D)
+    pn = D.solver_from(mp, batch=3).nlp
+    z = np.random.default_rng(0).uniform(size=(3, pn.num_variables))
+    z[1, 0] = np.nan
+    z[2, 3] = np.inf
+    f = pn.eval_objective(z)
+    assert np.isfinite(f[0]) and np.isnan(f[1]) and not np.isfinite(f[2])
+    pn.close()
+
+
+def test_symbolic_derivative_mode_matches(monkeypatch):
+    """DTO_DERIV=sympy lowers the expanded symbolic derivative expressions (the literal form the
+    reference's closures hold); it must agree with the oracle like the default DAG mode does."""
+    monkeypatch.setenv("DTO_DERIV", "sympy")
+    for name, kw, B, config in [("pendulum", dict(), 4, 1), ("cartpole", dict(T=11), 3, 2)]:
+        fx = np.load(os.path.join(HERE, tag(name, kw) + ".npz"))
+        pn = D.solver_from(M.BUILDERS[name](D, **kw), batch=B).nlp
+        out = _eval_all(pn, fx["z"], fx["lam"], fx["sigma"], fx["w"])
+        for k in ("f", "g", "c", "J", "H"):
+            assert_close(f"sympy-mode {name} {k}", out[k], fx[k])
+        pn.close()
