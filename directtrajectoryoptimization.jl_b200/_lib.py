@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         "dto_launch_count": (i64, [vp]),
         "dto_algorithmic_bytes_per_problem": (i64, [vp]),
         "dto_kernel_smem_bytes": (i64, [vp, C.c_int]),
+        "dto_shape_compiled_gather": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

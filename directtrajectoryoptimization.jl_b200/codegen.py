@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import sympy as sp
 
-CODEGEN_VERSION = "4"
+CODEGEN_VERSION = "5"
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 MODEL_DIR = os.path.join(PKG_DIR, "_models")
@@ -46,7 +46,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 4, "min_ctas": 1}
+    t = {"warps": 4, "min_ctas": 1, "gather_unroll": 8}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -132,6 +132,7 @@ class ModelSpec:
     cost: List[ElementSpec]
     stage: List[ElementSpec]
     general: Optional[GeneralSpec] = None
+    hg_classes: List[tuple] = field(default_factory=list)   # compiled gather recipes (recipes.py)
 
 
 # ----------------------------------------------------------------------------- C printing
@@ -493,6 +494,39 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
         m.append("        }")
         m.append("    }")
     LAM = ", const double* __restrict__ lam"
+    # compiled Hessian gather classes
+    ncls = len(spec.hg_classes)
+    vmax = max([len(r) for r in spec.hg_classes] + [0])
+    m.append(f"    static constexpr int HG_NCLASS = {ncls};")
+    m.append(f"    static constexpr int HG_VMAX = {vmax};")
+    m.append(f"    __device__ __forceinline__ static void hg_compute(int cls, const double* __restrict__ own, "
+             f"const double* __restrict__ prev, double (&v)[{max(vmax, 1)}])")
+    m.append("    {")
+    m.append("        switch (cls) {")
+
+    def _src(k):
+        return f"own[{k}]" if k >= 0 else f"prev[{-k - 2}]"
+
+    for c, rec in enumerate(spec.hg_classes):
+        m.append(f"        case {c}:")
+        for j, srcs in enumerate(rec):
+            terms = [_src(k) for k in srcs if k != -1]
+            m.append(f"            v[{j}] = {' + '.join(terms) if terms else '0.0'};")
+        m.append("            break;")
+    m.append("        default: break;")
+    m.append("        }")
+    m.append("    }")
+    m.append(f"    __device__ __forceinline__ static void hg_store(int cls, const double (&v)[{max(vmax, 1)}], double* __restrict__ dst)")
+    m.append("    {")
+    m.append("        switch (cls) {")
+    for c, rec in enumerate(spec.hg_classes):
+        m.append(f"        case {c}:")
+        for j in range(len(rec)):
+            m.append(f"            dst[{j}] = v[{j}];")
+        m.append("            break;")
+    m.append("        default: break;")
+    m.append("        }")
+    m.append("    }")
     m += _dispatch("cost", len(spec.cost), "val", "double", "", "")
     m += _dispatch("cost", len(spec.cost), "grad", "void", ", double* __restrict__ G", ", G")
     m += _dispatch("cost", len(spec.cost), "hess", "void", ", const double sigma, double* __restrict__ H", ", sigma, H")
@@ -556,6 +590,14 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
                  f"{int(gen.has_hess)}, {nh}, gen_hr, gen_hc, {len(gen.ineq)}, gen_iq, "
                  "{gen_tmpl0, gen_tmpl1, gen_tmpl2}, {gen_zbase0, gen_zbase1, gen_zbase2}, "
                  "{gen_wbase0, gen_wbase1, gen_wbase2}, {gen_lbase0, gen_lbase1, gen_lbase2}};")
+    hg_ns = [len(r) for r in spec.hg_classes]
+    hg_of, acc = [], 0
+    for n_ in hg_ns:
+        hg_of.append(acc)
+        acc += n_
+    d.append(_int_array("hg_nslots", hg_ns))
+    d.append(_int_array("hg_ofs", hg_of))
+    d.append(_int_array("hg_src", [k for r in spec.hg_classes for srcs in r for k in srcs]))
     fused = 0
     for k in range(len(spec.dyn)):
         fused = max(fused, stats.get(f"dyn{k}_jac_hess", 0))
@@ -568,6 +610,7 @@ static const dto_model_vtable model_vtable = {{
     {len(spec.dyn)}, {len(spec.cost)}, {len(spec.stage)},
     dyn_descs, cost_descs, stage_descs, {"&gen_desc" if gen is not None else "nullptr"},
     {halo}, DTO_WARPS, {fused},
+    {len(spec.hg_classes)}, hg_nslots, hg_ofs, hg_src,
     model_launch, model_smem
 }};
 extern "C" __attribute__((visibility("default"))) const dto_model_vtable* dto_model_entry(void) {{ return &model_vtable; }}
@@ -598,6 +641,7 @@ def spec_hash(spec: ModelSpec) -> str:
         h.update(b"|")
         for el in els:
             feed_el(el)
+    h.update(repr(spec.hg_classes).encode())
     if spec.general is not None:
         g = spec.general
         h.update(repr((g.num_variables, g.num_parameter, g.jac_rows, g.jac_cols, g.has_hess, g.hess_rows, g.hess_cols,
@@ -622,7 +666,8 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}: the CUDA model library cannot be built (no CPU fallback exists)")
     tune = _tuning()
-    cmd = [NVCC, *NVCC_ARCH, f"-DDTO_WARPS={tune['warps']}", f"-DDTO_MIN_CTAS={tune['min_ctas']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+    cmd = [NVCC, *NVCC_ARCH, f"-DDTO_WARPS={tune['warps']}", f"-DDTO_MIN_CTAS={tune['min_ctas']}",
+           f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
            "-I", CSRC_DIR, "-o", so + ".tmp", cu]
     t1 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -32,6 +32,9 @@
 #ifndef DTO_MIN_CTAS
 #define DTO_MIN_CTAS 1
 #endif
+#ifndef DTO_GATHER_UNROLL
+#define DTO_GATHER_UNROLL 8
+#endif
 
 #define DTO_MODE_G 1
 #define DTO_MODE_C 2
@@ -42,20 +45,30 @@ namespace dto {
 
 __device__ __forceinline__ dto_knot_entry load_knot(const dto_knot_entry* __restrict__ tab, int t)
 {
-    // 48-byte entry = 3 x 16-byte read-only loads
+    // 64-byte entry = 4 x 16-byte read-only loads
     const int4* p = reinterpret_cast<const int4*>(tab + t);
-    int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
     dto_knot_entry e;
     e.zofs = a.x; e.nx = a.y; e.wofs = a.z; e.kdyn = a.w;
     e.kcost = b.x; e.kstage = b.y; e.rdyn = b.z; e.rstage = b.w;
     e.jdyn = c.x; e.jstage = c.y; e.hterm = c.z; e.hslot = c.w;
+    e.hclass = d.x; e.hprev = d.y; e.pad0 = 0; e.pad1 = 0;
     return e;
 }
 
 __device__ __forceinline__ void warp_stream_out(double* __restrict__ dst, const double* __restrict__ src, int n, int lane)
 {
-    // dst is 8-byte aligned only (slot ranges start anywhere); one 256-byte row per warp instruction
-    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+    // dst is 8-byte aligned only (slot ranges start anywhere); one 256-byte row per warp instruction,
+    // four rows in flight per trip
+    int i = lane;
+    for (; i + 96 < n; i += 128) {
+        const double v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
+        dst[i] = v0;
+        dst[i + 32] = v1;
+        dst[i + 64] = v2;
+        dst[i + 96] = v3;
+    }
+    for (; i < n; i += 32) dst[i] = src[i];
 }
 
 template <int MODE>
@@ -158,6 +171,30 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
     }
     __syncwarp();
 
+    // ---- compiled Hessian gather (recipes.py): each lane sums the terms of ITS knot's slots with
+    // straight-line code (no table loads), then the slot values overwrite the (now dead) term
+    // buffer so that the stream-out below is a plain coalesced copy.
+    constexpr bool HG = DO_H && (M::HG_NCLASS > 0);
+    if (HG && a.use_hclass) {
+        double v[M::HG_VMAX > 0 ? M::HG_VMAX : 1];
+        const long long g = g0 + lane - (HALO ? 1 : 0);
+        const bool own = (g < g1) && (g >= g0);
+        int cls = -1;
+        double* dst = nullptr;
+        if (own) {
+            const int b = (int)(g / T);
+            const int t = (int)(g - (long long)b * T);
+            const dto_knot_entry ke = load_knot(a.knot, t);
+            const double* ownp = sm + base[DTO_SEG_HTERM] + (b - b0) * L_h + (ke.hterm - k0.hterm);
+            cls = ke.hclass;
+            dst = sm + base[DTO_SEG_HTERM] + (b - b0) * a.nnz_H + (ke.hslot - k0.hslot);
+            M::hg_compute(cls, ownp, ownp - ke.hprev, v);
+        }
+        __syncwarp();
+        if (own) M::hg_store(cls, v, dst);
+        __syncwarp();
+    }
+
     // ---- stream-out phase: per (problem) sub-tile, coalesced ----
     {
         int b = b0, ta = t0;
@@ -183,31 +220,37 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
                 warp_stream_out(a.J + (size_t)b * a.nnz_J + ea.jstage,
                                 sm + base[DTO_SEG_JSTAGE] + db * L_js + (ea.jstage - k0.jstage), eb.jstage - ea.jstage, lane);
             }
-            if (DO_H) {
+            if (HG && a.use_hclass) {
+                warp_stream_out(a.H + (size_t)b * a.nnz_H + ea.hslot,
+                                sm + base[DTO_SEG_HTERM] + db * a.nnz_H + (ea.hslot - k0.hslot), eb.hslot - ea.hslot, lane);
+            } else if (DO_H) {
                 const double* __restrict__ smh = sm + base[DTO_SEG_HTERM] + db * L_h - k0.hterm;
                 double* __restrict__ Hb = a.H + (size_t)b * a.nnz_H;
                 const int4* __restrict__ src4 = reinterpret_cast<const int4*>(a.hsrc4);
+                // DTO_GATHER_UNROLL table records per lane are in flight before the first use: the
+                // records live in L2 (one 16-byte coalesced load each), so the exposed latency is
+                // one L2 round trip per 32*UNROLL slots instead of one per 32 slots.
                 int s = ea.hslot + lane;
-                // two slots per lane per trip: both table records are in flight before any use
-                for (; s + 32 < eb.hslot; s += 64) {
-                    const int4 q0 = __ldg(src4 + s), q1 = __ldg(src4 + s + 32);
-                    double a0 = q0.x >= 0 ? smh[q0.x] : 0.0, a1 = q1.x >= 0 ? smh[q1.x] : 0.0;
-                    if (q0.y >= 0) a0 += smh[q0.y];
-                    if (q1.y >= 0) a1 += smh[q1.y];
-                    if (q0.z >= 0) a0 += smh[q0.z];
-                    if (q1.z >= 0) a1 += smh[q1.z];
-                    if (q0.w >= 0) a0 += smh[q0.w];
-                    if (q1.w >= 0) a1 += smh[q1.w];
-                    Hb[s] = a0;
-                    Hb[s + 32] = a1;
+                for (; s + 32 * (DTO_GATHER_UNROLL - 1) < eb.hslot; s += 32 * DTO_GATHER_UNROLL) {
+                    int4 q[DTO_GATHER_UNROLL];
+#pragma unroll
+                    for (int k = 0; k < DTO_GATHER_UNROLL; ++k) q[k] = __ldg(src4 + s + 32 * k);
+#pragma unroll
+                    for (int k = 0; k < DTO_GATHER_UNROLL; ++k) {
+                        double acc = q[k].x >= 0 ? smh[q[k].x] : 0.0;
+                        if (q[k].y >= 0) acc += smh[q[k].y];
+                        if (q[k].z >= 0) acc += smh[q[k].z];
+                        if (q[k].w >= 0) acc += smh[q[k].w];
+                        Hb[s + 32 * k] = acc;
+                    }
                 }
-                if (s < eb.hslot) {
+                for (; s < eb.hslot; s += 32) {
                     const int4 q0 = __ldg(src4 + s);
-                    double a0 = q0.x >= 0 ? smh[q0.x] : 0.0;
-                    if (q0.y >= 0) a0 += smh[q0.y];
-                    if (q0.z >= 0) a0 += smh[q0.z];
-                    if (q0.w >= 0) a0 += smh[q0.w];
-                    Hb[s] = a0;
+                    double acc = q0.x >= 0 ? smh[q0.x] : 0.0;
+                    if (q0.y >= 0) acc += smh[q0.y];
+                    if (q0.z >= 0) acc += smh[q0.z];
+                    if (q0.w >= 0) acc += smh[q0.w];
+                    Hb[s] = acc;
                 }
             }
             rem -= cnt;

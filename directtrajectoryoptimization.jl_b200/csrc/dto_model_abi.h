@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 4
+#define DTO_MODEL_ABI_VERSION 5
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -73,7 +73,10 @@ typedef struct dto_knot_entry {
     int32_t jstage;  /* first stage Jacobian slot (absolute in J)                          */
     int32_t hterm;   /* first Hessian TERM of knot t; per knot: [cost][dynamics][stage]    */
     int32_t hslot;   /* first Hessian slot whose row is a variable of knot t               */
-} dto_knot_entry;
+    int32_t hclass;  /* compiled gather-recipe class of knot t (-1: use the table gather)  */
+    int32_t hprev;   /* hterm[t] - hterm[t-1] (0 for t = 0)                                */
+    int32_t pad0, pad1;
+} dto_knot_entry;    /* 16 x int32 = 64 bytes */
 
 /* Kernel ids for dto_model_vtable.launch */
 enum {
@@ -115,6 +118,7 @@ typedef struct dto_launch_args {
      * index = segment id below */
     int32_t seg_cap[6];
     int32_t seg_pad[6];   /* halo pad (doubles) in front of a segment, 0 unless halo */
+    int32_t use_hclass;   /* 1: every knot matched a compiled gather class of the model library */
 } dto_launch_args;
 
 enum { DTO_SEG_G = 0, DTO_SEG_CDYN = 1, DTO_SEG_CSTAGE = 2, DTO_SEG_JDYN = 3, DTO_SEG_JSTAGE = 4, DTO_SEG_HTERM = 5 };
@@ -132,6 +136,12 @@ typedef struct dto_model_vtable {
     int32_t warps_per_cta;
     /* fp64 instruction estimate per knot for the fused Jac+Hess pass (codegen op counts) */
     int32_t ops_fused_per_knot;
+    /* compiled Hessian gather recipes (recipes.py): class c has hg_nslots[c] slots whose 4 encoded
+     * sources start at hg_src[4*hg_ofs[c]] (k>=0 own term, k<=-2 previous knot's term -k-2, -1 none) */
+    int32_t n_hg_classes;
+    const int32_t* hg_nslots;
+    const int32_t* hg_ofs;
+    const int32_t* hg_src;
     /* Enqueue kernel `kernel_id` (+ its general-constraint companion) on `stream`.
      * Returns 0 or a cudaError_t value. */
     int (*launch)(int kernel_id, const dto_launch_args* args, void* stream);

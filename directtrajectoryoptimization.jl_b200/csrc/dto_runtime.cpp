@@ -84,6 +84,7 @@ struct dto_shape {
     std::vector<double> c_lower, c_upper;
     int32_t seg_cap[6] = {0, 0, 0, 0, 0, 0};
     int32_t seg_pad[6] = {0, 0, 0, 0, 0, 0};
+    bool use_hclass = false;
 };
 
 struct dto_shard {
@@ -366,6 +367,11 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         e.jstage = (int32_t)jstage;
         e.hterm = (int32_t)hterm;
         e.hslot = 0;  // filled below
+        for (int t = 0; t <= T; ++t) {
+            s->knot[t].hclass = -1;
+            s->knot[t].hprev = t > 0 ? s->knot[t].hterm - s->knot[t - 1].hterm : 0;
+            s->knot[t].pad0 = s->knot[t].pad1 = 0;
+        }
     }
     if (gen) {
         DTO_REQUIRE(gen->num_variables == s->N_z, "dto_shape_create: general constraint built for %d variables, shape has %lld",
@@ -491,6 +497,33 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         DTO_REQUIRE(n <= 4, "dto_shape_create: Hessian slot %lld has %d knot contributors (max 4)", (long long)sl, n);
         for (int32_t k = 0; k < n; ++k) s->hsrc4[4 * sl + k] = s->hsrc[s->hptr[sl] + k];
     }
+    // match every knot's gather recipe against the compiled classes of the model library
+    {
+        const dto_model_vtable* vt = m->vt;
+        bool all = vt->n_hg_classes > 0;
+        for (int t = 0; t < T && all; ++t) {
+            const int32_t s0 = s->knot[t].hslot, s1 = s->knot[t + 1].hslot;
+            int found = -1;
+            for (int c = 0; c < vt->n_hg_classes && found < 0; ++c) {
+                if (vt->hg_nslots[c] != s1 - s0) continue;
+                const int32_t* src = vt->hg_src + 4 * (size_t)vt->hg_ofs[c];
+                bool same = true;
+                for (int32_t sl = s0; sl < s1 && same; ++sl)
+                    for (int k = 0; k < 4 && same; ++k) {
+                        const int32_t id = s->hsrc4[4 * (size_t)sl + k];
+                        int32_t enc = -1;
+                        if (id >= 0) enc = id >= s->knot[t].hterm ? id - s->knot[t].hterm : -2 - (id - s->knot[t - 1].hterm);
+                        same = enc == src[4 * (size_t)(sl - s0) + k];
+                    }
+                if (same) found = c;
+            }
+            if (found < 0) all = false;
+            else s->knot[t].hclass = found;
+        }
+        if (!all)
+            for (int t = 0; t < T; ++t) s->knot[t].hclass = -1;
+        s->use_hclass = all;
+    }
     s->gen_hslot.resize(gen_terms.size());
     for (size_t i = 0; i < gen_terms.size(); ++i) s->gen_hslot[i] = slot_of(gen_terms[i].row, gen_terms[i].col);
     if (gen) {
@@ -521,6 +554,11 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         for (int k = 0; k < 6; ++k) {
             s->seg_cap[k] = cyclic_window_max(sz[k], 32);
             s->seg_pad[k] = 0;
+        }
+        {   // the compiled gather writes slot values over the term buffer: size it for both
+            std::vector<int32_t> nslot(T);
+            for (int t = 0; t < T; ++t) nslot[t] = s->knot[t + 1].hslot - s->knot[t].hslot;
+            s->seg_cap[DTO_SEG_HTERM] = std::max(s->seg_cap[DTO_SEG_HTERM], cyclic_window_max(nslot, 32));
         }
         if (m->vt->hess_halo) {
             s->seg_pad[DTO_SEG_JDYN] = *std::max_element(sz[DTO_SEG_JDYN].begin(), sz[DTO_SEG_JDYN].end());
@@ -612,7 +650,10 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
         a->seg_cap[k] = s->seg_cap[k];
         a->seg_pad[k] = s->seg_pad[k];
     }
+    a->use_hclass = s->use_hclass ? 1 : 0;
 }
+
+extern "C" int dto_shape_compiled_gather(const dto_shape* s) { return (s && s->use_hclass) ? 1 : 0; }
 
 extern "C" int64_t dto_kernel_smem_bytes(const dto_shape* s, int kernel_id)
 {

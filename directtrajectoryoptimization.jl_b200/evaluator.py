@@ -286,6 +286,9 @@ class BatchedNLPData:
     def algorithmic_bytes_per_problem(self) -> int:
         return int(_lib.lib().dto_algorithmic_bytes_per_problem(self.shape))
 
+    def compiled_gather(self) -> bool:
+        return bool(_lib.lib().dto_shape_compiled_gather(self.shape))
+
     def kernel_smem_bytes(self, kernel_id: int) -> int:
         return int(_lib.lib().dto_kernel_smem_bytes(self.shape, kernel_id))
 
@@ -332,6 +335,14 @@ class Solver:
         general = general_constraint if (general_constraint is not None and general_constraint.spec is not None) else None
         spec = ModelSpec(name=name, dyn=[e.spec for e in dyn_u], cost=[e.spec for e in cost_u],
                          stage=[e.spec for e in stage_u], general=general.spec if general else None)
+        # compiled Hessian gather: the distinct per-knot recipes of THIS shape (a handful for any horizon)
+        from .recipes import classes_of, knot_recipes
+        rec = knot_recipes(T, dyn_k, cost_k, stage_k, spec.dyn, spec.cost, spec.stage, spec.general)
+        import os
+        if rec is not None and os.environ.get("DTO_TABLE_GATHER", "0") != "1":
+            classes, _ = classes_of(rec)
+            if len(classes) <= 16 and max(len(c) for c in classes) <= 128:
+                spec.hg_classes = classes
         self.model = Model(spec, verbose=verbose)
 
         pdim = []

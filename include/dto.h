@@ -160,6 +160,9 @@ int64_t dto_launch_count(const dto_batch* b);
 /* algorithmic bytes of one fused Jacobian+Hessian call per problem:
  * 8*(N_z + N_c + N_w + nnz_J + nnz_H) + 8 */
 int64_t dto_algorithmic_bytes_per_problem(const dto_shape* s);
+/* 1 if every knot of the shape matched a compiled Hessian-gather class of the model library
+ * (straight-line gather, no table loads); 0 = the generic table-driven gather is used */
+int dto_shape_compiled_gather(const dto_shape* s);
 /* dynamic shared memory per CTA of the knot kernel for `kernel_id` */
 int64_t dto_kernel_smem_bytes(const dto_shape* s, int kernel_id);
 

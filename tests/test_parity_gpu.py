@@ -51,7 +51,7 @@ def test_callbacks_match_oracle(name, kw, B, config):
     assert_close("constraint", c, ref["c"])
     assert_close("jacobian", J, ref["J"])
     assert_close("hessian", H, ref["H"])
-    # fused pass must reproduce the separate passes bit for bit
+    # fused pass must reproduce the separate passes (to rounding: separately compiled programs)
     J2 = np.full_like(J, np.nan)
     H2 = np.full_like(H, np.nan)
     pn.eval_jacobian_hessian(J2, H2)
