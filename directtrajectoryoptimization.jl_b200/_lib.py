@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
         "dto_eval_constraint_jacobian": (C.c_int, [vp, vp]),
         "dto_eval_hessian_lagrangian": (C.c_int, [vp, vp]),
         "dto_eval_jacobian_hessian": (C.c_int, [vp, vp, vp]),
+        "dto_eval_jacobian_hessian_host": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int]),
         "dto_get_problem": (C.c_int, [vp, C.c_int, i64, vp]),
         "dto_get_last_x": (C.c_int, [vp, i64, vp]),
         "dto_device_pointer": (vp, [vp, C.c_int, C.c_int]),

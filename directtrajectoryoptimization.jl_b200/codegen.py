@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import sympy as sp
 
-CODEGEN_VERSION = "5"
+CODEGEN_VERSION = "8"
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 MODEL_DIR = os.path.join(PKG_DIR, "_models")
@@ -46,7 +46,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 4, "min_ctas": 1, "gather_unroll": 8}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -295,7 +295,7 @@ def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict, cpoo
     chunks: List[str] = []
 
     def fn(name, extra_sig, outputs, ret=None):
-        body = emit(g, outputs, load, cpool=cpool)
+        body = emit(g, outputs, load, cpool=cpool, order=_tuning().get("emit", 0))
         c = count_ops(g, [n for _, n in outputs])
         stats[f"{pre}_{name}"] = sum(v for kk, v in c.items())
         stats[f"{pre}_{name}_mix"] = c
@@ -484,6 +484,14 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
     # the struct name is unique per model: several model libraries live in one process and C++
     # template instantiations / inline statics with equal mangled names may be shared across them
     m: List[str] = [f"struct DtoModel_{source_hash} {{", f"    static constexpr int HESS_HALO = {halo};"]
+    els_all = list(spec.dyn) + list(spec.cost) + list(spec.stage)
+    m.append(f"    static constexpr int MAX_NX = {max([e.nx for e in els_all] + [e.n_out for e in spec.dyn] + [0])};")
+    m.append(f"    static constexpr int MAX_NU = {max([e.nu for e in els_all] + [0])};")
+    m.append(f"    static constexpr int MAX_NY = {max([e.n_out for e in spec.dyn] + [0])};")
+    m.append(f"    static constexpr int MAX_NW = {max([e.nw for e in els_all] + [0])};")
+    m.append(f"    static constexpr int MAX_NC = {max([e.n_out for e in spec.stage] + [0])};")
+    dyn_w = any(set(e.args["w"]) & set().union(*[x.free_symbols for x in e.evaluate]) for e in spec.dyn if len(e.args["w"]))
+    m.append(f"    static constexpr bool DYN_USES_W = {'true' if dyn_w else 'false'};")
     for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
         m.append(f"    __device__ __forceinline__ static int {role}_nh(int k)")
         m.append("    {")

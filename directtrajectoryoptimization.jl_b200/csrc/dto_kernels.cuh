@@ -52,7 +52,7 @@ __device__ __forceinline__ dto_knot_entry load_knot(const dto_knot_entry* __rest
     e.zofs = a.x; e.nx = a.y; e.wofs = a.z; e.kdyn = a.w;
     e.kcost = b.x; e.kstage = b.y; e.rdyn = b.z; e.rstage = b.w;
     e.jdyn = c.x; e.jstage = c.y; e.hterm = c.z; e.hslot = c.w;
-    e.hclass = d.x; e.hprev = d.y; e.pad0 = 0; e.pad1 = 0;
+    e.hclass = d.x; e.hprev = d.y; e.pad0 = d.z; e.pad1 = d.w;
     return e;
 }
 
@@ -193,6 +193,24 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
         __syncwarp();
         if (own) M::hg_store(cls, v, dst);
         __syncwarp();
+        // general-constraint Hessian entries owned by this lane's knot: last in the reference's +=
+        // order (src/moi.jl:112-118), added in shared memory so H is written to HBM exactly once
+        if (a.gen_nhess > 0) {
+            if (own) {
+                const int b = (int)(g / T);
+                const int t = (int)(g - (long long)b * T);
+                const int p0 = __ldg(a.gh_ptr + t), p1 = __ldg(a.gh_ptr + t + 1);
+                const int khs = load_knot(a.knot, t).hslot;
+                for (int p = p0; p < p1; ++p) {
+                    const int2 e = __ldg(reinterpret_cast<const int2*>(a.gh_ent) + p);  // slot, instance
+                    const int4 inst = __ldg(reinterpret_cast<const int4*>(a.gen_inst[2]) + e.y);
+                    const double val = M::gen_eval(2, inst.x, a.z + (size_t)b * a.N_z + inst.y, a.w + (size_t)b * a.N_w + inst.z,
+                                                   a.lam + (size_t)b * a.N_c + a.gen_row0 + inst.w);
+                    dst[e.x - khs] += val;
+                }
+            }
+            __syncwarp();
+        }
     }
 
     // ---- stream-out phase: per (problem) sub-tile, coalesced ----
@@ -372,10 +390,12 @@ inline int launch(int kernel_id, const dto_launch_args* pa, void* stream)
         return launch_general<M, 1>(a, st);
     case DTO_K_HESSIAN:
         if ((e = launch_knot<M, DTO_MODE_H>(a, st))) return e;
+        if (M::HG_NCLASS > 0 && a.use_hclass) return 0;  // general Hessian fused into the knot kernel
         return launch_general<M, 2>(a, st);
     case DTO_K_JAC_HESS:
         if ((e = launch_knot<M, DTO_MODE_J | DTO_MODE_H>(a, st))) return e;
         if ((e = launch_general<M, 1>(a, st))) return e;
+        if (M::HG_NCLASS > 0 && a.use_hclass) return 0;
         return launch_general<M, 2>(a, st);
     default:
         return (int)cudaErrorInvalidValue;

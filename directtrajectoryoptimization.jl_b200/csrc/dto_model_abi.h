@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 5
+#define DTO_MODEL_ABI_VERSION 7
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -75,7 +75,8 @@ typedef struct dto_knot_entry {
     int32_t hslot;   /* first Hessian slot whose row is a variable of knot t               */
     int32_t hclass;  /* compiled gather-recipe class of knot t (-1: use the table gather)  */
     int32_t hprev;   /* hterm[t] - hterm[t-1] (0 for t = 0)                                */
-    int32_t pad0, pad1;
+    int32_t pad0;    /* length of w_t (parameter_dim[t])                                   */
+    int32_t pad1;
 } dto_knot_entry;    /* 16 x int32 = 64 bytes */
 
 /* Kernel ids for dto_model_vtable.launch */
@@ -119,6 +120,10 @@ typedef struct dto_launch_args {
     int32_t seg_cap[6];
     int32_t seg_pad[6];   /* halo pad (doubles) in front of a segment, 0 unless halo */
     int32_t use_hclass;   /* 1: every knot matched a compiled gather class of the model library */
+    /* general-constraint Hessian entries grouped by the knot that owns their slot (fused into the
+     * knot kernel when use_hclass): entries gh_ptr[t]..gh_ptr[t+1], each = (slot, instance) */
+    const int32_t* gh_ptr;  /* [T+1] */
+    const int32_t* gh_ent;  /* [gen_nhess][2] */
 } dto_launch_args;
 
 enum { DTO_SEG_G = 0, DTO_SEG_CDYN = 1, DTO_SEG_CSTAGE = 2, DTO_SEG_JDYN = 3, DTO_SEG_JSTAGE = 4, DTO_SEG_HTERM = 5 };

@@ -81,6 +81,7 @@ struct dto_shape {
     std::vector<int32_t> hsrc4;                  // [nnz_H][4] packed, -1 padded; slot with no knot term: zero term
     std::vector<int32_t> gen_inst[3];            // [n][4]
     std::vector<int32_t> gen_hslot;
+    std::vector<int32_t> gh_ptr, gh_ent;         // general Hessian entries grouped by owning knot
     std::vector<double> c_lower, c_upper;
     int32_t seg_cap[6] = {0, 0, 0, 0, 0, 0};
     int32_t seg_pad[6] = {0, 0, 0, 0, 0, 0};
@@ -97,6 +98,9 @@ struct dto_shard {
     int32_t* d_hsrc4 = nullptr;
     int32_t* d_gen_inst[3] = {nullptr, nullptr, nullptr};
     int32_t* d_gen_hslot = nullptr;
+    int32_t* d_gh_ptr = nullptr;
+    int32_t* d_gh_ent = nullptr;
+    cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // chunk pipeline of the one-call host path
 };
 
 struct dto_batch {
@@ -370,7 +374,8 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         for (int t = 0; t <= T; ++t) {
             s->knot[t].hclass = -1;
             s->knot[t].hprev = t > 0 ? s->knot[t].hterm - s->knot[t - 1].hterm : 0;
-            s->knot[t].pad0 = s->knot[t].pad1 = 0;
+            s->knot[t].pad0 = (t < T && d->parameter_dim) ? d->parameter_dim[t] : 0;  // length of w_t
+            s->knot[t].pad1 = 0;
         }
     }
     if (gen) {
@@ -526,6 +531,27 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
     }
     s->gen_hslot.resize(gen_terms.size());
     for (size_t i = 0; i < gen_terms.size(); ++i) s->gen_hslot[i] = slot_of(gen_terms[i].row, gen_terms[i].col);
+    {   // group by the knot owning the slot (hslot[] is monotone in t)
+        s->gh_ptr.assign(T + 1, 0);
+        std::vector<int> owner(gen_terms.size());
+        for (size_t i = 0; i < gen_terms.size(); ++i) {
+            int lo = 0, hi = T;  // last t with hslot[t] <= slot
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) / 2;
+                if (s->knot[mid].hslot <= s->gen_hslot[i]) lo = mid; else hi = mid;
+            }
+            owner[i] = lo;
+            s->gh_ptr[lo + 1]++;
+        }
+        for (int t = 0; t < T; ++t) s->gh_ptr[t + 1] += s->gh_ptr[t];
+        s->gh_ent.assign(gen_terms.size() * 2, 0);
+        std::vector<int32_t> fill(s->gh_ptr.begin(), s->gh_ptr.end() - 1);
+        for (size_t i = 0; i < gen_terms.size(); ++i) {
+            const int32_t p = fill[owner[i]]++;
+            s->gh_ent[2 * p] = s->gen_hslot[i];
+            s->gh_ent[2 * p + 1] = (int32_t)i;
+        }
+    }
     if (gen) {
         const int n[3] = {gen->num_constraint, gen->nnz_jac, gen->has_hess ? gen->nnz_hess : 0};
         for (int cls = 0; cls < 3; ++cls) {
@@ -640,6 +666,8 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
         a->hsrc4 = sh->d_hsrc4;
         for (int k = 0; k < 3; ++k) a->gen_inst[k] = sh->d_gen_inst[k];
         a->gen_hslot = sh->d_gen_hslot;
+        a->gh_ptr = sh->d_gh_ptr;
+        a->gh_ent = sh->d_gh_ent;
     }
     a->gen_nrow = (int32_t)s->n_gen_rows;
     a->gen_njac = (int32_t)s->n_gen_jac;
@@ -704,7 +732,11 @@ extern "C" void dto_batch_destroy(dto_batch* b)
         for (int32_t*& p : sh.d_gen_inst)
             if (p) cudaFree(p);
         if (sh.d_gen_hslot) cudaFree(sh.d_gen_hslot);
+        if (sh.d_gh_ptr) cudaFree(sh.d_gh_ptr);
+        if (sh.d_gh_ent) cudaFree(sh.d_gh_ent);
         if (sh.stream && sh.own_stream) cudaStreamDestroy(sh.stream);
+        for (cudaStream_t& ps : sh.pipe)
+            if (ps) cudaStreamDestroy(ps);
     }
     cudaGetLastError();
     delete b;
@@ -759,6 +791,8 @@ extern "C" int dto_batch_create(dto_shape* s, int64_t B, const int* devices, int
             for (int k = 0; k < 3; ++k)
                 if ((r = upload(&sh.d_gen_inst[k], s->gen_inst[k], sh.stream))) return r;
             if ((r = upload(&sh.d_gen_hslot, s->gen_hslot, sh.stream))) return r;
+            if ((r = upload(&sh.d_gh_ptr, s->gh_ptr, sh.stream))) return r;
+            if ((r = upload(&sh.d_gh_ent, s->gh_ent, sh.stream))) return r;
             // inputs are allocated eagerly, outputs on first use
             for (int arr : {DTO_ARRAY_Z, DTO_ARRAY_LAMBDA, DTO_ARRAY_SIGMA, DTO_ARRAY_W})
                 if ((r = ensure_array(b, sh, arr))) return r;
@@ -888,7 +922,7 @@ static int launch_all(dto_batch* b, int kernel_id)
         int64_t n = 1;
         if (kernel_id == DTO_K_CONSTRAINT) n += a.gen_nrow > 0;
         if (kernel_id == DTO_K_JACOBIAN || kernel_id == DTO_K_JAC_HESS) n += a.gen_njac > 0;
-        if (kernel_id == DTO_K_HESSIAN || kernel_id == DTO_K_JAC_HESS) n += a.gen_nhess > 0;
+        if (kernel_id == DTO_K_HESSIAN || kernel_id == DTO_K_JAC_HESS) n += (a.gen_nhess > 0 && !a.use_hclass);
         b->launches += n;
     }
     return DTO_OK;
@@ -917,6 +951,60 @@ extern "C" int dto_eval_jacobian_hessian(dto_batch* b, double* J, double* H)
     if ((r = d2h(b, DTO_ARRAY_J, J))) return r;
     if ((r = d2h(b, DTO_ARRAY_H, H))) return r;
     return sync_all(b);
+}
+
+extern "C" int dto_eval_jacobian_hessian_host(dto_batch* b, const double* z, const double* sigma, const double* lambda, double* J,
+                                              double* H, int nchunks)
+{
+    if (!b || !z || !sigma || !lambda) return fail(DTO_ERR_BAD_ARG, "dto_eval_jacobian_hessian_host: null argument");
+    const dto_shape* s = b->shape;
+    if (!s->hessian_available)
+        return fail(DTO_ERR_NO_HESSIAN, "Hessian requested but a Cost was built without evaluate_hessian (reference throws at src/costs.jl:68)");
+    if (nchunks <= 0) nchunks = 8;
+    const int64_t wz = s->N_z, wl = s->N_c, wj = s->nnz_J, wh = s->nnz_H;
+    for (dto_shard& sh : b->shards) {
+        if (sh.size == 0) continue;
+        int r;
+        for (int arr : {DTO_ARRAY_Z, DTO_ARRAY_LAMBDA, DTO_ARRAY_SIGMA, DTO_ARRAY_W, DTO_ARRAY_J, DTO_ARRAY_H})
+            if ((r = ensure_array(b, sh, arr))) return r;
+        DTO_CUDA(cudaSetDevice(sh.device));
+        DTO_CUDA(cudaStreamSynchronize(sh.stream));  // parameters / earlier work on the shard's main stream
+        for (cudaStream_t& ps : sh.pipe)
+            if (!ps) DTO_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+        const int64_t nc = std::min<int64_t>(nchunks, sh.size);
+        const int64_t per = (sh.size + nc - 1) / nc;
+        for (int64_t k = 0; k < nc; ++k) {
+            const int64_t first = k * per, cnt = std::min<int64_t>(per, sh.size - first);
+            if (cnt <= 0) break;
+            cudaStream_t st = sh.pipe[k % 4];
+            const int64_t g = sh.begin + first;  // global problem index
+            DTO_CUDA(cudaMemcpyAsync(sh.arr[DTO_ARRAY_Z] + first * wz, z + g * wz, (size_t)(cnt * wz) * sizeof(double), cudaMemcpyHostToDevice, st));
+            DTO_CUDA(cudaMemcpyAsync(sh.arr[DTO_ARRAY_LAMBDA] + first * wl, lambda + g * wl, (size_t)(cnt * wl) * sizeof(double), cudaMemcpyHostToDevice, st));
+            DTO_CUDA(cudaMemcpyAsync(sh.arr[DTO_ARRAY_SIGMA] + first, sigma + g, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+            dto_launch_args a;
+            fill_args(s, &sh, &a);
+            a.B = cnt;
+            a.z += first * wz;
+            a.lam += first * wl;
+            a.sigma += first;
+            a.w += first * s->N_w;
+            a.J += first * wj;
+            a.H += first * wh;
+            const int e = s->model->vt->launch(DTO_K_JAC_HESS, &a, (void*)st);
+            if (e != 0) return fail(DTO_ERR_CUDA, "kernel launch (fused, chunk %lld) failed: %s", (long long)k, cudaGetErrorString((cudaError_t)e));
+            b->launches += 1 + (a.gen_njac > 0) + (a.gen_nhess > 0 && !a.use_hclass);
+            if (J) DTO_CUDA(cudaMemcpyAsync(J + g * wj, sh.arr[DTO_ARRAY_J] + first * wj, (size_t)(cnt * wj) * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (H) DTO_CUDA(cudaMemcpyAsync(H + g * wh, sh.arr[DTO_ARRAY_H] + first * wh, (size_t)(cnt * wh) * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (dto_shard& sh : b->shards) {
+        if (sh.size == 0) continue;
+        DTO_CUDA(cudaSetDevice(sh.device));
+        for (cudaStream_t ps : sh.pipe)
+            if (ps) DTO_CUDA(cudaStreamSynchronize(ps));
+    }
+    b->have_x = b->have_duals = true;
+    return DTO_OK;
 }
 
 extern "C" int dto_get_problem(dto_batch* b, int array, int64_t problem, double* out)

@@ -244,10 +244,18 @@ class BatchedNLPData:
             self.set_duals(1.0 if scaling is None else scaling, duals)
         _lib.check(_lib.lib().dto_eval_hessian_lagrangian(self.handle, _p(H)))
 
-    def eval_jacobian_hessian(self, jacobian, hessian, variables=None, scaling=None, duals=None):
+    def eval_jacobian_hessian(self, jacobian, hessian, variables=None, scaling=None, duals=None, chunks: int = 0):
         """Fused Jacobian + Hessian-of-Lagrangian pass (one kernel over the knots)."""
         J = _out(jacobian, (self.batch, self.num_jacobian), "jacobian")
         H = _out(hessian, (self.batch, self.num_hessian), "hessian")
+        if variables is not None and duals is not None:
+            # one pipelined host call: chunked copy-in / kernel / copy-out over several streams
+            z = _f64(variables, (self.batch, self.num_variables), "variables")
+            s = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if scaling is None else scaling, dtype=np.float64),
+                                                     (self.batch,)))
+            lam = _f64(duals, (self.batch, self.num_constraint), "duals")
+            _lib.check(_lib.lib().dto_eval_jacobian_hessian_host(self.handle, _p(z), _p(s), _p(lam), _p(J), _p(H), chunks))
+            return
         if variables is not None:
             self.set_x(variables)
         if duals is not None:

@@ -431,7 +431,7 @@ def _needs_pool(v: float) -> bool:
 
 
 def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], str], indent: str = "    ",
-         prefix: str = "t", cpool: Optional[Dict[float, int]] = None, cname: str = "dto_k") -> List[str]:
+         prefix: str = "t", cpool: Optional[Dict[float, int]] = None, cname: str = "dto_k", order: int = 0) -> List[str]:
     """Straight-line C for the nodes reachable from `outputs` [(lhs, node)], DFS post-order in
     output order (keeps live ranges short); sin/cos of one argument become one sincos()."""
     name: Dict[int, str] = {}
@@ -501,6 +501,97 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
             name[n] = nm
             lines.append(f"{indent}const double {nm} = {op}({ref(a[0])});")
 
+    if order == 2:
+        # register-pressure-aware list scheduling: among the ready nodes pick the one that retires the
+        # most live values (last uses) -- ptxas largely keeps source order for long FP64 blocks, so
+        # the emitted order decides how many registers the ~1000-instruction knot program needs
+        def core(n: int) -> int:
+            while g.op[n] == "neg":
+                n = g.args[n][0]
+            return n
+
+        nodes = [n for n in sorted(need) if g.op[n] not in ("const", "neg")]
+        ops_of = {n: [core(a) for a in g.args[n] if g.op[core(a)] != "const"] for n in nodes}
+        uses: Dict[int, int] = {n: 0 for n in nodes}
+        consumers: Dict[int, List[int]] = {n: [] for n in nodes}
+        for n in nodes:
+            for a in set(ops_of[n]):
+                uses[a] += 1
+                consumers[a].append(n)
+        outs_of: Dict[int, List[str]] = {}
+        for lhs, root in outputs:
+            outs_of.setdefault(root, []).append(lhs)
+        for lhs, root in outputs:
+            c = core(root)
+            if g.op[c] != "const":
+                uses[c] += 0  # stores are emitted right at definition: they do not extend the live range
+        missing = {n: len(set(ops_of[n])) for n in nodes}
+        ready = [n for n in nodes if missing[n] == 0]
+        done = set()
+        last_pick = -1
+        order_idx = {n: i for i, n in enumerate(nodes)}
+        stored = set()
+
+        def flush_outputs():
+            for lhs, root in outputs:
+                if lhs in stored:
+                    continue
+                c = core(root)
+                if g.op[c] == "const" or c in done:
+                    lines.append(f"{indent}{lhs} = {ref(root)};")
+                    stored.add(lhs)
+
+        flush_outputs()
+        while ready:
+            best, best_key = None, None
+            for n in ready:
+                frees = sum(1 for a in set(ops_of[n]) if uses[a] == 1)
+                creates = 0 if (not consumers[n]) else 1
+                # prefer: most net frees, then consumers of the value defined last (chains), then source order
+                key = (frees - creates, 1 if last_pick in ops_of[n] else 0, -order_idx[n])
+                if best_key is None or key > best_key:
+                    best, best_key = n, key
+            n = best
+            ready.remove(n)
+            define(n)
+            if g.op[n] in ("sin", "cos") and g.args[n][0] in paired:  # sincos defines both
+                for m_ in (sin_of[g.args[n][0]], cos_of[g.args[n][0]]):
+                    if m_ not in done and m_ != n:
+                        done.add(m_)
+                        if m_ in ready:
+                            ready.remove(m_)
+                        for a in set(ops_of[m_]):
+                            uses[a] -= 1
+                        for c_ in consumers[m_]:
+                            missing[c_] -= 1
+                            if missing[c_] == 0 and c_ not in done:
+                                ready.append(c_)
+            done.add(n)
+            last_pick = n
+            for a in set(ops_of[n]):
+                uses[a] -= 1
+            for c_ in consumers[n]:
+                missing[c_] -= 1
+                if missing[c_] == 0 and c_ not in done and c_ not in ready:
+                    ready.append(c_)
+            flush_outputs()
+        flush_outputs()
+        assert len(stored) == len(outputs), "scheduler left outputs unstored"
+        return lines
+    if order == 1:
+        # level order: every node at its dependency depth (maximal ILP in source order; ptxas then
+        # trades it against registers), outputs stored as soon as their node exists
+        depth: Dict[int, int] = {}
+        for n in sorted(need):
+            depth[n] = 1 + max([depth[a] for a in g.args[n]], default=0) if g.op[n] not in ("const",) else 0
+        pending: Dict[int, List[str]] = {}
+        for lhs, root in outputs:
+            pending.setdefault(root, []).append(lhs)
+        for n in sorted((n for n in need if g.op[n] not in ("const", "neg")), key=lambda n: (depth[n], n)):
+            define(n)
+        for lhs, root in outputs:
+            lines.append(f"{indent}{lhs} = {ref(root)};")
+        return lines
     # iterative DFS post-order
     for lhs, root in outputs:
         stack2 = [(root, False)]

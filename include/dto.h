@@ -132,6 +132,14 @@ int dto_eval_hessian_lagrangian(dto_batch* b, double* H /* [B][num_hessian] */);
  * common subexpressions; the benchmark unit). Either output may be NULL to skip its copy. */
 int dto_eval_jacobian_hessian(dto_batch* b, double* J, double* H);
 
+/* The same fused pass as ONE host call: z, sigma, lambda in -- J, H out. Each shard is cut into
+ * `nchunks` (<= 0: library default) contiguous sub-batches that are pipelined over several CUDA
+ * streams (copy-in of chunk k+1 and copy-out of chunk k-1 overlap the kernel of chunk k, and the
+ * two PCIe directions overlap each other). Host buffers should be page-locked for the overlap
+ * to happen; pageable memory still works. z/sigma/lambda stay resident afterwards. */
+int dto_eval_jacobian_hessian_host(dto_batch* b, const double* z, const double* sigma, const double* lambda, double* J,
+                                   double* H, int nchunks);
+
 /* one-Ipopt-per-problem drivers: copy one problem's slice of the last results (device -> host) */
 typedef enum dto_array {
     DTO_ARRAY_Z = 0, DTO_ARRAY_LAMBDA = 1, DTO_ARRAY_SIGMA = 2, DTO_ARRAY_W = 3, DTO_ARRAY_F = 4,
