@@ -189,3 +189,25 @@ def test_partition_rule():
     assert sharding.partition(2, 4) == [(0, 1), (1, 1), (2, 0), (2, 0)]
     cover = [i for b, n in sharding.partition(1001, 7) for i in range(b, b + n)]
     assert cover == list(range(1001))
+
+
+def test_json_spec_round_trip_builds_identical_model(tmp_path):
+    """The language-neutral JSON spec (what the Julia glue writes) reproduces the same model library
+    content hash as the python front end: same expressions, patterns and gather classes."""
+    import json
+    from dto_b200 import spec_io
+    for name, kw in (("pendulum", dict()), ("cartpole", dict(T=11)), ("car", dict(T=12, obstacle="general"))):
+        mp = M.BUILDERS[name](D, **kw)
+        s = D.solver_from(mp, batch=1)
+        T = mp["T"]
+        kd, kc, ks = [k.tolist() for k in s.nlp._keep[:3]]
+        doc = spec_io.dump_spec(s.model.spec, dict(T=T, dynamics_kind=kd, cost_kind=kc, stage_kind=ks))
+        p = tmp_path / f"{name}.json"
+        p.write_text(json.dumps(doc))
+        spec2 = spec_io.load_spec(json.loads(p.read_text()))
+        assert codegen.spec_hash(spec2) == codegen.spec_hash(s.model.spec), name
+        assert spec_io.main([str(p)]) == 0
+    # a front-end pattern that disagrees with the structural detection is rejected
+    doc["dynamics"][0]["jacobian_sparsity"][0][0] = 2
+    with pytest.raises(ValueError):
+        spec_io.load_spec(doc)
