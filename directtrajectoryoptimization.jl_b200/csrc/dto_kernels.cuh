@@ -35,6 +35,9 @@
 #ifndef DTO_GATHER_UNROLL
 #define DTO_GATHER_UNROLL 8
 #endif
+#ifndef DTO_L2_PREFETCH
+#define DTO_L2_PREFETCH 1
+#endif
 
 #define DTO_MODE_G 1
 #define DTO_MODE_C 2
@@ -114,6 +117,19 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
     const long long g1 = (g0 + OWN < total) ? g0 + OWN : total;
     const int b0 = (int)(g0 / T);
     const int t0 = (int)(g0 - (long long)b0 * T);
+
+    // L2 prefetch of the inputs of the tile that will start when this one retires (the grid is
+    // consumed in order, `tiles_in_flight` warps at a time): its loads then hit L2, not HBM.
+    if (a.tiles_in_flight > 0) {
+        const long long ga = g0 + (long long)a.tiles_in_flight * OWN;
+        if (ga < total) {
+            const long long zf = ga * a.N_z / T, lf = ga * a.N_c / T;       // flat offsets (approximate is fine)
+            const int zl = (OWN * a.N_z / T + a.N_z / T) / 16 + 2;           // 128-byte lines of the z range
+            const int ll = (OWN * a.N_c / T) / 16 + 2;
+            if (lane < zl) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.z + zf + lane * 16));
+            if ((MODE & DTO_MODE_H) && lane < ll) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.lam + lf + lane * 16));
+        }
+    }
 
     int base[6];
     const int per_warp = smem_doubles_per_warp<MODE>(a, base);
@@ -351,7 +367,29 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
             return (int)e;
         }
     }
-    knot_kernel<M, MODE><<<(unsigned)ctas, DTO_WARPS * 32, (size_t)smem, st>>>(a);
+    dto_launch_args b = a;
+    b.tiles_in_flight = 0;
+#if DTO_L2_PREFETCH
+    {
+        static int resident_warps[16] = {0};  // per device, for the shared-memory size it was computed with
+        static int64_t resident_smem[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 16) {
+            if (resident_warps[dev] == 0 || resident_smem[dev] != smem) {
+                resident_smem[dev] = smem;
+                int sms = 0, per_sm = 0;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knot_kernel<M, MODE>, DTO_WARPS * 32, (size_t)smem) != cudaSuccess)
+                    per_sm = 0;
+                resident_warps[dev] = sms * per_sm * DTO_WARPS;
+                cudaGetLastError();
+            }
+            b.tiles_in_flight = resident_warps[dev];
+        }
+    }
+#endif
+    knot_kernel<M, MODE><<<(unsigned)ctas, DTO_WARPS * 32, (size_t)smem, st>>>(b);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         fprintf(stderr, "[dto] knot_kernel<mode %d> launch failed: %s (grid %lld, block %d, smem %lld)\n", MODE, cudaGetErrorString(e),

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 7
+#define DTO_MODEL_ABI_VERSION 8
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -124,6 +124,9 @@ typedef struct dto_launch_args {
      * knot kernel when use_hclass): entries gh_ptr[t]..gh_ptr[t+1], each = (slot, instance) */
     const int32_t* gh_ptr;  /* [T+1] */
     const int32_t* gh_ent;  /* [gen_nhess][2] */
+    /* filled by the model library at launch: how many warp tiles run concurrently on the device; a
+     * starting warp prefetches (L2) the inputs of the tile that many positions ahead */
+    int32_t tiles_in_flight;
 } dto_launch_args;
 
 enum { DTO_SEG_G = 0, DTO_SEG_CDYN = 1, DTO_SEG_CSTAGE = 2, DTO_SEG_JDYN = 3, DTO_SEG_JSTAGE = 4, DTO_SEG_HTERM = 5 };
