@@ -48,6 +48,16 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the one
+    committed `ncu --set full` capture of this workload (profiles/traffic_r01.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def _fp64_peak():
     p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
     if os.path.exists(p):
@@ -105,6 +115,14 @@ class ClockSampler:
                 "window": "timed region + identical untimed continuation (>=1 s under load)"}
 
 
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1: do not trust it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def build_c_baseline(T: int, verbose=False):
     from examples import models as M
     from oracle import api as O, cgen
@@ -140,7 +158,7 @@ def run_reference(args):
         return 0
     from util import make_inputs
     co, mo = build_c_baseline(args.T)
-    threads = co.max_threads()
+    threads = host_threads()
     Bs = args.ref_sample
     z, lam, sigma, w = make_inputs("cartpole", mo, co.NZ, co.NC, co.NW, Bs, config=2, shard=0)
     what = 8 | 16
@@ -284,7 +302,8 @@ def run_ours(args):
             "gpu_launches": int(n1 - n0),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (_ncu_traffic() or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "traffic_source": (_ncu_traffic() or {}).get("source"),
                          "algorithmic_bytes_per_launch": bytes_per_launch},
         }
         if ops:
@@ -293,7 +312,7 @@ def run_ours(args):
                             "peak_gdfma": fp / 1e9, "note": "cartpole RK3 is FP64-pipe bound (SURVEY 8d); ops = sympy count_ops"}
         if world == 1 and not args.no_cpu:
             co, mo = build_c_baseline(T)
-            threads = co.max_threads()
+            threads = host_threads()
             v, Bs, reps, dtc = time_cpu(co, z, lam, sigma, w, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{Bs} of {B} problems x T={T}, {reps} passes, {dtc:.1f} s, oracle C twin (no-CSE "
