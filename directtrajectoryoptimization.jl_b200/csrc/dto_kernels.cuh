@@ -59,6 +59,13 @@ __device__ __forceinline__ dto_knot_entry load_knot(const dto_knot_entry* __rest
     return e;
 }
 
+// flat item index -> (problem, knot) without an integer divide (magic number from the runtime)
+__device__ __forceinline__ void split_item(const dto_launch_args& a, int g, int& b, int& t)
+{
+    b = (int)(((unsigned long long)(unsigned)g * a.div_mul) >> a.div_shift);
+    t = g - b * a.T;
+}
+
 __device__ __forceinline__ void warp_stream_out(double* __restrict__ dst, const double* __restrict__ src, int n, int lane)
 {
     // dst is 8-byte aligned only (slot ranges start anywhere); one 256-byte row per warp instruction,
@@ -111,21 +118,24 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int T = a.T;
-    const long long total = a.B * (long long)T;
-    const long long g0 = ((long long)blockIdx.x * DTO_WARPS + wib) * OWN;  // first OWN item of this warp
+    const int total = (int)(a.B * T);  // the runtime guarantees B*T < 2^31 per shard
+    const int g0 = (int)((blockIdx.x * DTO_WARPS + wib) * OWN);  // first OWN item of this warp
     if (g0 >= total) return;
-    const long long g1 = (g0 + OWN < total) ? g0 + OWN : total;
-    const int b0 = (int)(g0 / T);
-    const int t0 = (int)(g0 - (long long)b0 * T);
+    const int g1 = (g0 + OWN < total) ? g0 + OWN : total;
+    int b0, t0;
+    split_item(a, g0, b0, t0);
 
     // L2 prefetch of the inputs of the tile that will start when this one retires (the grid is
     // consumed in order, `tiles_in_flight` warps at a time): its loads then hit L2, not HBM.
     if (a.tiles_in_flight > 0) {
-        const long long ga = g0 + (long long)a.tiles_in_flight * OWN;
+        const long long ga = (long long)g0 + (long long)a.tiles_in_flight * OWN;
         if (ga < total) {
-            const long long zf = ga * a.N_z / T, lf = ga * a.N_c / T;       // flat offsets (approximate is fine)
-            const int zl = (OWN * a.N_z / T + a.N_z / T) / 16 + 2;           // 128-byte lines of the z range
-            const int ll = (OWN * a.N_c / T) / 16 + 2;
+            int ba, ta_;
+            split_item(a, (int)ga, ba, ta_);
+            const size_t zf = (size_t)ba * a.N_z + (size_t)ta_ * a.z_per_knot;   // approximate start is fine
+            const size_t lf = (size_t)ba * a.N_c + (size_t)ta_ * a.c_per_knot;
+            const int zl = ((OWN + 1) * a.z_per_knot) / 16 + 2;                   // 128-byte lines of the z range
+            const int ll = (OWN * a.c_per_knot) / 16 + 2;
             if (lane < zl) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.z + zf + lane * 16));
             if ((MODE & DTO_MODE_H) && lane < ll) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.lam + lf + lane * 16));
         }
@@ -143,12 +153,12 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
 
     // ---- compute phase: one item per lane ----
     {
-        const long long g = g0 + lane - (HALO ? 1 : 0);
+        const int g = g0 + lane - (HALO ? 1 : 0);
         const bool in = (g < g1) && (g >= g0 || (HALO && t0 > 0));
         if (in) {
             const bool own = g >= g0;
-            const int b = (int)(g / T);
-            const int t = (int)(g - (long long)b * T);
+            int b, t;
+            split_item(a, g, b, t);
             const int db = b - b0;
             const dto_knot_entry ke = load_knot(a.knot, t);
             const dto_knot_entry kn = load_knot(a.knot, t + 1);
@@ -193,13 +203,13 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
     constexpr bool HG = DO_H && (M::HG_NCLASS > 0);
     if (HG && a.use_hclass) {
         double v[M::HG_VMAX > 0 ? M::HG_VMAX : 1];
-        const long long g = g0 + lane - (HALO ? 1 : 0);
+        const int g = g0 + lane - (HALO ? 1 : 0);
         const bool own = (g < g1) && (g >= g0);
         int cls = -1;
         double* dst = nullptr;
+        int b = 0, t = 0;
         if (own) {
-            const int b = (int)(g / T);
-            const int t = (int)(g - (long long)b * T);
+            split_item(a, g, b, t);
             const dto_knot_entry ke = load_knot(a.knot, t);
             const double* ownp = sm + base[DTO_SEG_HTERM] + (b - b0) * L_h + (ke.hterm - k0.hterm);
             cls = ke.hclass;
@@ -213,8 +223,6 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
         // order (src/moi.jl:112-118), added in shared memory so H is written to HBM exactly once
         if (a.gen_nhess > 0) {
             if (own) {
-                const int b = (int)(g / T);
-                const int t = (int)(g - (long long)b * T);
                 const int p0 = __ldg(a.gh_ptr + t), p1 = __ldg(a.gh_ptr + t + 1);
                 const int khs = load_knot(a.knot, t).hslot;
                 for (int p = p0; p < p1; ++p) {
@@ -232,9 +240,9 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
     // ---- stream-out phase: per (problem) sub-tile, coalesced ----
     {
         int b = b0, ta = t0;
-        long long rem = g1 - g0;
+        int rem = g1 - g0;
         while (rem > 0) {
-            const int cnt = (rem < (long long)(T - ta)) ? (int)rem : (T - ta);
+            const int cnt = (rem < T - ta) ? rem : (T - ta);
             const int tb = ta + cnt;
             const int db = b - b0;
             const dto_knot_entry ea = load_knot(a.knot, ta);

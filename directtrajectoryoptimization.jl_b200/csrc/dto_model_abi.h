@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 8
+#define DTO_MODEL_ABI_VERSION 9
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -127,6 +127,10 @@ typedef struct dto_launch_args {
     /* filled by the model library at launch: how many warp tiles run concurrently on the device; a
      * starting warp prefetches (L2) the inputs of the tile that many positions ahead */
     int32_t tiles_in_flight;
+    /* division of a flat item index g < 2^31 by T without a divide: g / T == (g * div_mul) >> div_shift */
+    uint32_t div_mul;
+    int32_t div_shift;
+    int32_t z_per_knot, c_per_knot;  /* N_z / T, N_c / T (prefetch address estimate) */
 } dto_launch_args;
 
 enum { DTO_SEG_G = 0, DTO_SEG_CDYN = 1, DTO_SEG_CSTAGE = 2, DTO_SEG_JDYN = 3, DTO_SEG_JSTAGE = 4, DTO_SEG_HTERM = 5 };

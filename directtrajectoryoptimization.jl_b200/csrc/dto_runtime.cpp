@@ -679,6 +679,15 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
         a->seg_pad[k] = s->seg_pad[k];
     }
     a->use_hclass = s->use_hclass ? 1 : 0;
+    {   // magic number for g / T, exact for g < 2^31 (k = 31 + ceil(log2 T), M = ceil(2^k / T) < 2^32)
+        int lg = 0;
+        while ((1ll << lg) < s->T) ++lg;
+        const int k = 31 + lg;
+        a->div_shift = k;
+        a->div_mul = (uint32_t)((((unsigned __int128)1 << k) + (unsigned)s->T - 1) / (unsigned)s->T);
+        a->z_per_knot = (int32_t)(s->N_z / s->T);
+        a->c_per_knot = (int32_t)(s->N_c / s->T);
+    }
 }
 
 extern "C" int dto_shape_compiled_gather(const dto_shape* s) { return (s && s->use_hclass) ? 1 : 0; }
@@ -767,6 +776,11 @@ extern "C" int dto_batch_create(dto_shape* s, int64_t B, const int* devices, int
     }
     for (int dv : devs) DTO_REQUIRE(dv >= 0 && dv < count, "dto_batch_create: device %d not in [0,%d)", dv, count);
     DTO_REQUIRE(B * std::max<int64_t>(s->nnz_J, s->nnz_H) < (1ll << 40), "dto_batch_create: batch too large");
+    {
+        const int64_t nsh = ndev == 0 ? 1 : ndev;
+        DTO_REQUIRE(((B + nsh - 1) / nsh) * (int64_t)s->T < (1ll << 31) - 64,
+                    "dto_batch_create: %lld problems x %d knots per shard exceed 2^31 items; use more shards", (long long)((B + nsh - 1) / nsh), s->T);
+    }
 
     dto_batch* b = new (std::nothrow) dto_batch();
     if (!b) return fail(DTO_ERR_OOM, "dto_batch_create: out of host memory");
