@@ -373,6 +373,71 @@ def build_linear_general(api, T=11):
     )
 
 
+def build_heterogeneous(api, evaluate_hessian=True):
+    """Not from the reference's examples: a deliberately irregular problem that exercises what the
+    reference's data model allows: state/action dims change along the horizon,
+    every knot has its own Dynamics/Cost object, per-knot parameter vectors of different lengths in the
+    reference's vcat layout, nonlinear stage constraints with inequalities on some knots only, and a
+    nonlinear GeneralConstraint coupling distant knots."""
+    nx = [2, 2, 3, 3, 2, 2]
+    nu = [1, 2, 1, 1, 1, 0]
+    nw = [0, 1, 2, 0, 1, 1]
+    T = len(nx)
+
+    def make_dyn(t):
+        n0, m0, n1 = nx[t], nu[t], nx[t + 1]
+
+        def f(y, x, u, w):
+            out = []
+            for i in range(n1):
+                xi = x[i % n0]
+                uj = u[i % m0]
+                p = w[0] if nw[t] > 0 else 0.3
+                out.append(y[i] - (xi + 0.1 * (sin(xi * uj) + p * cos(y[i]) * x[(i + 1) % n0] ** 2 - 0.5 * uj)))
+            return arr(*out)
+
+        return api.Dynamics(f, n1, n0, m0, num_parameter=nw[t], evaluate_hessian=evaluate_hessian)
+
+    def make_cost(t):
+        def c(x, u, w):
+            v = 0.0
+            for i in range(nx[t]):
+                v = v + (0.5 + 0.1 * i) * x[i] ** 2 + 0.01 * x[i] ** 4
+            for j in range(nu[t]):
+                v = v + 0.2 * u[j] ** 2 + 0.05 * u[j] * x[0]
+            if nw[t] > 0:
+                v = v + w[nw[t] - 1] * x[0]
+            return v
+
+        return api.Cost(c, nx[t], nu[t], num_parameter=nw[t], evaluate_hessian=evaluate_hessian)
+
+    def make_con(t):
+        if t in (1, 4):
+            return api.Constraint()
+        if t == 2:
+            return api.Constraint(lambda x, u, w: arr(x[0] * x[1] - w[1], sin(u[0]) + x[2] ** 2 - 1.0), nx[t], nu[t],
+                                  num_parameter=nw[t], indices_inequality=[2], evaluate_hessian=evaluate_hessian)
+        if t == T - 1:
+            return api.Constraint(lambda x, u, w: arr(x[0] ** 2 + x[1] ** 2 - 1.0), nx[t], 0, num_parameter=nw[t],
+                                  evaluate_hessian=evaluate_hessian)
+        return api.Constraint(lambda x, u, w: arr(x[0] - 0.1 * u[0], x[1] * u[0]), nx[t], nu[t], num_parameter=nw[t],
+                              indices_inequality=[1, 2], evaluate_hessian=evaluate_hessian)
+
+    nz = sum(nx) + sum(nu)
+    npar = sum(nw)
+
+    def g(z, w):
+        return arr(z[0] * z[nz - 1] - 0.5, sin(z[3]) * z[7] + w[npar - 1] * z[1] ** 2, z[2] + z[5])
+
+    general = api.GeneralConstraint(g, nz, npar, indices_inequality=[2], evaluate_hessian=evaluate_hessian)
+    return dict(
+        name="heterogeneous", T=T, n=None, m=None, nx=nx, nu=nu, nw=nw,
+        dynamics=[make_dyn(t) for t in range(T - 1)], objective=[make_cost(t) for t in range(T)],
+        constraints=[make_con(t) for t in range(T)],
+        bounds=[api.Bound(nx[t], nu[t]) for t in range(T)], general=general, evaluate_hessian=evaluate_hessian,
+    )
+
+
 BUILDERS = {
     "pendulum": build_pendulum,
     "cartpole": build_cartpole,
@@ -380,4 +445,5 @@ BUILDERS = {
     "car": build_car,
     "acrobot_hessian_test": build_acrobot_hessian_test,
     "linear_general": build_linear_general,
+    "heterogeneous": build_heterogeneous,
 }

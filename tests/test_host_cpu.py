@@ -25,6 +25,7 @@ SHAPES = [
     ("car", dict(T=7, obstacle="stage")),
     ("acrobot_hessian_test", dict()),
     ("linear_general", dict(T=6)),
+    ("heterogeneous", dict()),
 ]
 
 

@@ -59,3 +59,49 @@ def test_callbacks_match_oracle(name, kw, B, config):
     assert_close("fused jacobian", J2, ref["J"])
     assert_close("fused hessian", H2, ref["H"])
     pn.close()
+
+
+def test_heterogeneous_problem_matches_oracle():
+    """Dims, element kinds and parameter lengths change from knot to knot, stage constraints exist on
+    some knots only, and a nonlinear GeneralConstraint couples distant knots (reference data model:
+    SURVEY Q1, Q7, Q10, Q11). Parameters use the reference's vcat(parameters...) layout."""
+    mo, mp = M.build_heterogeneous(O), M.build_heterogeneous(D)
+    B = 37
+    r = np.random.default_rng(99)
+    nw = mo["nw"]
+    psolver = D.Solver(mp["dynamics"], mp["objective"], mp["constraints"], mp["bounds"], evaluate_hessian=True,
+                       general_constraint=mp["general"], batch=B, name="heterogeneous")
+    pn = psolver.nlp
+    assert pn.num_parameter == sum(nw)
+    z = r.uniform(-1, 1, (B, pn.num_variables))
+    lam = r.normal(size=(B, pn.num_constraint))
+    sigma = r.uniform(0.2, 2.0, B)
+    w = r.uniform(-1, 1, (B, pn.num_parameter))
+    pn.set_parameters(w)
+    f = pn.eval_objective(z)
+    g = np.full((B, pn.num_variables), np.nan)
+    c = np.full((B, pn.num_constraint), np.nan)
+    J = np.full((B, pn.num_jacobian), np.nan)
+    H = np.full((B, pn.num_hessian), np.nan)
+    pn.eval_objective_gradient(g)
+    pn.eval_constraint(c)
+    pn.eval_constraint_jacobian(J)
+    pn.eval_hessian_lagrangian(H, None, sigma, lam)
+    J2, H2 = np.full_like(J, np.nan), np.full_like(H, np.nan)
+    pn.eval_jacobian_hessian(J2, H2, z, sigma, lam)
+    osolver = O.solver_from(mo, parameters=[np.zeros(n) for n in nw] + [np.zeros(0)])
+    on = osolver.nlp
+    assert pn.jacobian_structure() == on.jacobian_structure()
+    assert pn.hessian_lagrangian_structure() == on.hessian_lagrangian_structure()
+    off = np.concatenate([[0], np.cumsum(nw)])
+    for b in range(B):
+        osolver.set_parameters([w[b, off[t]:off[t + 1]] for t in range(len(nw))] + [np.zeros(0)])
+        assert_close("f", f[b], on.eval_objective(z[b]))
+        ref = np.zeros(pn.num_variables); on.eval_objective_gradient(ref, z[b]); assert_close("g", g[b], ref)
+        ref = np.zeros(pn.num_constraint); on.eval_constraint(ref, z[b]); assert_close("c", c[b], ref)
+        ref = np.zeros(pn.num_jacobian); on.eval_constraint_jacobian(ref, z[b]); assert_close("J", J[b], ref)
+        assert_close("J fused", J2[b], ref)
+        ref = np.zeros(pn.num_hessian); on.eval_hessian_lagrangian(ref, z[b], float(sigma[b]), lam[b])
+        assert_close("H", H[b], ref)
+        assert_close("H fused", H2[b], ref)
+    pn.close()
