@@ -46,7 +46,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 56, "ws_creg": 224}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -490,6 +490,7 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
     m.append(f"    static constexpr int MAX_NY = {max([e.n_out for e in spec.dyn] + [0])};")
     m.append(f"    static constexpr int MAX_NW = {max([e.nw for e in els_all] + [0])};")
     m.append(f"    static constexpr int MAX_NC = {max([e.n_out for e in spec.stage] + [0])};")
+    m.append(f"    static constexpr int N_KINDS_MAX = {max(len(spec.dyn), len(spec.cost), len(spec.stage))};")
     dyn_w = any(set(e.args["w"]) & set().union(*[x.free_symbols for x in e.evaluate]) for e in spec.dyn if len(e.args["w"]))
     m.append(f"    static constexpr bool DYN_USES_W = {'true' if dyn_w else 'false'};")
     for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
@@ -635,7 +636,7 @@ def spec_hash(spec: ModelSpec) -> str:
     h.update(_deriv_mode().encode())
     with open(os.path.join(PKG_DIR, "ir.py"), "rb") as f:
         h.update(f.read())
-    for fname in ("dto_kernels.cuh", "dto_model_abi.h"):
+    for fname in ("dto_kernels.cuh", "dto_kernel_ws.cuh", "dto_model_abi.h"):
         with open(os.path.join(CSRC_DIR, fname), "rb") as f:
             h.update(f.read())
 
@@ -675,7 +676,9 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
         raise RuntimeError(f"nvcc not found at {NVCC}: the CUDA model library cannot be built (no CPU fallback exists)")
     tune = _tuning()
     cmd = [NVCC, *NVCC_ARCH, f"-DDTO_WARPS={tune['warps']}", f"-DDTO_MIN_CTAS={tune['min_ctas']}",
-           f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", f"-DDTO_L2_PREFETCH={tune['l2_prefetch']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+           f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", f"-DDTO_L2_PREFETCH={tune['l2_prefetch']}",
+           f"-DDTO_PERSIST={tune['persist']}", f"-DDTO_PWARPS={tune['pwarps']}", f"-DDTO_PCTAS={tune['pctas']}",
+           f"-DDTO_WS={tune['ws']}", f"-DDTO_WS_HREG={tune['ws_hreg']}", f"-DDTO_WS_CREG={tune['ws_creg']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
            "-I", CSRC_DIR, "-o", so + ".tmp", cu]
     t1 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)

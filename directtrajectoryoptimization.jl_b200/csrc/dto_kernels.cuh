@@ -38,6 +38,28 @@
 #ifndef DTO_L2_PREFETCH
 #define DTO_L2_PREFETCH 1
 #endif
+#ifndef DTO_PERSIST
+#define DTO_PERSIST 1      /* use the persistent pipeline kernel when the shape allows */
+#endif
+#ifndef DTO_PWARPS
+#define DTO_PWARPS 12      /* warps per persistent CTA (upper bound; fewer are launched if shared memory is short) */
+#endif
+#ifndef DTO_PCTAS
+#define DTO_PCTAS 1        /* persistent CTAs per SM */
+#endif
+#ifndef DTO_KT_SMEM_MAX
+#define DTO_KT_SMEM_MAX 384  /* knot-table entries (64 B each) staged in shared memory */
+#endif
+#ifndef DTO_WS
+#define DTO_WS 1           /* use the warp-specialised kernel when the shape allows */
+#endif
+#ifndef DTO_WS_HREG
+#define DTO_WS_HREG 56     /* registers per helper-warp thread after setmaxnreg.dec */
+#endif
+#ifndef DTO_WS_CREG
+#define DTO_WS_CREG 224    /* registers per compute-warp thread after setmaxnreg.inc (HREG + 2*CREG <= 512) */
+#endif
+#define DTO_SMEM_LIMIT (227 * 1024)
 
 #define DTO_MODE_G 1
 #define DTO_MODE_C 2
@@ -303,6 +325,424 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------
+// persistent pipeline variant of the per-knot kernel (the default; knot_kernel above is the
+// fallback for shapes it does not cover). Same lane = item / warp = tile decomposition and the
+// same arithmetic, but:
+//   * one CTA per SM for the whole launch, each warp walks tiles gw, gw+stride, ...;
+//   * the knot table is staged in shared memory once per CTA;
+//   * a tile's inputs (z, sigma, w: one flat range each; dynamics / stage multipliers: one range
+//     per problem touched) are fetched one tile AHEAD by bulk async copies (cp.async.bulk, TMA
+//     engine) into a double-buffered per-warp staging area, completion on a per-warp mbarrier:
+//     the compute phase reads shared memory only, no HBM latency is exposed;
+//   * outputs leave by bulk async stores (shared -> global) issued by one lane per
+//     (segment, problem) piece, so the warp starts the next tile while they drain.
+// Bulk copies need 16-byte aligned addresses and sizes: every staged range is placed at
+// slot + (global_index & 1), i.e. with the parity of its global position, and the copy moves the
+// 16-byte aligned hull (inputs) or the aligned body plus at most two single stores (outputs).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// knot entry through a generic pointer (shared-memory copy or the global table)
+__device__ __forceinline__ dto_knot_entry ld_knot(const dto_knot_entry* tab, int t)
+{
+    const int4* p = reinterpret_cast<const int4*>(tab + t);
+    const int4 a = p[0], b = p[1], c = p[2], d = p[3];
+    dto_knot_entry e;
+    e.zofs = a.x; e.nx = a.y; e.wofs = a.z; e.kdyn = a.w;
+    e.kcost = b.x; e.kstage = b.y; e.rdyn = b.z; e.rstage = b.w;
+    e.jdyn = c.x; e.jstage = c.y; e.hterm = c.z; e.hslot = c.w;
+    e.hclass = d.x; e.hprev = d.y; e.pad0 = d.z; e.pad1 = d.w;
+    return e;
+}
+
+// the prefix-sum field of a knot entry that positions output segment s (HTERM: the slot prefix)
+__device__ __forceinline__ int seg_field(const dto_knot_entry& e, int s)
+{
+    return s == DTO_SEG_G ? e.zofs : s == DTO_SEG_CDYN ? e.rdyn : s == DTO_SEG_CSTAGE ? e.rstage : s == DTO_SEG_JDYN ? e.jdyn
+           : s == DTO_SEG_JSTAGE ? e.jstage : e.hslot;
+}
+
+// offset (relative to the segment base) of the value `kex` of item (db, b) in the parity-aligned
+// piece layout: piece db starts at even_up(flat start) + 2*db + parity of its global start ADDRESS
+// (pb = parity of the array base pointer in doubles)
+__device__ __forceinline__ int piece_off(int db, int b, int N_s, int pb, int k0x, int kbx, int kTx, int kex)
+{
+    const int eax = db == 0 ? k0x : kbx;
+    const int flat = db == 0 ? 0 : (kTx - k0x) + (db - 1) * (kTx - kbx);
+    return ((flat + 1) & ~1) + 2 * db + (((b & N_s) ^ eax ^ pb) & 1) + (kex - eax);
+}
+__device__ __forceinline__ int ptr_parity(const void* p) { return (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1); }
+
+struct tile_t {
+    int g0, g1, b0, t0, bl, tl, tf, nsub;
+};
+template <bool HALO>
+__device__ __forceinline__ tile_t tile_geom(const dto_launch_args& a, int tile, int total)
+{
+    constexpr int OWN = HALO ? 31 : 32;
+    tile_t q;
+    q.g0 = tile * OWN;
+    q.g1 = (q.g0 + OWN < total) ? q.g0 + OWN : total;
+    split_item(a, q.g0, q.b0, q.t0);
+    split_item(a, q.g1 - 1, q.bl, q.tl);
+    q.tf = q.t0 - ((HALO && q.t0 > 0) ? 1 : 0);
+    q.nsub = q.bl - q.b0 + 1;
+    return q;
+}
+struct item_t {
+    int b, t, db;
+    bool in, own;
+};
+template <bool HALO>
+__device__ __forceinline__ item_t tile_item(const dto_launch_args& a, const tile_t& q, int lane)
+{
+    item_t m;
+    const int g = q.g0 + lane - (HALO ? 1 : 0);
+    m.in = (g < q.g1) && (g >= q.g0 || (HALO && q.t0 > 0));
+    m.own = (g < q.g1) && (g >= q.g0);
+    m.b = q.b0;
+    m.t = q.t0;
+    if (m.in) split_item(a, g, m.b, m.t);
+    m.db = m.b - q.b0;
+    return m;
+}
+// make the compiler forget what it knows about v: everything derived from it afterwards is recomputed
+// instead of being kept live in registers across the FP64 section
+__device__ __forceinline__ void forget(int& v) { asm volatile("" : "+r"(v)); }
+
+template <int MODE>
+__host__ __device__ inline int p_layout(const dto_launch_args& a, int* base, int* ioff, int* in_sz)
+{
+    constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
+    int n = 0;
+    for (int k = 0; k < 5; ++k) {
+        const bool need = (k == DTO_IN_Z) || (k == DTO_IN_W && a.w_flat) || (DO_H && k != DTO_IN_W);
+        if (ioff) ioff[k] = n;
+        if (need) n += a.in_cap[k];
+    }
+    if (in_sz) *in_sz = n;
+    int off = 2 + 2 * n;  // two mbarriers, two input buffers
+    for (int s = 0; s < 6; ++s) {
+        if (seg_active<MODE>(s)) {
+            const int pad = (a.seg_pad[s] + 1) & ~1;
+            if (base) base[s] = off + pad;
+            off += pad + ((a.seg_cap[s] + 1) & ~1) + 2 * a.nsub_max + 2;
+        } else if (base) {
+            base[s] = 0;
+        }
+    }
+    return (off + 1) & ~1;
+}
+
+template <class M, int MODE>
+__global__ void __launch_bounds__(DTO_PWARPS * 32, DTO_PCTAS) knot_kernel_p(const __grid_constant__ dto_launch_args a)
+{
+    extern __shared__ __align__(16) double dto_smem[];
+    constexpr bool DO_G = (MODE & DTO_MODE_G) != 0, DO_C = (MODE & DTO_MODE_C) != 0;
+    constexpr bool DO_J = (MODE & DTO_MODE_J) != 0, DO_H = (MODE & DTO_MODE_H) != 0;
+    constexpr bool HALO = DO_H && (M::HESS_HALO != 0);
+    constexpr int OWN = HALO ? 31 : 32;
+    constexpr bool HG = DO_H && (M::HG_NCLASS > 0);
+    // bulk-stored segments, piece order = segment order (at most 3 per instantiated MODE, 8 problems each)
+    static_assert((DO_G ? 1 : 0) + (DO_C ? 2 : 0) + (DO_J ? 2 : 0) + (HG ? 1 : 0) <= 4, "piece map needs <= 4 segments per mode");
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int T = a.T;
+    const int total = (int)(a.B * T);  // the runtime guarantees B*T < 2^31 per shard
+    const int tiles = (total + OWN - 1) / OWN;
+
+    const int kt_doubles = a.kt_smem ? (T + 1) * 8 : 0;
+    if (a.kt_smem) {
+        const int4* src = reinterpret_cast<const int4*>(a.knot);
+        int4* dst = reinterpret_cast<int4*>(dto_smem);
+        for (int i = threadIdx.x; i < (T + 1) * 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const dto_knot_entry* tab = a.kt_smem ? reinterpret_cast<const dto_knot_entry*>(dto_smem) : a.knot;
+
+    int base[6], ioff[5], in_sz;
+    const int per_warp = p_layout<MODE>(a, base, ioff, &in_sz);
+    double* __restrict__ sm = dto_smem + kt_doubles + (size_t)wib * per_warp;
+    const uint32_t bar0 = smem_u32(sm);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    const bool hg_on = HG && a.use_hclass;
+    const int gw = blockIdx.x * nwarps + wib;
+    const int stride = gridDim.x * nwarps;
+    int it = -1;
+    int tile = gw - stride;
+    while (true) {
+        const int nxt = tile + stride;
+        const bool have_next = nxt < tiles;
+        // ---- producer: bulk-fetch the inputs of tile `nxt` into staging buffer (it+1)&1 ----
+        if (have_next) {
+            const tile_t q = tile_geom<HALO>(a, nxt, total);
+            const dto_knot_entry kT = ld_knot(tab, T);
+            double* ib = sm + 2 + ((it + 1) & 1) * in_sz;
+            const uint32_t bar = bar0 + ((it + 1) & 1) * 8;
+            const dto_knot_entry ktf = ld_knot(tab, q.tf);
+            const double* src = nullptr;
+            int len = 0, slot = 0;
+            if (lane == 0) {
+                const dto_knot_entry kl1 = ld_knot(tab, q.tl + 1);
+                src = a.z + (size_t)q.b0 * a.N_z + ktf.zofs;
+                len = (q.bl - q.b0) * a.N_z + kl1.zofs + (q.tl + 1 < T ? kl1.nx : 0) - ktf.zofs;
+                slot = ioff[DTO_IN_Z];
+            } else if (lane == 1) {
+                if (DO_H) {
+                    src = a.sigma + q.b0;
+                    len = q.nsub;
+                    slot = ioff[DTO_IN_SIGMA];
+                }
+            } else if (lane == 2) {
+                if (a.w_flat) {
+                    const dto_knot_entry kl = ld_knot(tab, q.tl);
+                    src = a.w + (size_t)q.b0 * a.N_w + ktf.wofs;
+                    len = (q.bl - q.b0) * a.N_w + kl.wofs + kl.pad0 - ktf.wofs;
+                    slot = ioff[DTO_IN_W];
+                }
+            } else if (DO_H) {
+                const int j = (lane - 3) >> 1, st = (lane - 3) & 1;
+                if (j < q.nsub) {
+                    const dto_knot_entry ea = ld_knot(tab, j == 0 ? q.tf : 0);
+                    const dto_knot_entry eb = ld_knot(tab, j == q.nsub - 1 ? q.tl + 1 : T);
+                    const int r0 = st ? ea.rstage : ea.rdyn, r1 = st ? eb.rstage : eb.rdyn;
+                    const int rT = st ? kT.rstage : kT.rdyn;
+                    const int Ls = st ? kT.rstage - kT.rdyn : kT.rdyn;  // rows per problem: stage rows follow the dynamics rows
+                    const int flat = j == 0 ? 0 : (rT - (st ? ktf.rstage : ktf.rdyn)) + (j - 1) * Ls;
+                    src = a.lam + (size_t)(q.b0 + j) * a.N_c + r0;
+                    len = r1 - r0;
+                    slot = ioff[st ? DTO_IN_LSTAGE : DTO_IN_LDYN] + ((flat + 1) & ~1) + 2 * j;
+                }
+            }
+            if (len > 0) {
+                const int mis = ptr_parity(src);  // the range lands at slot + mis: same 16-byte phase as in HBM
+                const uint32_t bytes = (uint32_t)((len + mis + 1) & ~1) * 8u;
+                mbar_expect_tx(bar, bytes);
+                bulk_load(smem_u32(ib + slot), src - mis, bytes, bar);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        }
+
+        // ---- consumer: tile `tile` from staging buffer it&1 ----
+        if (it >= 0) {
+            mbar_wait(bar0 + (it & 1) * 8, (it >> 1) & 1);  // this tile's inputs have landed
+            bulk_wait_read();                               // the previous tile's output staging has been read
+            __syncwarp();
+            {   // -- compute phase: one item per lane; only pointers derived here are live inside it
+                const tile_t q = tile_geom<HALO>(a, tile, total);
+                const item_t m = tile_item<HALO>(a, q, lane);
+                if (m.in) {
+                    const dto_knot_entry kb = ld_knot(tab, 0), kT = ld_knot(tab, T);
+                    const dto_knot_entry k0 = ld_knot(tab, q.t0), ktf = ld_knot(tab, q.tf), ke = ld_knot(tab, m.t);
+                    const double* __restrict__ ib = sm + 2 + (it & 1) * in_sz;
+                    const int b = m.b, db = m.db;
+                    const int kn_zofs = ld_knot(tab, m.t + 1).zofs;
+                    const double* __restrict__ x =
+                        ib + ioff[DTO_IN_Z] + (((q.b0 & a.N_z) ^ ktf.zofs ^ ptr_parity(a.z)) & 1) + db * a.N_z + (ke.zofs - ktf.zofs);
+                    const double* __restrict__ u = x + ke.nx;
+                    const double* __restrict__ y = x + (kn_zofs - ke.zofs);
+                    const double* __restrict__ w =
+                        a.w_flat ? ib + ioff[DTO_IN_W] + (((q.b0 & a.N_w) ^ ktf.wofs ^ ptr_parity(a.w)) & 1) + db * a.N_w + (ke.wofs - ktf.wofs)
+                                 : a.w + (size_t)b * a.N_w + ke.wofs;
+                    const double* __restrict__ lam_d = nullptr;
+                    const double* __restrict__ lam_s = nullptr;
+                    if (DO_H) {
+                        const int pl = ptr_parity(a.lam);
+                        lam_d = ib + ioff[DTO_IN_LDYN] + piece_off(db, b, a.N_c, pl, ktf.rdyn, kb.rdyn, kT.rdyn, ke.rdyn);
+                        lam_s = ib + ioff[DTO_IN_LSTAGE] + piece_off(db, b, a.N_c, pl, ktf.rstage, kb.rstage, kT.rstage, ke.rstage);
+                    }
+                    double* hterm = sm + base[DTO_SEG_HTERM] + db * kT.hterm + (ke.hterm - k0.hterm);
+                    if (m.own) {
+                        if (DO_G)
+                            M::cost_grad(ke.kcost, x, u, w,
+                                         sm + base[DTO_SEG_G] + piece_off(db, b, a.N_z, ptr_parity(a.g), k0.zofs, kb.zofs, kT.zofs, ke.zofs));
+                        if (DO_H)
+                            M::cost_hess(ke.kcost, x, u, w, ib[ioff[DTO_IN_SIGMA] + ((q.b0 ^ ptr_parity(a.sigma)) & 1) + db], hterm);
+                    }
+                    if (DO_H) hterm += M::cost_nh(ke.kcost);
+                    if (ke.kdyn >= 0) {
+                        if (DO_C)
+                            M::dyn_res(ke.kdyn, y, x, u, w,
+                                       sm + base[DTO_SEG_CDYN] + piece_off(db, b, a.N_c, ptr_parity(a.c), k0.rdyn, kb.rdyn, kT.rdyn, ke.rdyn));
+                        double* jd = sm + base[DTO_SEG_JDYN] + piece_off(db, b, a.nnz_J, ptr_parity(a.J), k0.jdyn, kb.jdyn, kT.jdyn, ke.jdyn);
+                        if (DO_J && DO_H) M::dyn_jac_hess(ke.kdyn, y, x, u, w, lam_d, jd, hterm);
+                        else if (DO_J) M::dyn_jac(ke.kdyn, y, x, u, w, jd);
+                        else if (DO_H) M::dyn_hess(ke.kdyn, y, x, u, w, lam_d, hterm);
+                        if (DO_H) hterm += M::dyn_nh(ke.kdyn);
+                    }
+                    if (m.own && ke.kstage >= 0) {
+                        if (DO_C)
+                            M::stage_res(ke.kstage, x, u, w,
+                                         sm + base[DTO_SEG_CSTAGE] +
+                                             piece_off(db, b, a.N_c, ptr_parity(a.c), k0.rstage, kb.rstage, kT.rstage, ke.rstage));
+                        double* js =
+                            sm + base[DTO_SEG_JSTAGE] + piece_off(db, b, a.nnz_J, ptr_parity(a.J), k0.jstage, kb.jstage, kT.jstage, ke.jstage);
+                        if (DO_J && DO_H) M::stage_jac_hess(ke.kstage, x, u, w, lam_s, js, hterm);
+                        else if (DO_J) M::stage_jac(ke.kstage, x, u, w, js);
+                        else if (DO_H) M::stage_hess(ke.kstage, x, u, w, lam_s, hterm);
+                    }
+                }
+            }
+            forget(tile);
+            __syncwarp();
+
+            // ---- compiled Hessian gather: terms -> slot values, in place, parity-aligned pieces ----
+            if (hg_on) {
+                const tile_t q = tile_geom<HALO>(a, tile, total);
+                const item_t m = tile_item<HALO>(a, q, lane);
+                const dto_knot_entry kb = ld_knot(tab, 0), kT = ld_knot(tab, T);
+                const dto_knot_entry k0 = ld_knot(tab, q.t0), ke = ld_knot(tab, m.t);
+                double v[M::HG_VMAX > 0 ? M::HG_VMAX : 1];
+                double* dst = sm + base[DTO_SEG_HTERM] + piece_off(m.db, m.b, a.nnz_H, ptr_parity(a.H), k0.hslot, kb.hslot, kT.hslot, ke.hslot);
+                if (m.own) {
+                    const double* ownp = sm + base[DTO_SEG_HTERM] + m.db * kT.hterm + (ke.hterm - k0.hterm);
+                    M::hg_compute(ke.hclass, ownp, ownp - ke.hprev, v);
+                }
+                __syncwarp();
+                if (m.own) M::hg_store(ke.hclass, v, dst);
+                if (a.gen_nhess > 0) {
+                    __syncwarp();
+                    if (m.own) {
+                        const int b = m.b;
+                        const int p0 = __ldg(a.gh_ptr + m.t), p1 = __ldg(a.gh_ptr + m.t + 1);
+                        for (int p = p0; p < p1; ++p) {
+                            const int2 e = __ldg(reinterpret_cast<const int2*>(a.gh_ent) + p);  // slot, instance
+                            const int4 inst = __ldg(reinterpret_cast<const int4*>(a.gen_inst[2]) + e.y);
+                            const double val = M::gen_eval(2, inst.x, a.z + (size_t)b * a.N_z + inst.y, a.w + (size_t)b * a.N_w + inst.z,
+                                                           a.lam + (size_t)b * a.N_c + a.gen_row0 + inst.w);
+                            dst[e.x - ke.hslot] += val;
+                        }
+                    }
+                }
+            }
+            fence_async_smem();  // generic-proxy writes of this lane -> visible to the bulk-store engine
+            __syncwarp();
+
+            // ---- stream-out: one lane per (segment, problem) piece: lane = 8*segment + problem ----
+            {
+                const tile_t q = tile_geom<HALO>(a, tile, total);
+                const int si = lane >> 3, j = lane & 7;
+                int sg = -1;
+                {
+                    int c = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        if (seg_active<MODE>(k) && (k != DTO_SEG_HTERM || HG)) {
+                            if (c == si && (k != DTO_SEG_HTERM || hg_on)) sg = k;
+                            ++c;
+                        }
+                }
+                if (sg >= 0 && j < q.nsub) {
+                    const dto_knot_entry kb = ld_knot(tab, 0), kT = ld_knot(tab, T), k0 = ld_knot(tab, q.t0);
+                    const dto_knot_entry ea = ld_knot(tab, j == 0 ? q.t0 : 0);
+                    const dto_knot_entry eb = ld_knot(tab, j == q.nsub - 1 ? q.tl + 1 : T);
+                    const int x0 = seg_field(ea, sg);
+                    int len = seg_field(eb, sg) - x0;
+                    const bool isc = sg == DTO_SEG_CDYN || sg == DTO_SEG_CSTAGE, isj = sg == DTO_SEG_JDYN || sg == DTO_SEG_JSTAGE;
+                    const int N_s = sg == DTO_SEG_G ? a.N_z : isc ? a.N_c : isj ? a.nnz_J : a.nnz_H;
+                    double* arr = sg == DTO_SEG_G ? a.g : isc ? a.c : isj ? a.J : a.H;
+                    double* __restrict__ dst = arr + (size_t)(q.b0 + j) * N_s + x0;
+                    const int bs = sg == DTO_SEG_G ? base[0] : sg == DTO_SEG_CDYN ? base[1] : sg == DTO_SEG_CSTAGE ? base[2]
+                                   : sg == DTO_SEG_JDYN ? base[3] : sg == DTO_SEG_JSTAGE ? base[4] : base[5];
+                    const double* sp =
+                        sm + bs + piece_off(j, q.b0 + j, N_s, ptr_parity(arr), seg_field(k0, sg), seg_field(kb, sg), seg_field(kT, sg), x0);
+                    if (len > 0) {
+                        if (ptr_parity(dst)) {  // odd position: single head store
+                            *dst = *sp;
+                            ++dst; ++sp; --len;
+                        }
+                        if (len & 1) {
+                            dst[len - 1] = sp[len - 1];
+                            --len;
+                        }
+                        if (len > 0) bulk_store(dst, smem_u32(sp), (uint32_t)len * 8u);
+                    }
+                }
+                bulk_commit();
+            }
+            // ---- table-driven Hessian gather (shapes without compiled recipes): direct coalesced stores ----
+            if (DO_H && !hg_on) {
+                const tile_t q = tile_geom<HALO>(a, tile, total);
+                const int k0_hterm = ld_knot(tab, q.t0).hterm, L_h = ld_knot(tab, T).hterm;
+                int bq = q.b0, ta = q.t0;
+                int rem = q.g1 - q.g0;
+                while (rem > 0) {
+                    const int cnt = (rem < T - ta) ? rem : (T - ta);
+                    const dto_knot_entry ea = ld_knot(tab, ta);
+                    const dto_knot_entry eb = ld_knot(tab, ta + cnt);
+                    const double* __restrict__ smh = sm + base[DTO_SEG_HTERM] + (bq - q.b0) * L_h - k0_hterm;
+                    double* __restrict__ Hb = a.H + (size_t)bq * a.nnz_H;
+                    const int4* __restrict__ src4 = reinterpret_cast<const int4*>(a.hsrc4);
+                    for (int s = ea.hslot + lane; s < eb.hslot; s += 32) {
+                        const int4 q0 = __ldg(src4 + s);
+                        double acc = q0.x >= 0 ? smh[q0.x] : 0.0;
+                        if (q0.y >= 0) acc += smh[q0.y];
+                        if (q0.z >= 0) acc += smh[q0.z];
+                        if (q0.w >= 0) acc += smh[q0.w];
+                        Hb[s] = acc;
+                    }
+                    rem -= cnt;
+                    ++bq;
+                    ta = 0;
+                }
+                __syncwarp();
+            }
+        }
+        if (!have_next) break;
+        tile = nxt;
+        ++it;
+    }
+    bulk_wait_all();
+}
+
+#include "dto_kernel_ws.cuh"
+
+// ---------------------------------------------------------------------------------------
 // objective value: one warp per problem, lanes stride over knots, xor-shuffle tree
 // (/root/reference/src/costs.jl:49-56)
 // ---------------------------------------------------------------------------------------
@@ -358,6 +798,26 @@ inline int64_t knot_smem_bytes(const dto_launch_args& a)
     return (int64_t)smem_doubles_per_warp<MODE>(a, nullptr) * DTO_WARPS * (int64_t)sizeof(double);
 }
 
+// persistent kernel launch plan: warps per CTA and shared memory, or warps = 0 if the shape is not covered
+template <int MODE>
+inline int plan_persistent(dto_launch_args& b, int64_t* smem_out)
+{
+    if (!DTO_PERSIST || !b.persist_ok) return 0;
+    const int64_t per_warp = (int64_t)p_layout<MODE>(b, nullptr, nullptr, nullptr) * (int64_t)sizeof(double);
+    for (int kt = 1; kt >= 0; --kt) {
+        if (kt && b.T + 1 > DTO_KT_SMEM_MAX) continue;
+        const int64_t ktb = kt ? (int64_t)(b.T + 1) * 64 : 0;
+        int64_t nw = (DTO_SMEM_LIMIT / DTO_PCTAS - 1024 - ktb) / per_warp;
+        if (nw > DTO_PWARPS) nw = DTO_PWARPS;
+        if (nw >= 4 || (kt == 0 && nw >= 2)) {
+            b.kt_smem = kt;
+            *smem_out = ktb + nw * per_warp;
+            return (int)nw;
+        }
+    }
+    return 0;
+}
+
 template <class M, int MODE>
 inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
 {
@@ -366,6 +826,64 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
     const long long total = a.B * (long long)a.T;
     if (total == 0) return 0;
     const long long warps = (total + own - 1) / own;
+    dto_launch_args b = a;
+    b.tiles_in_flight = 0;
+    {
+        const int64_t wsmem = plan_ws<M, MODE>(b);
+        if (wsmem > 0) {
+            static int sms[16] = {0};
+            static int64_t attr_smem[16] = {0};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev = (dev >= 0 && dev < 16) ? dev : 0;
+            if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+            if (wsmem > attr_smem[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(knot_kernel_ws<M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+                if (e != cudaSuccess) {
+                    fprintf(stderr, "[dto] cudaFuncSetAttribute(ws mode %d, smem %lld) failed: %s\n", MODE, (long long)wsmem, cudaGetErrorString(e));
+                    return (int)e;
+                }
+                attr_smem[dev] = wsmem;
+            }
+            long long ctas = (warps + DTO_WS_COMPUTE - 1) / DTO_WS_COMPUTE;
+            if (ctas > sms[dev]) ctas = sms[dev];
+            knot_kernel_ws<M, MODE><<<(unsigned)ctas, (DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, (size_t)wsmem, st>>>(b);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess)
+                fprintf(stderr, "[dto] knot_kernel_ws<mode %d> launch failed: %s (grid %lld, smem %lld)\n", MODE, cudaGetErrorString(e), ctas,
+                        (long long)wsmem);
+            return (int)e;
+        }
+    }
+    {
+        int64_t psmem = 0;
+        const int nw = plan_persistent<MODE>(b, &psmem);
+        if (nw > 0) {
+            static int sms[16] = {0};
+            static int64_t attr_smem[16] = {0};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            dev = (dev >= 0 && dev < 16) ? dev : 0;
+            if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+            if (psmem > attr_smem[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(knot_kernel_p<M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+                if (e != cudaSuccess) {
+                    fprintf(stderr, "[dto] cudaFuncSetAttribute(persistent mode %d, smem %lld) failed: %s\n", MODE, (long long)psmem,
+                            cudaGetErrorString(e));
+                    return (int)e;
+                }
+                attr_smem[dev] = psmem;
+            }
+            long long ctas = (warps + nw - 1) / nw;
+            if (ctas > (long long)sms[dev] * DTO_PCTAS) ctas = (long long)sms[dev] * DTO_PCTAS;
+            knot_kernel_p<M, MODE><<<(unsigned)ctas, nw * 32, (size_t)psmem, st>>>(b);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess)
+                fprintf(stderr, "[dto] knot_kernel_p<mode %d> launch failed: %s (grid %lld, block %d, smem %lld)\n", MODE,
+                        cudaGetErrorString(e), ctas, nw * 32, (long long)psmem);
+            return (int)e;
+        }
+    }
     const long long ctas = (warps + DTO_WARPS - 1) / DTO_WARPS;
     const int64_t smem = knot_smem_bytes<MODE>(a);
     if (smem > 48 * 1024) {  // opt in to large dynamic shared memory (per device, cheap)
@@ -375,8 +893,6 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
             return (int)e;
         }
     }
-    dto_launch_args b = a;
-    b.tiles_in_flight = 0;
 #if DTO_L2_PREFETCH
     {
         static int resident_warps[16] = {0};  // per device, for the shared-memory size it was computed with
@@ -448,14 +964,23 @@ inline int launch(int kernel_id, const dto_launch_args* pa, void* stream)
     }
 }
 
+template <int MODE>
+inline int64_t mode_smem_bytes(const dto_launch_args& a)
+{
+    dto_launch_args b = a;
+    int64_t ps = 0;
+    if (plan_persistent<MODE>(b, &ps) > 0) return ps;
+    return knot_smem_bytes<MODE>(a);  // (the warp-specialised plan needs the model type: see launch_knot)
+}
+
 inline int64_t smem_bytes(int kernel_id, const dto_launch_args* pa)
 {
     switch (kernel_id) {
-    case DTO_K_GRADIENT: return knot_smem_bytes<DTO_MODE_G>(*pa);
-    case DTO_K_CONSTRAINT: return knot_smem_bytes<DTO_MODE_C>(*pa);
-    case DTO_K_JACOBIAN: return knot_smem_bytes<DTO_MODE_J>(*pa);
-    case DTO_K_HESSIAN: return knot_smem_bytes<DTO_MODE_H>(*pa);
-    case DTO_K_JAC_HESS: return knot_smem_bytes<DTO_MODE_J | DTO_MODE_H>(*pa);
+    case DTO_K_GRADIENT: return mode_smem_bytes<DTO_MODE_G>(*pa);
+    case DTO_K_CONSTRAINT: return mode_smem_bytes<DTO_MODE_C>(*pa);
+    case DTO_K_JACOBIAN: return mode_smem_bytes<DTO_MODE_J>(*pa);
+    case DTO_K_HESSIAN: return mode_smem_bytes<DTO_MODE_H>(*pa);
+    case DTO_K_JAC_HESS: return mode_smem_bytes<DTO_MODE_J | DTO_MODE_H>(*pa);
     default: return 0;
     }
 }

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 9
+#define DTO_MODEL_ABI_VERSION 10
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -131,7 +131,16 @@ typedef struct dto_launch_args {
     uint32_t div_mul;
     int32_t div_shift;
     int32_t z_per_knot, c_per_knot;  /* N_z / T, N_c / T (prefetch address estimate) */
+    /* persistent pipeline kernel (knot_kernel_p): per-warp input staging capacities in doubles (even),
+     * index = DTO_IN_*; computed by the runtime over every possible tile start */
+    int32_t in_cap[5];
+    int32_t nsub_max;     /* most problems one 32-item tile can touch                              */
+    int32_t persist_ok;   /* shape is eligible for the persistent kernel (piece count fits a warp)  */
+    int32_t w_flat;       /* per-knot parameter slices are monotone: a tile's w is one flat range   */
+    int32_t kt_smem;      /* the model library sets it: knot table is staged in shared memory       */
 } dto_launch_args;
+
+enum { DTO_IN_Z = 0, DTO_IN_SIGMA = 1, DTO_IN_W = 2, DTO_IN_LDYN = 3, DTO_IN_LSTAGE = 4 };
 
 enum { DTO_SEG_G = 0, DTO_SEG_CDYN = 1, DTO_SEG_CSTAGE = 2, DTO_SEG_JDYN = 3, DTO_SEG_JSTAGE = 4, DTO_SEG_HTERM = 5 };
 

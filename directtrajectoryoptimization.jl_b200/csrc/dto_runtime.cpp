@@ -86,6 +86,9 @@ struct dto_shape {
     int32_t seg_cap[6] = {0, 0, 0, 0, 0, 0};
     int32_t seg_pad[6] = {0, 0, 0, 0, 0, 0};
     bool use_hclass = false;
+    int32_t in_cap[5] = {0, 0, 0, 0, 0};         // persistent kernel: input staging capacities per warp tile
+    int32_t nsub_max = 1;
+    bool persist_ok = false, w_flat = false;
 };
 
 struct dto_shard {
@@ -591,6 +594,42 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
             s->seg_pad[DTO_SEG_HTERM] = *std::max_element(sz[DTO_SEG_HTERM].begin(), sz[DTO_SEG_HTERM].end());
         }
     }
+    // ---- persistent pipeline kernel: input staging capacities, maximised over every tile start.
+    // A tile is at most 32 consecutive (b,t) items (31 own + halo, or 32 own); its z / sigma / w inputs
+    // are one flat range each, its dynamics / stage multipliers one range per problem touched.
+    {
+        std::vector<int32_t> nw(T);
+        bool mono = true;
+        for (int t = 0; t < T; ++t) {
+            nw[t] = s->knot[t].pad0;
+            if (t > 0 && (s->knot[t].wofs < s->knot[t - 1].wofs || s->knot[t].wofs + nw[t] < s->knot[t - 1].wofs + nw[t - 1])) mono = false;
+        }
+        s->w_flat = mono && s->N_w > 0;
+        int64_t cap[5] = {0, 0, 0, 0, 0};
+        int nsub_max = 1;
+        for (int tf = 0; tf < T; ++tf) {
+            int64_t zl = 0, ld = 0, ls = 0;
+            int nprob = 1, t = tf, tl = tf;
+            for (int i = 0; i < 32; ++i) {
+                zl += s->nx[t] + s->nu[t];
+                ld += s->knot[t + 1].rdyn - s->knot[t].rdyn;
+                ls += s->knot[t + 1].rstage - s->knot[t].rstage;
+                tl = t;
+                if (++t == T) { t = 0; if (i < 31) ++nprob; }
+            }
+            if (tl + 1 < T) zl += s->nx[tl + 1];
+            const int64_t wl = (int64_t)(nprob - 1) * s->N_w + s->knot[tl].wofs + nw[tl] - s->knot[tf].wofs;
+            cap[DTO_IN_Z] = std::max(cap[DTO_IN_Z], zl + 2);
+            cap[DTO_IN_SIGMA] = std::max<int64_t>(cap[DTO_IN_SIGMA], nprob + 2);
+            cap[DTO_IN_W] = std::max(cap[DTO_IN_W], s->w_flat ? wl + 2 : 0);
+            cap[DTO_IN_LDYN] = std::max(cap[DTO_IN_LDYN], ld + 3 * nprob + 2);
+            cap[DTO_IN_LSTAGE] = std::max(cap[DTO_IN_LSTAGE], ls + 3 * nprob + 2);
+            nsub_max = std::max(nsub_max, nprob);
+        }
+        for (int k = 0; k < 5; ++k) s->in_cap[k] = (int32_t)((cap[k] + 1) & ~(int64_t)1);
+        s->nsub_max = nsub_max;
+        s->persist_ok = nsub_max <= 8;
+    }
     guard.s = nullptr;
     *out = s;
     return DTO_OK;
@@ -679,6 +718,10 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
         a->seg_pad[k] = s->seg_pad[k];
     }
     a->use_hclass = s->use_hclass ? 1 : 0;
+    for (int k = 0; k < 5; ++k) a->in_cap[k] = s->in_cap[k];
+    a->nsub_max = s->nsub_max;
+    a->persist_ok = s->persist_ok ? 1 : 0;
+    a->w_flat = s->w_flat ? 1 : 0;
     {   // magic number for g / T, exact for g < 2^31 (k = 31 + ceil(log2 T), M = ceil(2^k / T) < 2^32)
         int lg = 0;
         while ((1ll << lg) < s->T) ++lg;
@@ -718,7 +761,8 @@ static int ensure_array(dto_batch* b, dto_shard& sh, int array)
     if (sh.arr[array]) return DTO_OK;
     const int64_t n = std::max<int64_t>(1, array_width(b->shape, array) * sh.size);
     DTO_CUDA(cudaSetDevice(sh.device));
-    DTO_CUDA(cudaMalloc((void**)&sh.arr[array], (size_t)n * sizeof(double)));
+    // +2 doubles: the persistent kernel's 16-byte bulk copies may touch one element past an odd-length array
+    DTO_CUDA(cudaMalloc((void**)&sh.arr[array], (size_t)(n + 2) * sizeof(double)));
     if (array == DTO_ARRAY_SIGMA) {
         std::vector<double> ones((size_t)n, 1.0);
         DTO_CUDA(cudaMemcpy(sh.arr[array], ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
