@@ -133,6 +133,7 @@ class ModelSpec:
     stage: List[ElementSpec]
     general: Optional[GeneralSpec] = None
     hg_classes: List[tuple] = field(default_factory=list)   # compiled gather recipes (recipes.py)
+    hg_meta: List[tuple] = field(default_factory=list)      # per class: (own cost terms, own dynamics terms, previous knot's cost terms)
 
 
 # ----------------------------------------------------------------------------- C printing
@@ -536,6 +537,38 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
     m.append("        default: break;")
     m.append("        }")
     m.append("    }")
+    # register-resident gather (warp-specialised kernel): own terms come from the per-role arrays the
+    # element functions just filled, previous-knot terms (always dynamics terms) from shared memory
+    maxc = max([e.nnz_hess for e in spec.cost] + [1])
+    maxd = max([e.nnz_hess for e in spec.dyn] + [1])
+    maxs = max([e.nnz_hess for e in spec.stage] + [1])
+    m.append(f"    static constexpr int MAXC = {maxc};")
+    m.append(f"    static constexpr int MAXD = {maxd};")
+    m.append(f"    static constexpr int MAXS = {maxs};")
+    m.append(f"    __device__ __forceinline__ static void hg_compute_r(int cls, const double (&tc)[{maxc}], const double (&td)[{maxd}], "
+             f"const double (&ts)[{maxs}], const double* __restrict__ prevd, double (&v)[{max(vmax, 1)}])")
+    m.append("    {")
+    m.append("        switch (cls) {")
+    for c, rec in enumerate(spec.hg_classes):
+        nc_, nd_, ncp_ = spec.hg_meta[c] if c < len(spec.hg_meta) else (0, 0, 0)
+
+        def _srcr(k, nc_=nc_, nd_=nd_, ncp_=ncp_):
+            if k >= 0:
+                if k < nc_:
+                    return f"tc[{k}]"
+                if k < nc_ + nd_:
+                    return f"td[{k - nc_}]"
+                return f"ts[{k - nc_ - nd_}]"
+            return f"prevd[{-k - 2 - ncp_}]"
+
+        m.append(f"        case {c}:")
+        for j, srcs in enumerate(rec):
+            terms = [_srcr(k) for k in srcs if k != -1]
+            m.append(f"            v[{j}] = {' + '.join(terms) if terms else '0.0'};")
+        m.append("            break;")
+    m.append("        default: break;")
+    m.append("        }")
+    m.append("    }")
     m += _dispatch("cost", len(spec.cost), "val", "double", "", "")
     m += _dispatch("cost", len(spec.cost), "grad", "void", ", double* __restrict__ G", ", G")
     m += _dispatch("cost", len(spec.cost), "hess", "void", ", const double sigma, double* __restrict__ H", ", sigma, H")
@@ -607,19 +640,20 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
     d.append(_int_array("hg_nslots", hg_ns))
     d.append(_int_array("hg_ofs", hg_of))
     d.append(_int_array("hg_src", [k for r in spec.hg_classes for srcs in r for k in srcs]))
+    d.append(_int_array("hg_meta", [v for c in range(len(spec.hg_classes)) for v in (spec.hg_meta[c] if c < len(spec.hg_meta) else (-1, -1, -1))]))
     fused = 0
     for k in range(len(spec.dyn)):
         fused = max(fused, stats.get(f"dyn{k}_jac_hess", 0))
     stats["ops_fused_per_knot"] = fused
     d.append(f"""
 static int model_launch(int kernel_id, const dto_launch_args* a, void* stream) {{ return dto::launch<DtoModel>(kernel_id, a, stream); }}
-static int64_t model_smem(int kernel_id, const dto_launch_args* a) {{ return dto::smem_bytes(kernel_id, a); }}
+static int64_t model_smem(int kernel_id, const dto_launch_args* a) {{ return dto::smem_bytes<DtoModel>(kernel_id, a); }}
 static const dto_model_vtable model_vtable = {{
     DTO_MODEL_ABI_VERSION, "{spec.name}", "{source_hash}",
     {len(spec.dyn)}, {len(spec.cost)}, {len(spec.stage)},
     dyn_descs, cost_descs, stage_descs, {"&gen_desc" if gen is not None else "nullptr"},
     {halo}, DTO_WARPS, {fused},
-    {len(spec.hg_classes)}, hg_nslots, hg_ofs, hg_src,
+    {len(spec.hg_classes)}, hg_nslots, hg_ofs, hg_src, hg_meta,
     model_launch, model_smem
 }};
 extern "C" __attribute__((visibility("default"))) const dto_model_vtable* dto_model_entry(void) {{ return &model_vtable; }}
@@ -651,6 +685,7 @@ def spec_hash(spec: ModelSpec) -> str:
         for el in els:
             feed_el(el)
     h.update(repr(spec.hg_classes).encode())
+    h.update(repr(spec.hg_meta).encode())
     if spec.general is not None:
         g = spec.general
         h.update(repr((g.num_variables, g.num_parameter, g.jac_rows, g.jac_cols, g.has_hess, g.hess_rows, g.hess_cols,

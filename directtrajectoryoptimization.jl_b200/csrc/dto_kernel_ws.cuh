@@ -22,8 +22,10 @@
 #define DTO_WS_DESC_DOUBLES 192  /* 3 x int4 per item, 32 items */
 #define DTO_WS_PIECE_DOUBLES 64  /* 1 x int4 per piece, 32 pieces */
 
+// yterms = doubles of the per-lane dynamics-term exchange buffer (32 * MAXD when a dynamics Hessian
+// reaches next-state rows, else 0); *yt_off receives its offset
 template <int MODE>
-__host__ __device__ inline int ws_layout(const dto_launch_args& a, int* base, int* ioff, int* in_sz, int* stage_sz)
+__host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, int* base, int* ioff, int* in_sz, int* stage_sz, int* yt_off)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
     int n = 0;
@@ -36,11 +38,15 @@ __host__ __device__ inline int ws_layout(const dto_launch_args& a, int* base, in
     const int st = n + DTO_WS_DESC_DOUBLES + DTO_WS_PIECE_DOUBLES;
     if (stage_sz) *stage_sz = st;
     int off = 4 + 2 * st;  // four mbarriers, two stages
+    if (yt_off) *yt_off = off;
+    off += (yterms + 1) & ~1;
     for (int s = 0; s < 6; ++s) {
         if (seg_active<MODE>(s)) {
-            const int pad = (a.seg_pad[s] + 1) & ~1;
+            // Hessian terms stay in registers here: the HTERM segment stages slot values only
+            const int pad = s == DTO_SEG_HTERM ? 0 : (a.seg_pad[s] + 1) & ~1;
+            const int cap = s == DTO_SEG_HTERM ? a.hslot_cap : a.seg_cap[s];
             if (base) base[s] = off + pad;
-            off += pad + ((a.seg_cap[s] + 1) & ~1) + 2 * a.nsub_max + 2;
+            off += pad + ((cap + 1) & ~1) + 2 * a.nsub_max + 2;
         } else if (base) {
             base[s] = 0;
         }
@@ -72,8 +78,9 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     }
     const dto_knot_entry* tab = a.kt_smem ? reinterpret_cast<const dto_knot_entry*>(dto_smem) : a.knot;
 
-    int base[6], ioff[5], in_sz, stage_sz;
-    const int per_warp = ws_layout<MODE>(a, base, ioff, &in_sz, &stage_sz);
+    constexpr int YTERMS = HALO ? 32 * M::MAXD : 0;
+    int base[6], ioff[5], in_sz, stage_sz, yt_off;
+    const int per_warp = ws_layout<MODE>(a, YTERMS, base, ioff, &in_sz, &stage_sz, &yt_off);
     if (warp >= DTO_WS_HELPERS && lane == 0) {
         const uint32_t bar = smem_u32(dto_smem + kt_doubles + (size_t)(warp - DTO_WS_HELPERS) * per_warp);
         mbar_init(bar, 1);
@@ -176,7 +183,6 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                     const int jd_off = DO_J ? base[DTO_SEG_JDYN] + piece_off(db, b, a.nnz_J, ptr_parity(a.J), k0.jdyn, kb.jdyn, kT.jdyn, ke.jdyn) : 0;
                     const int js_off =
                         DO_J ? base[DTO_SEG_JSTAGE] + piece_off(db, b, a.nnz_J, ptr_parity(a.J), k0.jstage, kb.jstage, kT.jstage, ke.jstage) : 0;
-                    const int ht_off = DO_H ? base[DTO_SEG_HTERM] + db * kT.hterm + (ke.hterm - k0.hterm) : 0;
                     const int hd_off =
                         DO_H ? base[DTO_SEG_HTERM] + piece_off(db, b, a.nnz_H, ptr_parity(a.H), k0.hslot, kb.hslot, kT.hslot, ke.hslot) : 0;
                     const int flags = (m.in ? 1 : 0) | (m.own ? 2 : 0);
@@ -188,8 +194,8 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                     d1.x = (ke.kcost & 255) | ((ke.kdyn & 255) << 8) | ((ke.kstage & 255) << 16) | ((ke.hclass & 255) << 24);
                     d1.y = g_off | (cd_off << 16);
                     d1.z = cs_off | (jd_off << 16);
-                    d1.w = js_off | (ht_off << 16);
-                    d2.x = hd_off | (ke.hprev << 16);
+                    d1.w = js_off;
+                    d2.x = hd_off;
                     d2.y = b;
                     d2.z = m.t;
                     d2.w = ke.hslot;
@@ -253,57 +259,54 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
             bulk_wait_read();                        // the previous tile's output staging has been read
             __syncwarp();
             {
-                const int4 d0 = dsc[lane], d1 = dsc[32 + lane];
+                const int4 d0 = dsc[lane], d1 = dsc[32 + lane], d2 = dsc[64 + lane];
                 const int flags = d0.w >> 16;
+                const bool own = (flags & 2) != 0;
+                // Hessian terms of this lane's knot, by role: registers (all indices are compile-time)
+                double tc[M::MAXC], td[M::MAXD], ts[M::MAXS];
+                double* yt = smc + yt_off + lane * M::MAXD;  // dynamics terms for the next lane's gather
                 if (flags & 1) {
-                    const bool own = (flags & 2) != 0;
                     const double* __restrict__ x = smc + (d0.x & 0xffff);
                     const double* __restrict__ u = x + (d0.x >> 16);
                     const double* __restrict__ y = smc + (d0.y & 0xffff);
                     const int kcost = d1.x & 255, kdyn = (d1.x >> 8) & 255, kstage = (d1.x >> 16) & 255;
                     const double* __restrict__ w = smc + ((unsigned)d0.y >> 16);
-                    if (!a.w_flat) w = a.w + (size_t)dsc[64 + lane].y * a.N_w + ((unsigned)d0.y >> 16);
+                    if (!a.w_flat) w = a.w + (size_t)d2.y * a.N_w + ((unsigned)d0.y >> 16);
                     const double* __restrict__ lam_d = smc + (d0.z & 0xffff);
                     const double* __restrict__ lam_s = smc + ((unsigned)d0.z >> 16);
-                    double* hterm = smc + ((unsigned)d1.w >> 16);
                     if (own) {
                         if (DO_G) M::cost_grad(kcost, x, u, w, smc + (d1.y & 0xffff));
-                        if (DO_H) M::cost_hess(kcost, x, u, w, smc[d0.w & 0xffff], hterm);
+                        if (DO_H) M::cost_hess(kcost, x, u, w, smc[d0.w & 0xffff], tc);
                     }
-                    if (DO_H) hterm += M::cost_nh(kcost);
                     if (kdyn != 255) {
                         if (DO_C) M::dyn_res(kdyn, y, x, u, w, smc + ((unsigned)d1.y >> 16));
                         double* jd = smc + ((unsigned)d1.z >> 16);
-                        if (DO_J && DO_H) M::dyn_jac_hess(kdyn, y, x, u, w, lam_d, jd, hterm);
+                        if (DO_J && DO_H) M::dyn_jac_hess(kdyn, y, x, u, w, lam_d, jd, td);
                         else if (DO_J) M::dyn_jac(kdyn, y, x, u, w, jd);
-                        else if (DO_H) M::dyn_hess(kdyn, y, x, u, w, lam_d, hterm);
-                        if (DO_H) hterm += M::dyn_nh(kdyn);
+                        else if (DO_H) M::dyn_hess(kdyn, y, x, u, w, lam_d, td);
+                        if (HALO) {
+#pragma unroll
+                            for (int i = 0; i < M::MAXD; ++i) yt[i] = td[i];
+                        }
                     }
                     if (own && kstage != 255) {
                         if (DO_C) M::stage_res(kstage, x, u, w, smc + (d1.z & 0xffff));
                         double* js = smc + (d1.w & 0xffff);
-                        if (DO_J && DO_H) M::stage_jac_hess(kstage, x, u, w, lam_s, js, hterm);
+                        if (DO_J && DO_H) M::stage_jac_hess(kstage, x, u, w, lam_s, js, ts);
                         else if (DO_J) M::stage_jac(kstage, x, u, w, js);
-                        else if (DO_H) M::stage_hess(kstage, x, u, w, lam_s, hterm);
+                        else if (DO_H) M::stage_hess(kstage, x, u, w, lam_s, ts);
                     }
                 }
-            }
-            __syncwarp();
-            if (hg_on) {
-                const int4 d0 = dsc[lane], d1 = dsc[32 + lane], d2 = dsc[64 + lane];
-                const bool own = ((d0.w >> 16) & 2) != 0;
-                const int hclass = (int)((unsigned)d1.x >> 24);
-                double v[M::HG_VMAX > 0 ? M::HG_VMAX : 1];
-                double* dst = smc + (d2.x & 0xffff);
-                if (own) {
-                    const double* ownp = smc + ((unsigned)d1.w >> 16);
-                    M::hg_compute(hclass, ownp, ownp - ((unsigned)d2.x >> 16), v);
-                }
-                __syncwarp();
-                if (own) M::hg_store(hclass, v, dst);
-                if (a.gen_nhess > 0) {
-                    __syncwarp();
-                    if (own) {
+                if (HALO) __syncwarp();
+                // Hessian slots of this lane's knot: own terms from registers + the previous knot's
+                // dynamics terms, summed in the reference's += order (src/moi.jl:88-118)
+                if (hg_on && own) {
+                    const int hclass = (int)((unsigned)d1.x >> 24);
+                    double v[M::HG_VMAX > 0 ? M::HG_VMAX : 1];
+                    double* dst = smc + (d2.x & 0xffff);
+                    M::hg_compute_r(hclass, tc, td, ts, yt - M::MAXD, v);
+                    M::hg_store(hclass, v, dst);
+                    if (a.gen_nhess > 0) {
                         const int b = d2.y, t = d2.z;
                         const int p0 = __ldg(a.gh_ptr + t), p1 = __ldg(a.gh_ptr + t + 1);
                         for (int p = p0; p < p1; ++p) {
@@ -352,7 +355,8 @@ inline int64_t plan_ws(dto_launch_args& b)
     if (DO_H && !(M::HG_NCLASS > 0 && b.use_hclass)) return 0;     // table gather: other kernels
     if (M::N_KINDS_MAX >= 255 || M::HG_NCLASS >= 255) return 0;    // descriptor packs kinds in 8 bits
     if (!b.w_flat && b.N_w > 65535) return 0;
-    const int64_t per_warp = (int64_t)ws_layout<MODE>(b, nullptr, nullptr, nullptr, nullptr);
+    constexpr bool HALO = DO_H && (M::HESS_HALO != 0);
+    const int64_t per_warp = (int64_t)ws_layout<MODE>(b, HALO ? 32 * M::MAXD : 0, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (per_warp > 65535) return 0;                                // 16-bit region offsets
     for (int kt = 1; kt >= 0; --kt) {
         if (kt && b.T + 1 > DTO_KT_SMEM_MAX) continue;

@@ -964,23 +964,27 @@ inline int launch(int kernel_id, const dto_launch_args* pa, void* stream)
     }
 }
 
-template <int MODE>
+template <class M, int MODE>
 inline int64_t mode_smem_bytes(const dto_launch_args& a)
 {
     dto_launch_args b = a;
+    const int64_t ws = plan_ws<M, MODE>(b);
+    if (ws > 0) return ws;
     int64_t ps = 0;
     if (plan_persistent<MODE>(b, &ps) > 0) return ps;
-    return knot_smem_bytes<MODE>(a);  // (the warp-specialised plan needs the model type: see launch_knot)
+    return knot_smem_bytes<MODE>(a);
 }
 
+// dynamic shared memory of the kernel that launch<M>() would pick for kernel_id
+template <class M>
 inline int64_t smem_bytes(int kernel_id, const dto_launch_args* pa)
 {
     switch (kernel_id) {
-    case DTO_K_GRADIENT: return mode_smem_bytes<DTO_MODE_G>(*pa);
-    case DTO_K_CONSTRAINT: return mode_smem_bytes<DTO_MODE_C>(*pa);
-    case DTO_K_JACOBIAN: return mode_smem_bytes<DTO_MODE_J>(*pa);
-    case DTO_K_HESSIAN: return mode_smem_bytes<DTO_MODE_H>(*pa);
-    case DTO_K_JAC_HESS: return mode_smem_bytes<DTO_MODE_J | DTO_MODE_H>(*pa);
+    case DTO_K_GRADIENT: return mode_smem_bytes<M, DTO_MODE_G>(*pa);
+    case DTO_K_CONSTRAINT: return mode_smem_bytes<M, DTO_MODE_C>(*pa);
+    case DTO_K_JACOBIAN: return mode_smem_bytes<M, DTO_MODE_J>(*pa);
+    case DTO_K_HESSIAN: return mode_smem_bytes<M, DTO_MODE_H>(*pa);
+    case DTO_K_JAC_HESS: return mode_smem_bytes<M, DTO_MODE_J | DTO_MODE_H>(*pa);
     default: return 0;
     }
 }

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 10
+#define DTO_MODEL_ABI_VERSION 11
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -138,6 +138,7 @@ typedef struct dto_launch_args {
     int32_t persist_ok;   /* shape is eligible for the persistent kernel (piece count fits a warp)  */
     int32_t w_flat;       /* per-knot parameter slices are monotone: a tile's w is one flat range   */
     int32_t kt_smem;      /* the model library sets it: knot table is staged in shared memory       */
+    int32_t hslot_cap;    /* most Hessian slots 32 consecutive items own (slot staging of the ws kernel) */
 } dto_launch_args;
 
 enum { DTO_IN_Z = 0, DTO_IN_SIGMA = 1, DTO_IN_W = 2, DTO_IN_LDYN = 3, DTO_IN_LSTAGE = 4 };
@@ -163,6 +164,9 @@ typedef struct dto_model_vtable {
     const int32_t* hg_nslots;
     const int32_t* hg_ofs;
     const int32_t* hg_src;
+    /* per class: {own cost terms, own dynamics terms, cost terms of the previous knot}: a knot matches a
+     * class only if these agree too (the register-resident gather splits flat term ids by role) */
+    const int32_t* hg_meta;
     /* Enqueue kernel `kernel_id` (+ its general-constraint companion) on `stream`.
      * Returns 0 or a cudaError_t value. */
     int (*launch)(int kernel_id, const dto_launch_args* args, void* stream);

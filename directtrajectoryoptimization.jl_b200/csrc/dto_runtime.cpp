@@ -88,6 +88,7 @@ struct dto_shape {
     bool use_hclass = false;
     int32_t in_cap[5] = {0, 0, 0, 0, 0};         // persistent kernel: input staging capacities per warp tile
     int32_t nsub_max = 1;
+    int32_t hslot_cap = 0;
     bool persist_ok = false, w_flat = false;
 };
 
@@ -514,6 +515,9 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
             int found = -1;
             for (int c = 0; c < vt->n_hg_classes && found < 0; ++c) {
                 if (vt->hg_nslots[c] != s1 - s0) continue;
+                if (vt->hg_meta[3 * c] != hterm_cost[t] || vt->hg_meta[3 * c + 1] != hterm_dyn[t] ||
+                    vt->hg_meta[3 * c + 2] != (t > 0 ? hterm_cost[t - 1] : 0))
+                    continue;
                 const int32_t* src = vt->hg_src + 4 * (size_t)vt->hg_ofs[c];
                 bool same = true;
                 for (int32_t sl = s0; sl < s1 && same; ++sl)
@@ -587,7 +591,8 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         {   // the compiled gather writes slot values over the term buffer: size it for both
             std::vector<int32_t> nslot(T);
             for (int t = 0; t < T; ++t) nslot[t] = s->knot[t + 1].hslot - s->knot[t].hslot;
-            s->seg_cap[DTO_SEG_HTERM] = std::max(s->seg_cap[DTO_SEG_HTERM], cyclic_window_max(nslot, 32));
+            s->hslot_cap = cyclic_window_max(nslot, 32);
+            s->seg_cap[DTO_SEG_HTERM] = std::max(s->seg_cap[DTO_SEG_HTERM], s->hslot_cap);
         }
         if (m->vt->hess_halo) {
             s->seg_pad[DTO_SEG_JDYN] = *std::max_element(sz[DTO_SEG_JDYN].begin(), sz[DTO_SEG_JDYN].end());
@@ -722,6 +727,7 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
     a->nsub_max = s->nsub_max;
     a->persist_ok = s->persist_ok ? 1 : 0;
     a->w_flat = s->w_flat ? 1 : 0;
+    a->hslot_cap = s->hslot_cap;
     {   // magic number for g / T, exact for g < 2^31 (k = 31 + ceil(log2 T), M = ceil(2^k / T) < 2^32)
         int lg = 0;
         while ((1ll << lg) < s->T) ++lg;

@@ -344,13 +344,14 @@ class Solver:
         spec = ModelSpec(name=name, dyn=[e.spec for e in dyn_u], cost=[e.spec for e in cost_u],
                          stage=[e.spec for e in stage_u], general=general.spec if general else None)
         # compiled Hessian gather: the distinct per-knot recipes of THIS shape (a handful for any horizon)
-        from .recipes import classes_of, knot_recipes
+        from .recipes import classes_of, knot_meta, knot_recipes
         rec = knot_recipes(T, dyn_k, cost_k, stage_k, spec.dyn, spec.cost, spec.stage, spec.general)
         import os
         if rec is not None and os.environ.get("DTO_TABLE_GATHER", "0") != "1":
-            classes, _ = classes_of(rec)
+            classes, metas, _ = classes_of(rec, knot_meta(T, dyn_k, cost_k, stage_k, spec.dyn, spec.cost, spec.stage))
             if len(classes) <= 16 and max(len(c) for c in classes) <= 128:
                 spec.hg_classes = classes
+                spec.hg_meta = metas
         self.model = Model(spec, verbose=verbose)
 
         pdim = []

@@ -82,14 +82,31 @@ def knot_recipes(T: int, dyn_kind: Sequence[int], cost_kind: Sequence[int], stag
     return [tuple(x) for x in out]
 
 
-def classes_of(recipes: Sequence[Recipe]) -> Tuple[List[Recipe], List[int]]:
-    """Distinct recipes in order of first appearance, and the class id of every knot."""
+def knot_meta(T: int, dyn_kind: Sequence[int], cost_kind: Sequence[int], stage_kind: Sequence[int], dyn, cost, stage
+              ) -> List[Tuple[int, int, int]]:
+    """Per knot: (own cost terms, own dynamics terms, cost terms of the previous knot). With these a flat
+    term index of a recipe splits into (role, index inside the element), which is what the
+    register-resident gather of the warp-specialised kernel needs."""
+    nh_c = [cost[cost_kind[t]].nnz_hess for t in range(T)]
+    nh_d = [dyn[dyn_kind[t]].nnz_hess if t < T - 1 else 0 for t in range(T)]
+    return [(nh_c[t], nh_d[t], nh_c[t - 1] if t > 0 else 0) for t in range(T)]
+
+
+def classes_of(recipes: Sequence[Recipe], meta: Optional[Sequence[Tuple[int, int, int]]] = None):
+    """Distinct (recipe, meta) pairs in order of first appearance, and the class id of every knot.
+    Returns (classes, ids) without meta, (classes, metas, ids) with."""
     uniq: List[Recipe] = []
-    index: Dict[Recipe, int] = {}
+    metas: List[Tuple[int, int, int]] = []
+    index: Dict[tuple, int] = {}
     ids = []
-    for r in recipes:
-        if r not in index:
-            index[r] = len(uniq)
+    for t, r in enumerate(recipes):
+        key = (r, tuple(meta[t])) if meta is not None else (r,)
+        if key not in index:
+            index[key] = len(uniq)
             uniq.append(r)
-        ids.append(index[r])
-    return uniq, ids
+            if meta is not None:
+                metas.append(tuple(meta[t]))
+        ids.append(index[key])
+    if meta is None:
+        return uniq, ids
+    return uniq, metas, ids

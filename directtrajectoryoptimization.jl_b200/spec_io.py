@@ -150,13 +150,15 @@ def load_spec(doc: dict) -> ModelSpec:
                      general=_general(doc["general"]) if doc.get("general") else None)
     sh = doc.get("shape")
     if sh:
-        from .recipes import classes_of, knot_recipes
+        from .recipes import classes_of, knot_meta, knot_recipes
         rec = knot_recipes(sh["T"], sh["dynamics_kind"], sh["cost_kind"], sh["stage_kind"], spec.dyn, spec.cost, spec.stage,
                            spec.general)
         if rec is not None:
-            classes, _ = classes_of(rec)
+            classes, metas, _ = classes_of(rec, knot_meta(sh["T"], sh["dynamics_kind"], sh["cost_kind"], sh["stage_kind"],
+                                                          spec.dyn, spec.cost, spec.stage))
             if len(classes) <= 16 and max(len(c) for c in classes) <= 128:
                 spec.hg_classes = classes
+                spec.hg_meta = metas
     return spec
 
 
