@@ -12,20 +12,26 @@
 //     the Hessian slots (reference += order, src/moi.jl:88-118) and issue the bulk stores listed by
 //     the helper.
 // Helper h serves compute warps h and h+4 (all three live on SM sub-partition h, whose 512
-// registers per lane are split 40 + 232 + 232). Two input stages per compute warp, full/empty
-// mbarriers per stage; the output staging is single-buffered and guarded by
-// cp.async.bulk.wait_group.read.
+// registers per lane are split DTO_WS_HREG + 2 x DTO_WS_CREG). Per compute warp: two input stages
+// (mbarrier full[2]) and one or two output staging buffers (mbarriers out_full / out_empty), two when
+// shared memory allows. Round kk of a helper, per served compute warp: wait out_full(kk-2) -> issue
+// that tile's bulk stores -> produce tile kk into the input stage tile kk-2 just vacated -> wait for
+// the stores' shared-memory reads -> arrive out_empty. The compute warp only waits on full(k) and
+// out_empty(k - NOUT), both normally long since complete.
 #pragma once
 
 #define DTO_WS_COMPUTE 8
-#define DTO_WS_HELPERS 4
+#ifndef DTO_WS_HELPERS
+#define DTO_WS_HELPERS 4         /* 4: helper h serves compute warps h, h+4; 8: one helper per compute warp */
+#endif
 #define DTO_WS_DESC_DOUBLES 192  /* 3 x int4 per item, 32 items */
 #define DTO_WS_PIECE_DOUBLES 64  /* 1 x int4 per piece, 32 pieces */
 
 // yterms = doubles of the per-lane dynamics-term exchange buffer (32 * MAXD when a dynamics Hessian
 // reaches next-state rows, else 0); *yt_off receives its offset
 template <int MODE>
-__host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, int* base, int* ioff, int* in_sz, int* stage_sz, int* yt_off)
+__host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, int* base, int* ioff, int* in_sz, int* stage_sz, int* yt_off,
+                                         int* out0, int* out_sz)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
     int n = 0;
@@ -37,9 +43,11 @@ __host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, i
     if (in_sz) *in_sz = n;
     const int st = n + DTO_WS_DESC_DOUBLES + DTO_WS_PIECE_DOUBLES;
     if (stage_sz) *stage_sz = st;
-    int off = 4 + 2 * st;  // four mbarriers, two stages
+    int off = 8 + 2 * st;  // six mbarriers (8 doubles reserved), two input stages
     if (yt_off) *yt_off = off;
     off += (yterms + 1) & ~1;
+    const int out_begin = off;
+    if (out0) *out0 = off;
     for (int s = 0; s < 6; ++s) {
         if (seg_active<MODE>(s)) {
             // Hessian terms stay in registers here: the HTERM segment stages slot values only
@@ -51,7 +59,9 @@ __host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, i
             base[s] = 0;
         }
     }
-    return (off + 1) & ~1;
+    off = (off + 1) & ~1;
+    if (out_sz) *out_sz = off - out_begin;
+    return off;  // size with ONE output buffer; a second one adds *out_sz
 }
 
 template <class M, int MODE>
@@ -79,14 +89,13 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     const dto_knot_entry* tab = a.kt_smem ? reinterpret_cast<const dto_knot_entry*>(dto_smem) : a.knot;
 
     constexpr int YTERMS = HALO ? 32 * M::MAXD : 0;
-    int base[6], ioff[5], in_sz, stage_sz, yt_off;
-    const int per_warp = ws_layout<MODE>(a, YTERMS, base, ioff, &in_sz, &stage_sz, &yt_off);
+    int base[6], ioff[5], in_sz, stage_sz, yt_off, out0, out_sz;
+    const int NOUT = a.ws_nout;  // output staging buffers per compute warp (1 or 2)
+    const int per_warp1 = ws_layout<MODE>(a, YTERMS, base, ioff, &in_sz, &stage_sz, &yt_off, &out0, &out_sz);
+    const int per_warp = per_warp1 + (NOUT - 1) * out_sz;
     if (warp >= DTO_WS_HELPERS && lane == 0) {
         const uint32_t bar = smem_u32(dto_smem + kt_doubles + (size_t)(warp - DTO_WS_HELPERS) * per_warp);
-        mbar_init(bar, 1);
-        mbar_init(bar + 8, 1);
-        mbar_init(bar + 16, 1);
-        mbar_init(bar + 24, 1);
+        for (int i = 0; i < 6; ++i) mbar_init(bar + 8 * i, 1);  // full[2], out_full[2], out_empty[2]
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -96,154 +105,173 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     if (warp < DTO_WS_HELPERS) {
         // =============================== helper warp ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DTO_WS_HREG));
-        for (int k = 0;; ++k) {
+        for (int kk = 0;; ++kk) {
             bool any = false;
 #pragma unroll 1
             for (int ci = 0; ci < DTO_WS_COMPUTE / DTO_WS_HELPERS; ++ci) {
                 const int c = warp + ci * DTO_WS_HELPERS;
-                const int tile = blockIdx.x * DTO_WS_COMPUTE + c + k * stride;
-                if (tile >= tiles) continue;
+                const int tile0 = blockIdx.x * DTO_WS_COMPUTE + c;
+                const int tile = tile0 + kk * stride;                                // tile to produce
+                const bool have_drain = kk >= 2 && tile0 + (kk - 2) * stride < tiles;  // tile kk-2 to drain
+                const bool have_prod = tile < tiles;
+                if (!have_drain && !have_prod) continue;
                 any = true;
                 double* smc = dto_smem + kt_doubles + (size_t)c * per_warp;
                 const uint32_t bar0 = smem_u32(smc);
-                const int st = k & 1;
-                const uint32_t full = bar0 + st * 8, empty = bar0 + 16 + st * 8;
-                const int sbase = 4 + st * stage_sz;   // stage offset inside the region (doubles)
-                mbar_wait(empty, ((k >> 1) & 1) ^ 1);  // the compute warp released this stage (passes on first use)
-
-                const tile_t q = tile_geom<HALO>(a, tile, total);
-                const dto_knot_entry kb = ld_knot(tab, 0), kT = ld_knot(tab, T);
-                const dto_knot_entry k0 = ld_knot(tab, q.t0), ktf = ld_knot(tab, q.tf);
-                // ---- (1) bulk input copies, one lane per range ----
-                {
-                    const double* src = nullptr;
-                    int len = 0, slot = 0;
-                    if (lane == 0) {
-                        const dto_knot_entry kl1 = ld_knot(tab, q.tl + 1);
-                        src = a.z + (size_t)q.b0 * a.N_z + ktf.zofs;
-                        len = (q.bl - q.b0) * a.N_z + kl1.zofs + (q.tl + 1 < T ? kl1.nx : 0) - ktf.zofs;
-                        slot = ioff[DTO_IN_Z];
-                    } else if (lane == 1) {
-                        if (DO_H) {
-                            src = a.sigma + q.b0;
-                            len = q.nsub;
-                            slot = ioff[DTO_IN_SIGMA];
-                        }
-                    } else if (lane == 2) {
-                        if (a.w_flat) {
-                            const dto_knot_entry kl = ld_knot(tab, q.tl);
-                            src = a.w + (size_t)q.b0 * a.N_w + ktf.wofs;
-                            len = (q.bl - q.b0) * a.N_w + kl.wofs + kl.pad0 - ktf.wofs;
-                            slot = ioff[DTO_IN_W];
-                        }
-                    } else if (DO_H) {
-                        const int j = (lane - 3) >> 1, sg = (lane - 3) & 1;
-                        if (j < q.nsub) {
-                            const dto_knot_entry ea = ld_knot(tab, j == 0 ? q.tf : 0);
-                            const dto_knot_entry eb = ld_knot(tab, j == q.nsub - 1 ? q.tl + 1 : T);
-                            const int r0 = sg ? ea.rstage : ea.rdyn, r1 = sg ? eb.rstage : eb.rdyn;
-                            const int rT = sg ? kT.rstage : kT.rdyn;
-                            const int Ls = sg ? kT.rstage - kT.rdyn : kT.rdyn;  // rows per problem (stage rows follow the dynamics rows)
-                            const int flat = j == 0 ? 0 : (rT - (sg ? ktf.rstage : ktf.rdyn)) + (j - 1) * Ls;
-                            src = a.lam + (size_t)(q.b0 + j) * a.N_c + r0;
-                            len = r1 - r0;
-                            slot = ioff[sg ? DTO_IN_LSTAGE : DTO_IN_LDYN] + ((flat + 1) & ~1) + 2 * j;
-                        }
-                    }
+                const int st = kk & 1;  // input stage of tile kk and of tile kk-2
+                const uint32_t full = bar0 + st * 8;
+                const int sbase = 8 + st * stage_sz;  // stage offset inside the region (doubles)
+                const int od = (kk - 2) & (NOUT - 1), nd = (kk - 2) >> (NOUT - 1);  // output buffer / use count of tile kk-2 (NOUT is 1 or 2)
+                if (have_drain) {
+                    // ---- (0) tile kk-2 is complete in output buffer od: issue its stores (piece list of stage st)
+                    mbar_wait(bar0 + 16 + od * 8, nd & 1);
+                    const int4 pd = reinterpret_cast<const int4*>(smc + sbase + in_sz + DTO_WS_DESC_DOUBLES)[lane];
+                    int len = pd.w;
                     if (len > 0) {
-                        const int mis = ptr_parity(src);  // the range lands at slot + mis: same 16-byte phase as in HBM
-                        const uint32_t bytes = (uint32_t)((len + mis + 1) & ~1) * 8u;
-                        mbar_expect_tx(full, bytes);
-                        bulk_load(smem_u32(smc + sbase + slot), src - mis, bytes, full);
+                        double* dst = reinterpret_cast<double*>(((unsigned long long)(unsigned)pd.y << 32) | (unsigned long long)(unsigned)pd.x);
+                        const double* sp = smc + pd.z;
+                        if (ptr_parity(dst)) {  // odd position: single head store
+                            *dst = *sp;
+                            ++dst; ++sp; --len;
+                        }
+                        if (len & 1) {
+                            dst[len - 1] = sp[len - 1];
+                            --len;
+                        }
+                        if (len > 0) bulk_store(dst, smem_u32(sp), (uint32_t)len * 8u);
                     }
+                    bulk_commit();
+                    __syncwarp();  // every lane has read its piece before the stage is refilled
                 }
-                // ---- (2) item descriptors: everything the compute lane needs, as region offsets ----
-                {
-                    const item_t m = tile_item<HALO>(a, q, lane);
-                    const dto_knot_entry ke = ld_knot(tab, m.t);
-                    const int kn_zofs = ld_knot(tab, m.t + 1).zofs;
-                    const int b = m.b, db = m.db;
-                    const int x_off =
-                        sbase + ioff[DTO_IN_Z] + (((q.b0 & a.N_z) ^ ktf.zofs ^ ptr_parity(a.z)) & 1) + db * a.N_z + (ke.zofs - ktf.zofs);
-                    const int y_off = x_off + (kn_zofs - ke.zofs);
-                    const int w_off =
-                        a.w_flat ? sbase + ioff[DTO_IN_W] + (((q.b0 & a.N_w) ^ ktf.wofs ^ ptr_parity(a.w)) & 1) + db * a.N_w + (ke.wofs - ktf.wofs)
-                                 : ke.wofs;
-                    int ld_off = 0, ls_off = 0, sg_off = 0;
-                    if (DO_H) {
-                        const int pl = ptr_parity(a.lam);
-                        ld_off = sbase + ioff[DTO_IN_LDYN] + piece_off(db, b, a.N_c, pl, ktf.rdyn, kb.rdyn, kT.rdyn, ke.rdyn);
-                        ls_off = sbase + ioff[DTO_IN_LSTAGE] + piece_off(db, b, a.N_c, pl, ktf.rstage, kb.rstage, kT.rstage, ke.rstage);
-                        sg_off = sbase + ioff[DTO_IN_SIGMA] + ((q.b0 ^ ptr_parity(a.sigma)) & 1) + db;
-                    }
-                    const int g_off = DO_G ? base[DTO_SEG_G] + piece_off(db, b, a.N_z, ptr_parity(a.g), k0.zofs, kb.zofs, kT.zofs, ke.zofs) : 0;
-                    const int cd_off = DO_C ? base[DTO_SEG_CDYN] + piece_off(db, b, a.N_c, ptr_parity(a.c), k0.rdyn, kb.rdyn, kT.rdyn, ke.rdyn) : 0;
-                    const int cs_off =
-                        DO_C ? base[DTO_SEG_CSTAGE] + piece_off(db, b, a.N_c, ptr_parity(a.c), k0.rstage, kb.rstage, kT.rstage, ke.rstage) : 0;
-                    const int jd_off = DO_J ? base[DTO_SEG_JDYN] + piece_off(db, b, a.nnz_J, ptr_parity(a.J), k0.jdyn, kb.jdyn, kT.jdyn, ke.jdyn) : 0;
-                    const int js_off =
-                        DO_J ? base[DTO_SEG_JSTAGE] + piece_off(db, b, a.nnz_J, ptr_parity(a.J), k0.jstage, kb.jstage, kT.jstage, ke.jstage) : 0;
-                    const int hd_off =
-                        DO_H ? base[DTO_SEG_HTERM] + piece_off(db, b, a.nnz_H, ptr_parity(a.H), k0.hslot, kb.hslot, kT.hslot, ke.hslot) : 0;
-                    const int flags = (m.in ? 1 : 0) | (m.own ? 2 : 0);
-                    int4 d0, d1, d2;
-                    d0.x = x_off | (ke.nx << 16);
-                    d0.y = y_off | (w_off << 16);
-                    d0.z = ld_off | (ls_off << 16);
-                    d0.w = sg_off | (flags << 16);
-                    d1.x = (ke.kcost & 255) | ((ke.kdyn & 255) << 8) | ((ke.kstage & 255) << 16) | ((ke.hclass & 255) << 24);
-                    d1.y = g_off | (cd_off << 16);
-                    d1.z = cs_off | (jd_off << 16);
-                    d1.w = js_off;
-                    d2.x = hd_off;
-                    d2.y = b;
-                    d2.z = m.t;
-                    d2.w = ke.hslot;
-                    int4* dsc = reinterpret_cast<int4*>(smc + sbase + in_sz);
-                    dsc[lane] = d0;
-                    dsc[32 + lane] = d1;
-                    dsc[64 + lane] = d2;
-                }
-                // ---- (3) output piece list: lane = 8*segment + problem ----
-                {
-                    const int si = lane >> 3, j = lane & 7;
-                    int sg = -1;
+                if (have_prod) {
+                    const int ob = (kk & (NOUT - 1)) * out_sz;  // output buffer of tile kk: offset added to the segment bases
+                    const tile_t q = tile_geom<HALO>(a, tile, total);
+                    const int* tabw = reinterpret_cast<const int*>(tab);  // knot entry = 16 words
+                    // ---- (1) flat input ranges z / sigma / w: lanes 0..2 ----
                     {
-                        int cnt = 0;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r)
-                            if (seg_active<MODE>(r) && (r != DTO_SEG_HTERM || HG)) {
-                                if (cnt == si) sg = r;
-                                ++cnt;
+                        const double* src = nullptr;
+                        int len = 0, slot = 0;
+                        const int tfz = tabw[q.tf * 16 + 0], tfw = tabw[q.tf * 16 + 2];
+                        if (lane == 0) {
+                            const int e1z = tabw[(q.tl + 1) * 16 + 0], e1n = tabw[(q.tl + 1) * 16 + 1];
+                            src = a.z + (size_t)q.b0 * a.N_z + tfz;
+                            len = (q.bl - q.b0) * a.N_z + e1z + (q.tl + 1 < T ? e1n : 0) - tfz;
+                            slot = ioff[DTO_IN_Z];
+                        } else if (lane == 1) {
+                            if (DO_H) {
+                                src = a.sigma + q.b0;
+                                len = q.nsub;
+                                slot = ioff[DTO_IN_SIGMA];
                             }
+                        } else if (lane == 2) {
+                            if (a.w_flat) {
+                                src = a.w + (size_t)q.b0 * a.N_w + tfw;
+                                len = (q.bl - q.b0) * a.N_w + tabw[q.tl * 16 + 2] + tabw[q.tl * 16 + 14] - tfw;
+                                slot = ioff[DTO_IN_W];
+                            }
+                        }
+                        if (len > 0) {
+                            const int mis = ptr_parity(src);  // the range lands at slot + mis: same 16-byte phase as in HBM
+                            const uint32_t bytes = (uint32_t)((len + mis + 1) & ~1) * 8u;
+                            mbar_expect_tx(full, bytes);
+                            bulk_load(smem_u32(smc + sbase + slot), src - mis, bytes, full);
+                        }
                     }
-                    int4 pd = make_int4(0, 0, 0, 0);
-                    if (sg >= 0 && j < q.nsub) {
-                        const dto_knot_entry ea = ld_knot(tab, j == 0 ? q.t0 : 0);
-                        const dto_knot_entry eb = ld_knot(tab, j == q.nsub - 1 ? q.tl + 1 : T);
-                        const int x0 = seg_field(ea, sg);
-                        const int len = seg_field(eb, sg) - x0;
-                        const bool isc = sg == DTO_SEG_CDYN || sg == DTO_SEG_CSTAGE, isj = sg == DTO_SEG_JDYN || sg == DTO_SEG_JSTAGE;
-                        const int N_s = sg == DTO_SEG_G ? a.N_z : isc ? a.N_c : isj ? a.nnz_J : a.nnz_H;
-                        double* arr = sg == DTO_SEG_G ? a.g : isc ? a.c : isj ? a.J : a.H;
-                        double* dst = arr + (size_t)(q.b0 + j) * N_s + x0;
-                        const int bs = sg == DTO_SEG_G ? base[0] : sg == DTO_SEG_CDYN ? base[1] : sg == DTO_SEG_CSTAGE ? base[2]
-                                       : sg == DTO_SEG_JDYN ? base[3] : sg == DTO_SEG_JSTAGE ? base[4] : base[5];
-                        const int so =
-                            bs + piece_off(j, q.b0 + j, N_s, ptr_parity(arr), seg_field(k0, sg), seg_field(kb, sg), seg_field(kT, sg), x0);
-                        const unsigned long long dp = reinterpret_cast<unsigned long long>(dst);
-                        pd.x = (int)(unsigned)(dp & 0xffffffffull);
-                        pd.y = (int)(unsigned)(dp >> 32);
-                        pd.z = so;
-                        pd.w = len;
+                    // ---- (2) per (segment row, problem) ranges: lane = 4*row + j. Rows 0..5 are the output
+                    // segments (G, CDYN, CSTAGE, JDYN, JSTAGE, Hessian slots), rows 6,7 the dynamics / stage
+                    // multipliers. Each lane derives where its range starts in HBM and in the region; cst =
+                    // start - (prefix field of the range's first knot), so an item of that range sits at
+                    // cst + (its own prefix field).
+                    int cst = 0;
+                    {
+                        const int row = lane >> 2, j = lane & 3;
+                        const bool is_in = row >= 6;
+                        const bool active = is_in ? DO_H : (seg_active<MODE>(row) && (row != DTO_SEG_HTERM || HG));
+                        int4 pd = make_int4(0, 0, 0, 0);
+                        if (active && j < q.nsub) {
+                            const int wi = (0x76B98760u >> (4 * row)) & 15;  // word of the row's prefix field in a knot entry
+                            const int tfirst = is_in ? q.tf : q.t0;
+                            const int kfx = tabw[tfirst * 16 + wi], kTx = tabw[T * 16 + wi], kbx = tabw[wi];
+                            const int ea = j == 0 ? kfx : kbx;
+                            const int eb = tabw[(j == q.nsub - 1 ? q.tl + 1 : T) * 16 + wi];
+                            const int len = eb - ea;
+                            const bool isc = row == 1 || row == 2 || is_in, isj = row == 3 || row == 4;
+                            const int N_s = row == 0 ? a.N_z : isc ? a.N_c : isj ? a.nnz_J : a.nnz_H;
+                            const double* arr = row == 0 ? a.g : is_in ? a.lam : isc ? a.c : isj ? a.J : a.H;
+                            const double* gp = arr + (size_t)(q.b0 + j) * N_s + ea;
+                            const int par = ptr_parity(gp);
+                            const int flat = j == 0 ? 0 : (kTx - kfx) + (j - 1) * (kTx - kbx);
+                            const int sb = row == 0 ? base[0] : row == 1 ? base[1] : row == 2 ? base[2] : row == 3 ? base[3]
+                                           : row == 4 ? base[4] : row == 5 ? base[5] : row == 6 ? ioff[DTO_IN_LDYN] : ioff[DTO_IN_LSTAGE];
+                            const int start = (is_in ? sbase : ob) + sb + ((flat + 1) & ~1) + 2 * j + par;
+                            cst = start - ea;
+                            if (is_in) {
+                                if (len > 0) {
+                                    const uint32_t bytes = (uint32_t)((len + par + 1) & ~1) * 8u;
+                                    mbar_expect_tx(full, bytes);
+                                    bulk_load(smem_u32(smc + start - par), gp - par, bytes, full);
+                                }
+                            } else {
+                                const unsigned long long dp = reinterpret_cast<unsigned long long>(gp);
+                                pd.x = (int)(unsigned)(dp & 0xffffffffull);
+                                pd.y = (int)(unsigned)(dp >> 32);
+                                pd.z = start;
+                                pd.w = len;
+                            }
+                        }
+                        reinterpret_cast<int4*>(smc + sbase + in_sz + DTO_WS_DESC_DOUBLES)[lane] = pd;
                     }
-                    reinterpret_cast<int4*>(smc + sbase + in_sz + DTO_WS_DESC_DOUBLES)[lane] = pd;
+                    // ---- (3) item descriptors: region offsets of everything the compute lane touches ----
+                    {
+                        const item_t m = tile_item<HALO>(a, q, lane);
+                        const dto_knot_entry ke = ld_knot(tab, m.t);
+                        const int kn_zofs = tabw[(m.t + 1) * 16];
+                        const int db = m.db;
+                        const int tfz = tabw[q.tf * 16 + 0], tfw = tabw[q.tf * 16 + 2];
+                        const int x_off = sbase + ioff[DTO_IN_Z] + (((q.b0 & a.N_z) ^ tfz ^ ptr_parity(a.z)) & 1) + db * a.N_z + (ke.zofs - tfz);
+                        const int y_off = x_off + (kn_zofs - ke.zofs);
+                        const int w_off =
+                            a.w_flat ? sbase + ioff[DTO_IN_W] + (((q.b0 & a.N_w) ^ tfw ^ ptr_parity(a.w)) & 1) + db * a.N_w + (ke.wofs - tfw) : ke.wofs;
+                        const int g_off = __shfl_sync(0xffffffffu, cst, 0 * 4 + db) + ke.zofs;
+                        const int cd_off = __shfl_sync(0xffffffffu, cst, 1 * 4 + db) + ke.rdyn;
+                        const int cs_off = __shfl_sync(0xffffffffu, cst, 2 * 4 + db) + ke.rstage;
+                        const int jd_off = __shfl_sync(0xffffffffu, cst, 3 * 4 + db) + ke.jdyn;
+                        const int js_off = __shfl_sync(0xffffffffu, cst, 4 * 4 + db) + ke.jstage;
+                        const int hd_off = __shfl_sync(0xffffffffu, cst, 5 * 4 + db) + ke.hslot;
+                        const int ld_off = __shfl_sync(0xffffffffu, cst, 6 * 4 + db) + ke.rdyn;
+                        const int ls_off = __shfl_sync(0xffffffffu, cst, 7 * 4 + db) + ke.rstage;
+                        const int sg_off = sbase + ioff[DTO_IN_SIGMA] + ((q.b0 ^ ptr_parity(a.sigma)) & 1) + db;
+                        const int flags = (m.in ? 1 : 0) | (m.own ? 2 : 0);
+                        int4 d0, d1, d2;
+                        d0.x = x_off | (ke.nx << 16);
+                        d0.y = y_off | (w_off << 16);
+                        d0.z = DO_H ? (ld_off | (ls_off << 16)) : 0;
+                        d0.w = (DO_H ? sg_off : 0) | (flags << 16);
+                        d1.x = (ke.kcost & 255) | ((ke.kdyn & 255) << 8) | ((ke.kstage & 255) << 16) | ((ke.hclass & 255) << 24);
+                        d1.y = (DO_G ? g_off : 0) | ((DO_C ? cd_off : 0) << 16);
+                        d1.z = (DO_C ? cs_off : 0) | ((DO_J ? jd_off : 0) << 16);
+                        d1.w = DO_J ? js_off : 0;
+                        d2.x = DO_H ? hd_off : 0;
+                        d2.y = m.b;
+                        d2.z = m.t;
+                        d2.w = ke.hslot;
+                        int4* dsc = reinterpret_cast<int4*>(smc + sbase + in_sz);
+                        dsc[lane] = d0;
+                        dsc[32 + lane] = d1;
+                        dsc[64 + lane] = d2;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full);
+                }  // have_prod
+                if (have_drain) {
+                    bulk_wait_read();  // the stores of tile kk-2 have read their shared-memory source
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar0 + 32 + od * 8);  // out_empty: buffer od may be overwritten
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full);
             }
-            if (!any) break;
+            if (!any && kk >= 2) break;  // (a lone tile is produced in round 0 and drained in round 2)
         }
+        bulk_wait_all();
     } else {
         // =============================== compute warp ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DTO_WS_CREG));
@@ -254,10 +282,10 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
         int k = 0;
         for (int tile = blockIdx.x * DTO_WS_COMPUTE + c; tile < tiles; tile += stride, ++k) {
             const int st = k & 1;
-            const int4* dsc = reinterpret_cast<const int4*>(smc + 4 + st * stage_sz + in_sz);
-            mbar_wait(bar0 + st * 8, (k >> 1) & 1);  // inputs + descriptors of this tile are in the stage
-            bulk_wait_read();                        // the previous tile's output staging has been read
-            __syncwarp();
+            const int o = k & (NOUT - 1), no = k >> (NOUT - 1);
+            const int4* dsc = reinterpret_cast<const int4*>(smc + 8 + st * stage_sz + in_sz);
+            mbar_wait(bar0 + st * 8, (k >> 1) & 1);          // inputs + descriptors of this tile are in the stage
+            mbar_wait(bar0 + 32 + o * 8, (no & 1) ^ 1);      // output buffer o has been drained (passes on first use)
             {
                 const int4 d0 = dsc[lane], d1 = dsc[32 + lane], d2 = dsc[64 + lane];
                 const int flags = d0.w >> 16;
@@ -321,28 +349,8 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
             }
             fence_async_smem();  // this lane's generic-proxy writes -> visible to the bulk-store engine
             __syncwarp();
-            {   // stream-out from the helper's piece list
-                const int4 pd = reinterpret_cast<const int4*>(smc + 4 + st * stage_sz + in_sz + DTO_WS_DESC_DOUBLES)[lane];
-                int len = pd.w;
-                if (len > 0) {
-                    double* dst = reinterpret_cast<double*>(((unsigned long long)(unsigned)pd.y << 32) | (unsigned long long)(unsigned)pd.x);
-                    const double* sp = smc + pd.z;
-                    if (ptr_parity(dst)) {  // odd position: single head store
-                        *dst = *sp;
-                        ++dst; ++sp; --len;
-                    }
-                    if (len & 1) {
-                        dst[len - 1] = sp[len - 1];
-                        --len;
-                    }
-                    if (len > 0) bulk_store(dst, smem_u32(sp), (uint32_t)len * 8u);
-                }
-                bulk_commit();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 16 + st * 8);  // stage free for the helper
+            if (lane == 0) mbar_arrive(bar0 + 16 + o * 8);  // out_full: the helper streams the tile out and refills the stage
         }
-        bulk_wait_all();
     }
 }
 
@@ -351,19 +359,24 @@ template <class M, int MODE>
 inline int64_t plan_ws(dto_launch_args& b)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
-    if (!DTO_WS || !b.persist_ok) return 0;
+    if (!DTO_WS || !b.persist_ok || b.nsub_max > 4) return 0;   // (segment, problem) lane map: 8 rows x 4 problems
     if (DO_H && !(M::HG_NCLASS > 0 && b.use_hclass)) return 0;     // table gather: other kernels
     if (M::N_KINDS_MAX >= 255 || M::HG_NCLASS >= 255) return 0;    // descriptor packs kinds in 8 bits
     if (!b.w_flat && b.N_w > 65535) return 0;
     constexpr bool HALO = DO_H && (M::HESS_HALO != 0);
-    const int64_t per_warp = (int64_t)ws_layout<MODE>(b, HALO ? 32 * M::MAXD : 0, nullptr, nullptr, nullptr, nullptr, nullptr);
-    if (per_warp > 65535) return 0;                                // 16-bit region offsets
-    for (int kt = 1; kt >= 0; --kt) {
-        if (kt && b.T + 1 > DTO_KT_SMEM_MAX) continue;
-        const int64_t smem = (kt ? (int64_t)(b.T + 1) * 64 : 0) + per_warp * 8 * DTO_WS_COMPUTE;
-        if (smem <= DTO_SMEM_LIMIT - 1024) {
-            b.kt_smem = kt;
-            return smem;
+    int out_sz = 0;
+    const int64_t one = (int64_t)ws_layout<MODE>(b, HALO ? 32 * M::MAXD : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &out_sz);
+    for (int nout = 2; nout >= 1; --nout) {
+        const int64_t per_warp = one + (nout - 1) * (int64_t)out_sz;
+        if (per_warp > 65535) continue;  // 16-bit region offsets
+        for (int kt = 1; kt >= 0; --kt) {
+            if (kt && b.T + 1 > DTO_KT_SMEM_MAX) continue;
+            const int64_t smem = (kt ? (int64_t)(b.T + 1) * 64 : 0) + per_warp * 8 * DTO_WS_COMPUTE;
+            if (smem <= DTO_SMEM_LIMIT - 1024) {
+                b.kt_smem = kt;
+                b.ws_nout = nout;
+                return smem;
+            }
         }
     }
     return 0;

@@ -138,6 +138,7 @@ typedef struct dto_launch_args {
     int32_t persist_ok;   /* shape is eligible for the persistent kernel (piece count fits a warp)  */
     int32_t w_flat;       /* per-knot parameter slices are monotone: a tile's w is one flat range   */
     int32_t kt_smem;      /* the model library sets it: knot table is staged in shared memory       */
+    int32_t ws_nout;      /* the model library sets it: output staging buffers per compute warp (ws kernel) */
     int32_t hslot_cap;    /* most Hessian slots 32 consecutive items own (slot staging of the ws kernel) */
 } dto_launch_args;
 
