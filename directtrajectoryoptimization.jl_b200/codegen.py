@@ -46,7 +46,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 56, "ws_creg": 224, "ws_helpers": 4}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 232, "ws_helpers": 4, "ws_min_ops": 100}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -492,6 +492,8 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
     m.append(f"    static constexpr int MAX_NW = {max([e.nw for e in els_all] + [0])};")
     m.append(f"    static constexpr int MAX_NC = {max([e.n_out for e in spec.stage] + [0])};")
     m.append(f"    static constexpr int N_KINDS_MAX = {max(len(spec.dyn), len(spec.cost), len(spec.stage))};")
+    ops_fused = max([stats.get(f"dyn{k}_jac_hess", 0) for k in range(len(spec.dyn))] + [0])
+    m.append(f"    static constexpr int OPS_FUSED = {ops_fused};  // FP64 ops of the heaviest fused dynamics element")
     dyn_w = any(set(e.args["w"]) & set().union(*[x.free_symbols for x in e.evaluate]) for e in spec.dyn if len(e.args["w"]))
     m.append(f"    static constexpr bool DYN_USES_W = {'true' if dyn_w else 'false'};")
     for role, els in (("dyn", spec.dyn), ("cost", spec.cost), ("stage", spec.stage)):
@@ -545,8 +547,16 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
     m.append(f"    static constexpr int MAXC = {maxc};")
     m.append(f"    static constexpr int MAXD = {maxd};")
     m.append(f"    static constexpr int MAXS = {maxs};")
+    # previous-knot dynamics terms any class reads: fetched from the lane below by warp shuffles
+    prev_used = sorted({-k - 2 - (spec.hg_meta[c][2] if c < len(spec.hg_meta) else 0)
+                        for c, rec in enumerate(spec.hg_classes) for srcs in rec for k in srcs if k <= -2})
+    m.append(f"    __device__ __forceinline__ static void hg_prev_exchange(const double (&td)[{maxd}], double (&pd)[{maxd}])")
+    m.append("    {")
+    for i in prev_used:
+        m.append(f"        pd[{i}] = __shfl_up_sync(0xffffffffu, td[{i}], 1);")
+    m.append("    }")
     m.append(f"    __device__ __forceinline__ static void hg_compute_r(int cls, const double (&tc)[{maxc}], const double (&td)[{maxd}], "
-             f"const double (&ts)[{maxs}], const double* __restrict__ prevd, double (&v)[{max(vmax, 1)}])")
+             f"const double (&ts)[{maxs}], const double (&prevd)[{maxd}], double (&v)[{max(vmax, 1)}])")
     m.append("    {")
     m.append("        switch (cls) {")
     for c, rec in enumerate(spec.hg_classes):
@@ -714,7 +724,7 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
            f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", f"-DDTO_L2_PREFETCH={tune['l2_prefetch']}",
            f"-DDTO_PERSIST={tune['persist']}", f"-DDTO_PWARPS={tune['pwarps']}", f"-DDTO_PCTAS={tune['pctas']}",
            f"-DDTO_WS={tune['ws']}", f"-DDTO_WS_HREG={tune['ws_hreg']}", f"-DDTO_WS_CREG={tune['ws_creg']}",
-           f"-DDTO_WS_HELPERS={tune['ws_helpers']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+           f"-DDTO_WS_HELPERS={tune['ws_helpers']}", f"-DDTO_WS_MIN_OPS={tune['ws_min_ops']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
            "-I", CSRC_DIR, "-o", so + ".tmp", cu]
     t1 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -27,11 +27,8 @@
 #define DTO_WS_DESC_DOUBLES 192  /* 3 x int4 per item, 32 items */
 #define DTO_WS_PIECE_DOUBLES 64  /* 1 x int4 per piece, 32 pieces */
 
-// yterms = doubles of the per-lane dynamics-term exchange buffer (32 * MAXD when a dynamics Hessian
-// reaches next-state rows, else 0); *yt_off receives its offset
 template <int MODE>
-__host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, int* base, int* ioff, int* in_sz, int* stage_sz, int* yt_off,
-                                         int* out0, int* out_sz)
+__host__ __device__ inline int ws_layout(const dto_launch_args& a, int* base, int* ioff, int* in_sz, int* stage_sz, int* out0, int* out_sz)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
     int n = 0;
@@ -44,8 +41,6 @@ __host__ __device__ inline int ws_layout(const dto_launch_args& a, int yterms, i
     const int st = n + DTO_WS_DESC_DOUBLES + DTO_WS_PIECE_DOUBLES;
     if (stage_sz) *stage_sz = st;
     int off = 8 + 2 * st;  // six mbarriers (8 doubles reserved), two input stages
-    if (yt_off) *yt_off = off;
-    off += (yterms + 1) & ~1;
     const int out_begin = off;
     if (out0) *out0 = off;
     for (int s = 0; s < 6; ++s) {
@@ -88,10 +83,9 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     }
     const dto_knot_entry* tab = a.kt_smem ? reinterpret_cast<const dto_knot_entry*>(dto_smem) : a.knot;
 
-    constexpr int YTERMS = HALO ? 32 * M::MAXD : 0;
-    int base[6], ioff[5], in_sz, stage_sz, yt_off, out0, out_sz;
+    int base[6], ioff[5], in_sz, stage_sz, out0, out_sz;
     const int NOUT = a.ws_nout;  // output staging buffers per compute warp (1 or 2)
-    const int per_warp1 = ws_layout<MODE>(a, YTERMS, base, ioff, &in_sz, &stage_sz, &yt_off, &out0, &out_sz);
+    const int per_warp1 = ws_layout<MODE>(a, base, ioff, &in_sz, &stage_sz, &out0, &out_sz);
     const int per_warp = per_warp1 + (NOUT - 1) * out_sz;
     if (warp >= DTO_WS_HELPERS && lane == 0) {
         const uint32_t bar = smem_u32(dto_smem + kt_doubles + (size_t)(warp - DTO_WS_HELPERS) * per_warp);
@@ -292,7 +286,6 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                 const bool own = (flags & 2) != 0;
                 // Hessian terms of this lane's knot, by role: registers (all indices are compile-time)
                 double tc[M::MAXC], td[M::MAXD], ts[M::MAXS];
-                double* yt = smc + yt_off + lane * M::MAXD;  // dynamics terms for the next lane's gather
                 if (flags & 1) {
                     const double* __restrict__ x = smc + (d0.x & 0xffff);
                     const double* __restrict__ u = x + (d0.x >> 16);
@@ -312,10 +305,6 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                         if (DO_J && DO_H) M::dyn_jac_hess(kdyn, y, x, u, w, lam_d, jd, td);
                         else if (DO_J) M::dyn_jac(kdyn, y, x, u, w, jd);
                         else if (DO_H) M::dyn_hess(kdyn, y, x, u, w, lam_d, td);
-                        if (HALO) {
-#pragma unroll
-                            for (int i = 0; i < M::MAXD; ++i) yt[i] = td[i];
-                        }
                     }
                     if (own && kstage != 255) {
                         if (DO_C) M::stage_res(kstage, x, u, w, smc + (d1.z & 0xffff));
@@ -325,14 +314,17 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                         else if (DO_H) M::stage_hess(kstage, x, u, w, lam_s, ts);
                     }
                 }
-                if (HALO) __syncwarp();
+                // the previous knot's dynamics terms that feed this knot's rows come from the lane below
+                // (lane = consecutive items; with a halo, lane 0 is the item before the tile)
+                double pd[M::MAXD];
+                if (HALO) M::hg_prev_exchange(td, pd);
                 // Hessian slots of this lane's knot: own terms from registers + the previous knot's
                 // dynamics terms, summed in the reference's += order (src/moi.jl:88-118)
                 if (hg_on && own) {
                     const int hclass = (int)((unsigned)d1.x >> 24);
                     double v[M::HG_VMAX > 0 ? M::HG_VMAX : 1];
                     double* dst = smc + (d2.x & 0xffff);
-                    M::hg_compute_r(hclass, tc, td, ts, yt - M::MAXD, v);
+                    M::hg_compute_r(hclass, tc, td, ts, pd, v);
                     M::hg_store(hclass, v, dst);
                     if (a.gen_nhess > 0) {
                         const int b = d2.y, t = d2.z;
@@ -359,13 +351,15 @@ template <class M, int MODE>
 inline int64_t plan_ws(dto_launch_args& b)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
-    if (!DTO_WS || !b.persist_ok || b.nsub_max > 4) return 0;   // (segment, problem) lane map: 8 rows x 4 problems
+    if (!DTO_WS || !b.persist_ok || b.nsub_max > 4) return 0;
+    // light, HBM-bound work (models with few FP64 ops per knot; gradient / residual / Jacobian-only
+    // passes of any model): the plain kernel's occupancy wins (profiles/sweep_r01_s_per_kernel.jsonl)
+    if (!DO_H || M::OPS_FUSED < DTO_WS_MIN_OPS) return 0;   // (segment, problem) lane map: 8 rows x 4 problems
     if (DO_H && !(M::HG_NCLASS > 0 && b.use_hclass)) return 0;     // table gather: other kernels
     if (M::N_KINDS_MAX >= 255 || M::HG_NCLASS >= 255) return 0;    // descriptor packs kinds in 8 bits
     if (!b.w_flat && b.N_w > 65535) return 0;
-    constexpr bool HALO = DO_H && (M::HESS_HALO != 0);
     int out_sz = 0;
-    const int64_t one = (int64_t)ws_layout<MODE>(b, HALO ? 32 * M::MAXD : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &out_sz);
+    const int64_t one = (int64_t)ws_layout<MODE>(b, nullptr, nullptr, nullptr, nullptr, nullptr, &out_sz);
     for (int nout = 2; nout >= 1; --nout) {
         const int64_t per_warp = one + (nout - 1) * (int64_t)out_sz;
         if (per_warp > 65535) continue;  // 16-bit region offsets

@@ -54,10 +54,13 @@
 #define DTO_WS 1           /* use the warp-specialised kernel when the shape allows */
 #endif
 #ifndef DTO_WS_HREG
-#define DTO_WS_HREG 56     /* registers per helper-warp thread after setmaxnreg.dec */
+#define DTO_WS_HREG 40     /* registers per helper-warp thread after setmaxnreg.dec */
 #endif
 #ifndef DTO_WS_CREG
-#define DTO_WS_CREG 224    /* registers per compute-warp thread after setmaxnreg.inc (HREG + 2*CREG <= 512) */
+#define DTO_WS_CREG 232    /* registers per compute-warp thread after setmaxnreg.inc (HREG + 2*CREG <= 512) */
+#endif
+#ifndef DTO_WS_MIN_OPS
+#define DTO_WS_MIN_OPS 100 /* specialised / persistent kernels only for models with at least this many FP64 ops per knot */
 #endif
 #define DTO_SMEM_LIMIT (227 * 1024)
 
@@ -800,9 +803,9 @@ inline int64_t knot_smem_bytes(const dto_launch_args& a)
 
 // persistent kernel launch plan: warps per CTA and shared memory, or warps = 0 if the shape is not covered
 template <int MODE>
-inline int plan_persistent(dto_launch_args& b, int64_t* smem_out)
+inline int plan_persistent(dto_launch_args& b, int64_t* smem_out, int min_ops_ok = 1)
 {
-    if (!DTO_PERSIST || !b.persist_ok) return 0;
+    if (!DTO_PERSIST || !b.persist_ok || min_ops_ok == 0) return 0;
     const int64_t per_warp = (int64_t)p_layout<MODE>(b, nullptr, nullptr, nullptr) * (int64_t)sizeof(double);
     for (int kt = 1; kt >= 0; --kt) {
         if (kt && b.T + 1 > DTO_KT_SMEM_MAX) continue;
@@ -857,7 +860,7 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
     }
     {
         int64_t psmem = 0;
-        const int nw = plan_persistent<MODE>(b, &psmem);
+        const int nw = plan_persistent<MODE>(b, &psmem, (MODE & DTO_MODE_H) != 0 && M::OPS_FUSED >= DTO_WS_MIN_OPS);
         if (nw > 0) {
             static int sms[16] = {0};
             static int64_t attr_smem[16] = {0};
@@ -971,7 +974,7 @@ inline int64_t mode_smem_bytes(const dto_launch_args& a)
     const int64_t ws = plan_ws<M, MODE>(b);
     if (ws > 0) return ws;
     int64_t ps = 0;
-    if (plan_persistent<MODE>(b, &ps) > 0) return ps;
+    if (plan_persistent<MODE>(b, &ps, (MODE & DTO_MODE_H) != 0 && M::OPS_FUSED >= DTO_WS_MIN_OPS) > 0) return ps;
     return knot_smem_bytes<MODE>(a);
 }
 

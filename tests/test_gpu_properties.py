@@ -203,3 +203,43 @@ def test_table_gather_fallback_matches(monkeypatch):
     monkeypatch.delenv("DTO_TABLE_GATHER")
     pn = D.solver_from(M.build_acrobot(D, T=9), batch=3).nlp
     assert pn.compiled_gather()
+
+
+KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0"]
+VARIANT_MODELS = [("pendulum", dict(), 1), ("cartpole", dict(T=11), 2), ("acrobot", dict(T=9), 3),
+                  ("car", dict(T=12, obstacle="general"), 4)]
+
+
+@pytest.mark.parametrize("tune", KERNEL_VARIANTS)
+def test_kernel_variants_match_golden_and_each_other(tune, monkeypatch):
+    """The three per-knot kernels (plain one-tile-per-warp, persistent bulk-copy pipeline, warp-specialised)
+    run the same generated element code and the same += order, so they must agree with the golden
+    fixtures AND with the default selection to a few ulps (the compiler may contract a multiply of an
+    element term into the slot sum in one kernel and not in another, so not bit for bit), on batches
+    large enough for many tiles that straddle problem boundaries. DTO_TUNE forces: the plain kernel everywhere / the persistent kernel
+    for every Hessian pass / the specialised kernel for every Hessian pass (also of light models)."""
+    for name, kw, config in VARIANT_MODELS:
+        fx = np.load(os.path.join(HERE, tag(name, kw) + ".npz"))
+        B0 = fx["z"].shape[0]
+        reps = 40  # B0*reps problems: dozens of warp tiles
+        z, lam, sigma, w = (np.tile(fx[k], (reps,) + (1,) * (fx[k].ndim - 1)) for k in ("z", "lam", "sigma", "w"))
+        res = {}
+        for t in ("", tune):
+            if t:
+                monkeypatch.setenv("DTO_TUNE", t)
+            else:
+                monkeypatch.delenv("DTO_TUNE", raising=False)
+            pn = D.solver_from(M.BUILDERS[name](D, **kw), batch=B0 * reps).nlp
+            out = _eval_all(pn, z, lam, sigma, w)
+            J2, H2 = np.full_like(out["J"], np.nan), np.full_like(out["H"], np.nan)
+            pn.eval_jacobian_hessian(J2, H2, z, sigma, lam)
+            out["J2"], out["H2"] = J2, H2
+            res[t] = out
+            pn.close()
+        monkeypatch.delenv("DTO_TUNE", raising=False)
+        for k in ("f", "g", "c", "J", "H"):
+            assert_close(f"{tune} {name} {k}", res[tune][k][:B0], fx[k])
+        for k in ("g", "c", "J", "H", "J2", "H2"):
+            assert_close(f"{tune} vs default {name} {k}", res[tune][k], res[""][k], rtol=1e-14, atol=1e-16)
+        assert_close(f"{tune} fused J {name}", res[tune]["J2"], res[tune]["J"], rtol=1e-14, atol=1e-16)
+        assert_close(f"{tune} fused H {name}", res[tune]["H2"], res[tune]["H"], rtol=1e-14, atol=1e-16)

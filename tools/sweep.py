@@ -19,6 +19,7 @@ from dto_b200.evaluator import K_JAC_HESS
 from examples import models as M
 from util import make_inputs
 build_only = %r
+KID = %d
 model = M.BUILDERS[%r](D, **%r)
 s = D.solver_from(model, batch=%d, verbose=build_only)
 if build_only: sys.exit(0)
@@ -31,16 +32,16 @@ for i, n in enumerate(nl):
     if n.num_parameter: n.set_parameters(w)
     n.set_x(z); n.set_duals(sig, lam); n.set_stream(st.cuda_stream)
 with torch.cuda.stream(st):
-    for i in range(10): nl[i %% 3].launch(K_JAC_HESS)
+    for i in range(10): nl[i %% 3].launch(KID)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    for i in range(200): nl[i %% 3].launch(K_JAC_HESS)
+    for i in range(200): nl[i %% 3].launch(KID)
     e1.record(st); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 200
 byt = n0.algorithmic_bytes_per_problem() * n0.batch
-print(json.dumps({"tune": os.environ.get("DTO_TUNE", ""), "model": %r, "ms": ms, "GBs": byt / ms / 1e6,
-                  "evals_per_s": n0.batch * n0.T / ms * 1e3, "smem": n0.kernel_smem_bytes(5)}))
+print(json.dumps({"tune": os.environ.get("DTO_TUNE", ""), "kernel": KID, "model": %r, "ms": ms, "GBs": byt / ms / 1e6,
+                  "evals_per_s": n0.batch * n0.T / ms * 1e3, "smem": n0.kernel_smem_bytes(KID)}))
 """
 
 
@@ -59,12 +60,16 @@ def main():
             if len(parts) > 2:
                 B = int(parts[2])
     tunes = TUNES
+    kid = 5
+    for a in sys.argv[1:]:
+        if a.startswith("--kernel="):
+            kid = int(a.split("=", 1)[1])
     for a in sys.argv[1:]:
         if a.startswith("--tunes="):
             tunes = a.split("=", 1)[1].split(";")
     for t in tunes:
         env = dict(os.environ, DTO_TUNE=t)
-        code = CHILD % (ROOT, ROOT, build_only, model, kw, B, model, model + repr(kw))
+        code = CHILD % (ROOT, ROOT, build_only, kid, model, kw, B, model, model + repr(kw))
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
         out = (r.stdout.strip().splitlines() or [""])[-1]
         print(out if r.returncode == 0 else f"FAILED {t}: {r.stderr[-500:]}", flush=True)
