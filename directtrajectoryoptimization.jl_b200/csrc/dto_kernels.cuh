@@ -24,6 +24,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+#include <vector>
+
 #include "dto_model_abi.h"
 
 #ifndef DTO_WARPS
@@ -58,6 +61,12 @@
 #endif
 #ifndef DTO_WS_CREG
 #define DTO_WS_CREG 232    /* registers per compute-warp thread after setmaxnreg.inc (HREG + 2*CREG <= 512) */
+#endif
+#ifndef DTO_WS_PLAN
+#define DTO_WS_PLAN 1      /* precomputed tile-plan table for the ws kernel (0: helpers compute every tile's records) */
+#endif
+#ifndef DTO_WS_ALL_MODES
+#define DTO_WS_ALL_MODES 0 /* 1: ws kernel also for the gradient / residual / Jacobian-only passes */
 #endif
 #ifndef DTO_WS_MIN_OPS
 #define DTO_WS_MIN_OPS 100 /* specialised / persistent kernels only for models with at least this many FP64 ops per knot */
@@ -850,6 +859,7 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
             }
             long long ctas = (warps + DTO_WS_COMPUTE - 1) / DTO_WS_COMPUTE;
             if (ctas > sms[dev]) ctas = sms[dev];
+            b.ws_plan = ws_get_plan<M, MODE>(b, st);
             knot_kernel_ws<M, MODE><<<(unsigned)ctas, (DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, (size_t)wsmem, st>>>(b);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess)

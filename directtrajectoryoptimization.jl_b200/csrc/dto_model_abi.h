@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 11
+#define DTO_MODEL_ABI_VERSION 12
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -138,6 +138,8 @@ typedef struct dto_launch_args {
     int32_t persist_ok;   /* shape is eligible for the persistent kernel (piece count fits a warp)  */
     int32_t w_flat;       /* per-knot parameter slices are monotone: a tile's w is one flat range   */
     int32_t kt_smem;      /* the model library sets it: knot table is staged in shared memory       */
+    int64_t shape_id;     /* unique per dto_shape in this process (key of the model library's tile-plan cache) */
+    const void* ws_plan;  /* the model library sets it: tile-plan table of the ws kernel (NULL: compute in-kernel) */
     int32_t ws_nout;      /* the model library sets it: output staging buffers per compute warp (ws kernel) */
     int32_t hslot_cap;    /* most Hessian slots 32 consecutive items own (slot staging of the ws kernel) */
 } dto_launch_args;

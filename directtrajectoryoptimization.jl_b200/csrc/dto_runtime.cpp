@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -89,6 +90,7 @@ struct dto_shape {
     int32_t in_cap[5] = {0, 0, 0, 0, 0};         // persistent kernel: input staging capacities per warp tile
     int32_t nsub_max = 1;
     int32_t hslot_cap = 0;
+    int64_t shape_id = 0;
     bool persist_ok = false, w_flat = false;
 };
 
@@ -635,6 +637,10 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         s->nsub_max = nsub_max;
         s->persist_ok = nsub_max <= 8;
     }
+    {
+        static std::atomic<int64_t> next_shape_id{1};
+        s->shape_id = next_shape_id.fetch_add(1);
+    }
     guard.s = nullptr;
     *out = s;
     return DTO_OK;
@@ -728,6 +734,7 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
     a->persist_ok = s->persist_ok ? 1 : 0;
     a->w_flat = s->w_flat ? 1 : 0;
     a->hslot_cap = s->hslot_cap;
+    a->shape_id = s->shape_id;
     {   // magic number for g / T, exact for g < 2^31 (k = 31 + ceil(log2 T), M = ceil(2^k / T) < 2^32)
         int lg = 0;
         while ((1ll << lg) < s->T) ++lg;

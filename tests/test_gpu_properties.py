@@ -205,7 +205,7 @@ def test_table_gather_fallback_matches(monkeypatch):
     assert pn.compiled_gather()
 
 
-KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0"]
+KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0,ws_all=1", "ws_min_ops=0,ws_plan=0"]
 VARIANT_MODELS = [("pendulum", dict(), 1), ("cartpole", dict(T=11), 2), ("acrobot", dict(T=9), 3),
                   ("car", dict(T=12, obstacle="general"), 4)]
 
