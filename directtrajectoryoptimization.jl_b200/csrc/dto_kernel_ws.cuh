@@ -509,9 +509,9 @@ inline const void* ws_get_plan(const dto_launch_args& b, cudaStream_t st)
     for (const ws_plan_entry& e : cache)
         if (e.shape_id == b.shape_id && e.mode == MODE && e.dev == dev && e.sig == sig) return e.ptr;
     if (cache.size() >= 128) {  // bounded: drop everything once nothing can still be reading it
-        cudaDeviceSynchronize();
         for (const ws_plan_entry& e : cache) {
             cudaSetDevice(e.dev);
+            cudaDeviceSynchronize();
             cudaFree(e.ptr);
         }
         cudaSetDevice(dev);
