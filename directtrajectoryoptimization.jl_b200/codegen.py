@@ -46,7 +46,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 232, "ws_helpers": 4, "ws_min_ops": 100, "ws_plan": 1, "ws_all": 0}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 232, "ws_helpers": 4, "ws_min_ops": 100, "ws_plan": 1, "ws_all": 0, "bf": 0}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -244,6 +244,54 @@ __device__ __forceinline__ double dto_powi(double x)
     else return x * dto_powi<K - 1>(x);
 }
 __device__ __forceinline__ double dto_sign(double x) { return (x > 0.0) - (x < 0.0); }
+
+// Branch-free sin/cos and reciprocal for the straight-line element programs (tune bf=1). Outside
+// their domain they set `bad`; the generated function then re-evaluates itself with the library
+// functions, so results stay defined for every double (NaN / Inf / huge arguments included).
+// sincos: Cody-Waite reduction by pi/2 in three FMA steps (|x| < 2^31), fdlibm kernel polynomials
+// (< 1 ulp on [-pi/4, pi/4]), quadrant by selects.
+__device__ __forceinline__ void dto_sincos_bf(double x, double* sp, double* cp, unsigned& bad)
+{
+    bad |= (unsigned)((__double2hiint(x) & 0x7fffffff) >= 0x41e00000);  // |x| >= 2^31, Inf, NaN
+    const int k = __double2int_rn(x * 0.63661977236758138);
+    const double kd = (double)k;
+    double r = fma(-kd, __longlong_as_double(0x3ff921fb54442d18LL), x);
+    r = fma(-kd, __longlong_as_double(0x3c91a62633145c00LL), r);
+    r = fma(-kd, __longlong_as_double(0x397b839a252049c0LL), r);
+    const double z = r * r;
+    const double v = z * r;
+    double p = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    p = fma(z, p, 2.75573137070700676789e-06);
+    p = fma(z, p, -1.98412698298579493134e-04);
+    p = fma(z, p, 8.33333333332248946124e-03);
+    const double sr = fma(v, fma(z, p, -1.66666666666666324348e-01), r);
+    double q = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    q = fma(z, q, -2.75573143513906633035e-07);
+    q = fma(z, q, 2.48015872894767294178e-05);
+    q = fma(z, q, -1.38888888888741095749e-03);
+    q = fma(z, q, 4.16666666666666019037e-02);
+    const double hz = 0.5 * z;
+    const double w1 = 1.0 - hz;
+    const double cr = w1 + (((1.0 - w1) - hz) + z * (z * q));
+    const double a = (k & 1) ? cr : sr;
+    const double b = (k & 1) ? sr : cr;
+    *sp = (k & 2) ? -a : a;
+    *cp = ((k + 1) & 2) ? -b : b;
+}
+// reciprocal: hardware seed (2^-23) + two Newton steps (~1 ulp); flags denormal / huge / non-finite
+__device__ __forceinline__ double dto_rcp_bf(double x, unsigned& bad)
+{
+    const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+    bad |= (unsigned)((e - 3u) > 2040u);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double t = fma(-x, r, 1.0);
+    r = fma(r, t, r);
+    t = fma(-x, r, 1.0);
+    r = fma(r, t, r);
+    t = fma(-x, r, 1.0);
+    return fma(r, t, r);
+}
 """
 
 
@@ -296,12 +344,21 @@ def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict, cpoo
     chunks: List[str] = []
 
     def fn(name, extra_sig, outputs, ret=None):
-        body = emit(g, outputs, load, cpool=cpool, order=_tuning().get("emit", 0))
         c = count_ops(g, [n for _, n in outputs])
         stats[f"{pre}_{name}"] = sum(v for kk, v in c.items())
         stats[f"{pre}_{name}_mix"] = c
         chunks.append(f"__device__ __forceinline__ {'double' if ret else 'void'} {pre}_{name}({sig}{extra_sig})\n{{")
-        chunks.extend(body)
+        use_bf = bool(_tuning().get("bf", 0)) and not ret and any(c.get(k_, 0) for k_ in ("sin", "cos", "rcp"))
+        if use_bf:
+            # fast path: one basic block; slow path (library sin/cos, IEEE division) only when an argument
+            # left the domain of the branch-free functions
+            chunks.append("    unsigned dto_bad = 0u;")
+            chunks.extend(emit(g, outputs, load, cpool=cpool, order=_tuning().get("emit", 0), bf=True))
+            chunks.append("    if (__builtin_expect(dto_bad != 0u, 0)) {")
+            chunks.extend(emit(g, outputs, load, indent="        ", prefix="s", cpool=cpool, order=_tuning().get("emit", 0)))
+            chunks.append("    }")
+        else:
+            chunks.extend(emit(g, outputs, load, cpool=cpool, order=_tuning().get("emit", 0)))
         if ret:
             chunks.append(f"    return {ret};")
         chunks.append("}\n")

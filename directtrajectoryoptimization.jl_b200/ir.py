@@ -431,9 +431,14 @@ def _needs_pool(v: float) -> bool:
 
 
 def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], str], indent: str = "    ",
-         prefix: str = "t", cpool: Optional[Dict[float, int]] = None, cname: str = "dto_k", order: int = 0) -> List[str]:
+         prefix: str = "t", cpool: Optional[Dict[float, int]] = None, cname: str = "dto_k", order: int = 0,
+         bf: bool = False) -> List[str]:
     """Straight-line C for the nodes reachable from `outputs` [(lhs, node)], DFS post-order in
-    output order (keeps live ranges short); sin/cos of one argument become one sincos()."""
+    output order (keeps live ranges short); sin/cos of one argument become one sincos().
+    bf=True: sin/cos/reciprocal use the branch-free device functions dto_sincos_bf / dto_rcp_bf, which
+    OR a flag into the local `dto_bad` when an argument is outside their domain (the caller then
+    re-evaluates with the library functions): the whole program becomes ONE basic block, so ptxas can
+    overlap the serial Horner / Newton chains with independent work."""
     name: Dict[int, str] = {}
     lines: List[str] = []
     need = set()
@@ -486,7 +491,10 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
             lines.append(f"{indent}const double {nm} = {ref(a[0])} * {ref(a[1])};")
         elif op == "rcp":
             name[n] = nm
-            lines.append(f"{indent}const double {nm} = 1.0 / {ref(a[0])};")
+            if bf:
+                lines.append(f"{indent}const double {nm} = dto_rcp_bf({ref(a[0])}, dto_bad);")
+            else:
+                lines.append(f"{indent}const double {nm} = 1.0 / {ref(a[0])};")
         elif op == "powi":
             name[n] = nm
             lines.append(f"{indent}const double {nm} = dto_powi<{g.val[n]}>({ref(a[0])});")
@@ -496,7 +504,14 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
         elif op in ("sin", "cos") and a[0] in paired:
             s, c = sin_of[a[0]], cos_of[a[0]]
             name[s], name[c] = f"{prefix}{s}", f"{prefix}{c}"
-            lines.append(f"{indent}double {name[s]}, {name[c]}; sincos({ref(a[0])}, &{name[s]}, &{name[c]});")
+            fnm = "dto_sincos_bf" if bf else "sincos"
+            tail = ", dto_bad" if bf else ""
+            lines.append(f"{indent}double {name[s]}, {name[c]}; {fnm}({ref(a[0])}, &{name[s]}, &{name[c]}{tail});")
+        elif op in ("sin", "cos") and bf:
+            name[n] = nm
+            other = f"{nm}_o"
+            args_ = f"&{nm}, &{other}" if op == "sin" else f"&{other}, &{nm}"
+            lines.append(f"{indent}double {nm}, {other}; dto_sincos_bf({ref(a[0])}, {args_}, dto_bad);")
         else:
             name[n] = nm
             lines.append(f"{indent}const double {nm} = {op}({ref(a[0])});")

@@ -205,7 +205,7 @@ def test_table_gather_fallback_matches(monkeypatch):
     assert pn.compiled_gather()
 
 
-KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0,ws_all=1", "ws_min_ops=0,ws_plan=0"]
+KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0,ws_all=1", "ws_min_ops=0,ws_plan=0", "ws_min_ops=0,bf=1"]
 VARIANT_MODELS = [("pendulum", dict(), 1), ("cartpole", dict(T=11), 2), ("acrobot", dict(T=9), 3),
                   ("car", dict(T=12, obstacle="general"), 4)]
 
@@ -239,7 +239,41 @@ def test_kernel_variants_match_golden_and_each_other(tune, monkeypatch):
         monkeypatch.delenv("DTO_TUNE", raising=False)
         for k in ("f", "g", "c", "J", "H"):
             assert_close(f"{tune} {name} {k}", res[tune][k][:B0], fx[k])
+        # same element code in every kernel: a few ulps; bf=1 swaps the sin/cos/reciprocal implementation
+        # (each < 1 ulp, but not the library's bits), so it is held to the oracle tolerance instead
+        rt, at = (1e-12, 1e-14) if "bf=1" in tune else (1e-14, 1e-16)
         for k in ("g", "c", "J", "H", "J2", "H2"):
-            assert_close(f"{tune} vs default {name} {k}", res[tune][k], res[""][k], rtol=1e-14, atol=1e-16)
+            assert_close(f"{tune} vs default {name} {k}", res[tune][k], res[""][k], rtol=rt, atol=at)
         assert_close(f"{tune} fused J {name}", res[tune]["J2"], res[tune]["J"], rtol=1e-14, atol=1e-16)
         assert_close(f"{tune} fused H {name}", res[tune]["H2"], res[tune]["H"], rtol=1e-14, atol=1e-16)
+
+
+def test_branch_free_math_falls_back_outside_its_domain(monkeypatch):
+    """DTO_TUNE=bf=1 replaces sin/cos/reciprocal inside the generated element programs by branch-free
+    versions (one basic block); arguments outside their domain (|angle| >= 2^31, NaN, Inf, reciprocals of
+    denormal / huge values) must re-evaluate with the library functions and give the default path's
+    values, problem by problem."""
+    name, kw = "cartpole", dict(T=11)
+    fx = np.load(os.path.join(HERE, tag(name, kw) + ".npz"))
+    z, lam, sigma, w = (np.tile(fx[k], (4,) + (1,) * (fx[k].ndim - 1)).copy() for k in ("z", "lam", "sigma", "w"))
+    z[1, 1] = 3.0e10       # pole angle far beyond 2^31 at knot 0
+    z[2, 6] = -7.5e12      # and at knot 1
+    z[3, 3] = np.nan
+    z[4, 11] = np.inf
+    z[5, 1] = 2.0 ** 31    # boundary of the fast path
+    res = {}
+    for t in ("", "ws_min_ops=0,bf=1"):
+        if t:
+            monkeypatch.setenv("DTO_TUNE", t)
+        else:
+            monkeypatch.delenv("DTO_TUNE", raising=False)
+        pn = D.solver_from(M.BUILDERS[name](D, **kw), batch=z.shape[0]).nlp
+        res[t] = _eval_all(pn, z, lam, sigma, w)
+        pn.close()
+    monkeypatch.delenv("DTO_TUNE", raising=False)
+    for k in ("c", "J", "H"):
+        a, b = res["ws_min_ops=0,bf=1"][k], res[""][k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{k}: NaN pattern differs"
+        fin = np.isfinite(b)
+        assert_close(f"bf=1 {k}", a[fin], b[fin], rtol=1e-12, atol=1e-14)
+    assert np.isfinite(res[""]["J"][1]).all() and np.isfinite(res[""]["H"][2]).all()
