@@ -230,6 +230,16 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ dto_l
     P[128 + lane] = piece;
 }
 
+// Option (off by default, DTO_WS_SPLIT_GEN): on light models leave the general-constraint Hessian entries
+// (dependent table / z / lambda loads from HBM per knot, which stall the two compute warps of a
+// sub-partition) to general_kernel<2> after the knot kernel. Measured slower than the fused single write
+// (car T=201: 306 vs 238 us, profiles/experiments/sweep_r01_y_split_general.jsonl).
+template <class M>
+__host__ __device__ constexpr bool ws_split_general()
+{
+    return DTO_WS_SPLIT_GEN != 0 && M::OPS_FUSED < DTO_WS_MIN_OPS;
+}
+
 template <class M, int MODE>
 __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) knot_kernel_ws(const __grid_constant__ dto_launch_args a)
 {
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                     double* dst = smc + d2.x + o * out_sz;
                     M::hg_compute_r(hclass, tc, td, ts, pd, v);
                     M::hg_store(hclass, v, dst);
-                    if (a.gen_nhess > 0) {
+                    if (a.gen_nhess > 0 && !ws_split_general<M>()) {
                         const int b = dsc[128].x + d2.y, t = d2.z;
                         const int p0 = __ldg(a.gh_ptr + t), p1 = __ldg(a.gh_ptr + t + 1);
                         for (int p = p0; p < p1; ++p) {

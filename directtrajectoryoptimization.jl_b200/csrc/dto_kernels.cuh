@@ -25,6 +25,7 @@
 #include <stdio.h>
 
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "dto_model_abi.h"
@@ -67,6 +68,9 @@
 #endif
 #ifndef DTO_WS_ALL_MODES
 #define DTO_WS_ALL_MODES 0 /* 1: ws kernel also for the gradient / residual / Jacobian-only passes */
+#endif
+#ifndef DTO_WS_SPLIT_GEN
+#define DTO_WS_SPLIT_GEN 0 /* 1: ws kernel on light models leaves the general-constraint Hessian to general_kernel<2> (measured slower: car 238 -> 306 us) */
 #endif
 #ifndef DTO_WS_MIN_OPS
 #define DTO_WS_MIN_OPS 100 /* specialised / persistent kernels only for models with at least this many FP64 ops per knot */
@@ -831,8 +835,9 @@ inline int plan_persistent(dto_launch_args& b, int64_t* smem_out, int min_ops_ok
 }
 
 template <class M, int MODE>
-inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
+inline int launch_knot(const dto_launch_args& a, cudaStream_t st, bool* used_ws)
 {
+    *used_ws = false;
     constexpr bool HALO = ((MODE & DTO_MODE_H) != 0) && (M::HESS_HALO != 0);
     const long long own = HALO ? 31 : 32;
     const long long total = a.B * (long long)a.T;
@@ -865,6 +870,7 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st)
             if (e != cudaSuccess)
                 fprintf(stderr, "[dto] knot_kernel_ws<mode %d> launch failed: %s (grid %lld, smem %lld)\n", MODE, cudaGetErrorString(e), ctas,
                         (long long)wsmem);
+            *used_ws = true;
             return (int)e;
         }
     }
@@ -944,36 +950,58 @@ inline int launch_general(const dto_launch_args& a, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+// Enqueue the kernels of one callback. Returns the number of kernels launched (>= 0) or minus the
+// cudaError_t of the first failure.
 template <class M>
 inline int launch(int kernel_id, const dto_launch_args* pa, void* stream)
 {
     const dto_launch_args& a = *pa;
     cudaStream_t st = (cudaStream_t)stream;
-    int e = 0;
+    int e = 0, n = 0;
+    bool ws = false;
+    auto general = [&](auto cls, int count) -> int {  // companion kernel over the general-constraint block
+        if (count <= 0 || a.B == 0) return 0;
+        if ((e = launch_general<M, decltype(cls)::value>(a, st))) return -e;
+        ++n;
+        return 0;
+    };
+    using C0 = std::integral_constant<int, 0>;
+    using C1 = std::integral_constant<int, 1>;
+    using C2 = std::integral_constant<int, 2>;
+    if (a.B == 0) return 0;
     switch (kernel_id) {
     case DTO_K_OBJECTIVE:
-        if (a.B == 0) return 0;
         objective_kernel<M><<<(unsigned)((a.B + DTO_WARPS - 1) / DTO_WARPS), DTO_WARPS * 32, 0, st>>>(a);
-        return (int)cudaGetLastError();
+        e = (int)cudaGetLastError();
+        return e ? -e : 1;
     case DTO_K_GRADIENT:
-        return launch_knot<M, DTO_MODE_G>(a, st);
+        e = launch_knot<M, DTO_MODE_G>(a, st, &ws);
+        return e ? -e : 1;
     case DTO_K_CONSTRAINT:
-        if ((e = launch_knot<M, DTO_MODE_C>(a, st))) return e;
-        return launch_general<M, 0>(a, st);
+        if ((e = launch_knot<M, DTO_MODE_C>(a, st, &ws))) return -e;
+        ++n;
+        if (general(C0{}, a.gen_nrow)) return -e;
+        return n;
     case DTO_K_JACOBIAN:
-        if ((e = launch_knot<M, DTO_MODE_J>(a, st))) return e;
-        return launch_general<M, 1>(a, st);
+        if ((e = launch_knot<M, DTO_MODE_J>(a, st, &ws))) return -e;
+        ++n;
+        if (general(C1{}, a.gen_njac)) return -e;
+        return n;
     case DTO_K_HESSIAN:
-        if ((e = launch_knot<M, DTO_MODE_H>(a, st))) return e;
-        if (M::HG_NCLASS > 0 && a.use_hclass) return 0;  // general Hessian fused into the knot kernel
-        return launch_general<M, 2>(a, st);
-    case DTO_K_JAC_HESS:
-        if ((e = launch_knot<M, DTO_MODE_J | DTO_MODE_H>(a, st))) return e;
-        if ((e = launch_general<M, 1>(a, st))) return e;
-        if (M::HG_NCLASS > 0 && a.use_hclass) return 0;
-        return launch_general<M, 2>(a, st);
+    case DTO_K_JAC_HESS: {
+        if (kernel_id == DTO_K_HESSIAN) e = launch_knot<M, DTO_MODE_H>(a, st, &ws);
+        else e = launch_knot<M, DTO_MODE_J | DTO_MODE_H>(a, st, &ws);
+        if (e) return -e;
+        ++n;
+        if (kernel_id == DTO_K_JAC_HESS && general(C1{}, a.gen_njac)) return -e;
+        // general-constraint Hessian: fused into the knot kernel when the compiled gather is in use, unless
+        // the ws kernel runs a light model (ws_split_general)
+        const bool fused = M::HG_NCLASS > 0 && a.use_hclass && !(ws && ws_split_general<M>());
+        if (!fused && general(C2{}, a.gen_nhess)) return -e;
+        return n;
+    }
     default:
-        return (int)cudaErrorInvalidValue;
+        return -(int)cudaErrorInvalidValue;
     }
 }
 

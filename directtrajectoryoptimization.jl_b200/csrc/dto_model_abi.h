@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 12
+#define DTO_MODEL_ABI_VERSION 13
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -170,8 +170,8 @@ typedef struct dto_model_vtable {
     /* per class: {own cost terms, own dynamics terms, cost terms of the previous knot}: a knot matches a
      * class only if these agree too (the register-resident gather splits flat term ids by role) */
     const int32_t* hg_meta;
-    /* Enqueue kernel `kernel_id` (+ its general-constraint companion) on `stream`.
-     * Returns 0 or a cudaError_t value. */
+    /* Enqueue kernel `kernel_id` (+ its general-constraint companions) on `stream`.
+     * Returns the number of kernels launched (>= 0) or minus a cudaError_t value. */
     int (*launch)(int kernel_id, const dto_launch_args* args, void* stream);
     /* dynamic shared memory (bytes per CTA) the knot kernel `kernel_id` needs */
     int64_t (*smem_bytes)(int kernel_id, const dto_launch_args* args);

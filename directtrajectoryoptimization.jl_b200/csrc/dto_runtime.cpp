@@ -989,11 +989,8 @@ static int launch_all(dto_batch* b, int kernel_id)
         dto_launch_args a;
         fill_args(s, &sh, &a);
         const int e = s->model->vt->launch(kernel_id, &a, (void*)sh.stream);
-        if (e != 0) return fail(DTO_ERR_CUDA, "kernel launch (id %d) failed: %s", kernel_id, cudaGetErrorString((cudaError_t)e));
-        int64_t n = 1;
-        if (kernel_id == DTO_K_CONSTRAINT) n += a.gen_nrow > 0;
-        if (kernel_id == DTO_K_JACOBIAN || kernel_id == DTO_K_JAC_HESS) n += a.gen_njac > 0;
-        if (kernel_id == DTO_K_HESSIAN || kernel_id == DTO_K_JAC_HESS) n += (a.gen_nhess > 0 && !a.use_hclass);
+        if (e < 0) return fail(DTO_ERR_CUDA, "kernel launch (id %d) failed: %s", kernel_id, cudaGetErrorString((cudaError_t)(-e)));
+        const int64_t n = e;
         b->launches += n;
     }
     return DTO_OK;
@@ -1062,8 +1059,8 @@ extern "C" int dto_eval_jacobian_hessian_host(dto_batch* b, const double* z, con
             a.J += first * wj;
             a.H += first * wh;
             const int e = s->model->vt->launch(DTO_K_JAC_HESS, &a, (void*)st);
-            if (e != 0) return fail(DTO_ERR_CUDA, "kernel launch (fused, chunk %lld) failed: %s", (long long)k, cudaGetErrorString((cudaError_t)e));
-            b->launches += 1 + (a.gen_njac > 0) + (a.gen_nhess > 0 && !a.use_hclass);
+            if (e < 0) return fail(DTO_ERR_CUDA, "kernel launch (fused, chunk %lld) failed: %s", (long long)k, cudaGetErrorString((cudaError_t)(-e)));
+            b->launches += e;
             if (J) DTO_CUDA(cudaMemcpyAsync(J + g * wj, sh.arr[DTO_ARRAY_J] + first * wj, (size_t)(cnt * wj) * sizeof(double), cudaMemcpyDeviceToHost, st));
             if (H) DTO_CUDA(cudaMemcpyAsync(H + g * wh, sh.arr[DTO_ARRAY_H] + first * wh, (size_t)(cnt * wh) * sizeof(double), cudaMemcpyDeviceToHost, st));
         }
