@@ -240,6 +240,12 @@ __host__ __device__ constexpr bool ws_split_general()
     return DTO_WS_SPLIT_GEN != 0 && M::OPS_FUSED < DTO_WS_MIN_OPS;
 }
 
+// setmaxnreg can only hand out what the launch allocated (12 warps x 168 registers): a split that asks
+// for more makes the compute warps spin in setmaxnreg.inc forever (measured: a hung launch)
+static_assert(DTO_WS_HELPERS * DTO_WS_HREG + DTO_WS_COMPUTE * DTO_WS_CREG <= (DTO_WS_HELPERS + DTO_WS_COMPUTE) * 168,
+              "DTO_WS_HREG / DTO_WS_CREG exceed the registers of the launch");
+static_assert(DTO_WS_HREG % 8 == 0 && DTO_WS_CREG % 8 == 0 && DTO_WS_HREG >= 24 && DTO_WS_CREG <= 256, "setmaxnreg takes multiples of 8 in [24, 256]");
+
 template <class M, int MODE>
 __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) knot_kernel_ws(const __grid_constant__ dto_launch_args a)
 {
