@@ -46,7 +46,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 232, "ws_helpers": 4, "ws_min_ops": 100, "ws_plan": 1, "ws_all": 0, "bf": 0, "ws_split_gen": 0}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 0, "ws_split_gen": 0}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -533,6 +533,11 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
                 out.append("    return v;\n}\n")
         stats["gen_templates"] = [len(t) for t in templates]
 
+        def _span(e, prefix):
+            idx = [int(str(s_)[len(prefix):]) for s_ in e.free_symbols if str(s_).startswith(prefix)]
+            return max(idx) + 1 if idx else 0
+        stats["gen_hess_span"] = [(_span(e, "gz"), _span(e, "gw"), _span(e, "gl")) for e in templates[2]]
+
     halo = 0
     for el in spec.dyn:
         if el.has_hess and any(r > el.nx + el.nu for r in el.hess_rows):
@@ -694,11 +699,13 @@ def emit_model(spec: ModelSpec, source_hash: str) -> Tuple[str, dict]:
             for j, nm in enumerate(("tmpl", "zbase", "wbase", "lbase")):
                 d.append(_int_array(f"gen_{nm}{cls}", [t[j] for t in gen_inst[cls]]))
         nh = len(gen.hess) if gen.has_hess else 0
+        d.append(_int_array("gen_hspan", [v for t3 in stats.get("gen_hess_span", []) for v in t3]))
         d.append("static const dto_general_desc gen_desc = {"
                  f"{gen.num_variables}, {gen.num_parameter}, {len(gen.evaluate)}, {len(gen.jac)}, gen_jr, gen_jc, "
                  f"{int(gen.has_hess)}, {nh}, gen_hr, gen_hc, {len(gen.ineq)}, gen_iq, "
                  "{gen_tmpl0, gen_tmpl1, gen_tmpl2}, {gen_zbase0, gen_zbase1, gen_zbase2}, "
-                 "{gen_wbase0, gen_wbase1, gen_wbase2}, {gen_lbase0, gen_lbase1, gen_lbase2}};")
+                 "{gen_wbase0, gen_wbase1, gen_wbase2}, {gen_lbase0, gen_lbase1, gen_lbase2}, "
+                 f"{len(stats.get('gen_hess_span', []))}, gen_hspan}};")
     hg_ns = [len(r) for r in spec.hg_classes]
     hg_of, acc = [], 0
     for n_ in hg_ns:
@@ -777,11 +784,19 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}: the CUDA model library cannot be built (no CPU fallback exists)")
     tune = _tuning()
+    # light (HBM-bound) models: the ws kernel's compute warps need few registers and finish a tile quickly, so
+    # the per-tile work of a helper warp would bound the kernel: one helper per compute warp instead of one per
+    # two (unless DTO_TUNE says otherwise)
+    light = stats.get("ops_fused_per_knot", 0) < 100
+    if tune["ws_helpers"] == 0:  # 0 = automatic
+        tune["ws_helpers"] = 8 if light else 4
+    if tune["ws_creg"] == 0:
+        tune["ws_creg"] = 168 if tune["ws_helpers"] == 8 else 232
     cmd = [NVCC, *NVCC_ARCH, f"-DDTO_WARPS={tune['warps']}", f"-DDTO_MIN_CTAS={tune['min_ctas']}",
            f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", f"-DDTO_L2_PREFETCH={tune['l2_prefetch']}",
            f"-DDTO_PERSIST={tune['persist']}", f"-DDTO_PWARPS={tune['pwarps']}", f"-DDTO_PCTAS={tune['pctas']}",
            f"-DDTO_WS={tune['ws']}", f"-DDTO_WS_HREG={tune['ws_hreg']}", f"-DDTO_WS_CREG={tune['ws_creg']}",
-           f"-DDTO_WS_MIN_OPS={tune['ws_min_ops']}", f"-DDTO_WS_PLAN={tune['ws_plan']}", f"-DDTO_WS_ALL_MODES={tune['ws_all']}", f"-DDTO_WS_SPLIT_GEN={tune['ws_split_gen']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+           f"-DDTO_WS_MIN_OPS={tune['ws_min_ops']}", f"-DDTO_WS_PLAN={tune['ws_plan']}", f"-DDTO_WS_HELPERS={tune['ws_helpers']}", f"-DDTO_WS_ALL_MODES={tune['ws_all']}", f"-DDTO_WS_SPLIT_GEN={tune['ws_split_gen']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
            "-I", CSRC_DIR, "-o", so + ".tmp", cu]
     t1 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -27,14 +27,27 @@
 #pragma once
 
 #define DTO_WS_COMPUTE 8
-#define DTO_WS_HELPERS 4
+#ifndef DTO_WS_HELPERS
+#define DTO_WS_HELPERS 4          /* 4: helper h serves compute warps h, h+4 (FP64-heavy models); 8: one helper per compute warp */
+#endif
 #define DTO_WS_DESC_DOUBLES 192   /* 3 x int4 per item, 32 items */
 #define DTO_WS_PIECE_DOUBLES 64   /* 1 x int4 per piece, 32 pieces */
 #define DTO_WS_HDR_DOUBLES 2      /* 1 x int4: b0, ... */
-#define DTO_WS_PLAN_INT4 160      /* per (t0, parity): copy[32], d0[32], d1[32], d2[32], piece[32] */
+#define DTO_WS_PLAN_INT4 160      /* per (t0, parity): copy[32], d0[32], d1[32], d2[32], piece[32] (+ general records) */
+#define DTO_WS_GEN_K 2            /* general-constraint Hessian entries per knot carried as plan records */
+#define DTO_WS_GEN_LCAP 32        /* general-constraint multipliers staged per problem of a tile (doubles, even) */
+#define DTO_WS_GEN_INT4 (32 * DTO_WS_GEN_K + 8)  /* records[32][K] + count[32] */
+
+// shapes with a general-constraint Hessian carry DTO_WS_GEN_INT4 more int4 per plan block / stage
+template <int MODE>
+__host__ __device__ inline int ws_gen_int4(const dto_launch_args& a)
+{
+    return ((MODE & DTO_MODE_H) != 0 && a.gen_nhess > 0) ? DTO_WS_GEN_INT4 : 0;
+}
 
 template <int MODE>
-__host__ __device__ inline int ws_layout(const dto_launch_args& a, int* base, int* ioff, int* in_sz, int* stage_sz, int* out0, int* out_sz)
+__host__ __device__ inline int ws_layout(const dto_launch_args& a, int* base, int* ioff, int* in_sz, int* stage_sz, int* out0, int* out_sz,
+                                         int* gl_off = nullptr)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
     int n = 0;
@@ -43,8 +56,11 @@ __host__ __device__ inline int ws_layout(const dto_launch_args& a, int* base, in
         if (ioff) ioff[k] = n;
         if (need) n += a.in_cap[k];
     }
+    // general-constraint multipliers the tile's Hessian entries read: one staged range per problem touched
+    if (gl_off) *gl_off = n;
+    if (ws_gen_int4<MODE>(a)) n += 4 * (DTO_WS_GEN_LCAP + 2);
     if (in_sz) *in_sz = n;
-    const int st = n + DTO_WS_DESC_DOUBLES + DTO_WS_PIECE_DOUBLES + DTO_WS_HDR_DOUBLES;
+    const int st = n + DTO_WS_DESC_DOUBLES + DTO_WS_PIECE_DOUBLES + 2 * ws_gen_int4<MODE>(a) + DTO_WS_HDR_DOUBLES;
     if (stage_sz) *stage_sz = st;
     int off = 8 + 2 * st;  // six mbarriers (8 doubles reserved), two input stages
     const int out_begin = off;
@@ -217,12 +233,76 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ dto_l
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= 2 * a.T) return;
     const int t0 = w >> 1, pc = w & 1;
-    int base[6], ioff[5], in_sz, stage_sz, out0, out_sz;
-    ws_layout<MODE>(a, base, ioff, &in_sz, &stage_sz, &out0, &out_sz);
+    int base[6], ioff[5], in_sz, stage_sz, out0, out_sz, gl_off;
+    ws_layout<MODE>(a, base, ioff, &in_sz, &stage_sz, &out0, &out_sz, &gl_off);
     const tile_t q = tile_geom_at<HALO>(a, pc * a.T + t0, OWN);  // problem index = its parity: same alignment as any b0 of that parity
     int4 copy, piece, d0, d1, d2;
     ws_tile_records<M, MODE>(a, a.knot, q, lane, base, ioff, 8, copy, piece, d0, d1, d2);
-    int4* P = plan + (size_t)w * DTO_WS_PLAN_INT4;
+    const int G4 = ws_gen_int4<MODE>(a);
+    int4* P = plan + (size_t)w * (DTO_WS_PLAN_INT4 + G4);
+    if (G4) {
+        // ---- general-constraint Hessian entries owned by this lane's knot (src/general_constraint.jl:85-91) as
+        // records {slot offset | template, z offset, lambda offset, wbase}: their z comes from the staged z
+        // range, their multipliers from one extra staged range per problem (copy slots of lanes 4..7), so the
+        // compute lane evaluates them without a single load from HBM. A lane whose entries do not fit (more than
+        // K entries, z outside the tile, multiplier range longer than LCAP) gets count -1: in-kernel table path.
+        const int* tabw = reinterpret_cast<const int*>(a.knot);
+        const int T = a.T;
+        const int tfz = tabw[q.tf * 16 + 0];
+        const bool own = ((d0.w >> 16) & 2) != 0;
+        const int db = d2.y, t = d2.z;
+        const int p0 = own ? a.gh_ptr[t] : 0;
+        const int cnt = own ? a.gh_ptr[t + 1] - p0 : 0;
+        const int4* rec = reinterpret_cast<const int4*>(a.gh_rec);
+        int lmin = 0x7fffffff, lmax = -0x7fffffff;
+        for (int k = 0; k < cnt; ++k) {
+            const int4 r0 = rec[2 * (p0 + k)], r1 = rec[2 * (p0 + k) + 1];
+            if (r1.z > 0) {
+                lmin = min(lmin, r0.w);
+                lmax = max(lmax, r0.w + r1.z);
+            }
+        }
+        int glo[4], gpar[4];
+        bool gst[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool mine = own && db == j;
+            const int lo = __reduce_min_sync(0xffffffffu, mine ? lmin : 0x7fffffff);
+            const int hi = __reduce_max_sync(0xffffffffu, mine ? lmax : -0x7fffffff);
+            const int len = (lo != 0x7fffffff) ? hi - lo : 0;
+            gst[j] = len > 0 && len <= DTO_WS_GEN_LCAP;
+            glo[j] = lo;
+            gpar[j] = gst[j] ? ptr_parity(a.lam + (size_t)(pc + j) * a.N_c + a.gen_row0 + lo) : 0;
+            if (gst[j] && lane == 4 + j)
+                copy = make_int4(j * a.N_c + a.gen_row0 + lo - gpar[j], ((len + gpar[j] + 1) & ~1) * 8, 8 + gl_off + j * (DTO_WS_GEN_LCAP + 2), 3);
+        }
+        const int kl1z = tabw[(q.tl + 1) * 16 + 0], kl1n = tabw[(q.tl + 1) * 16 + 1];
+        const int zend_last = kl1z + (q.tl + 1 < T ? kl1n : 0);
+        const int zlo = db == 0 ? tfz : 0, zhi = (db == q.nsub - 1) ? zend_last : a.N_z;
+        const int zb0 = 8 + ioff[DTO_IN_Z] + (((q.b0 & a.N_z) ^ tfz ^ ptr_parity(a.z)) & 1) + db * a.N_z - tfz;  // + z index
+        bool ok = cnt <= DTO_WS_GEN_K;
+#pragma unroll
+        for (int k = 0; k < DTO_WS_GEN_K; ++k) {
+            int4 r = make_int4(0, 0, 0, 0);
+            if (k < cnt) {
+                const int4 r0 = rec[2 * (p0 + k)], r1 = rec[2 * (p0 + k) + 1];
+                const bool zin = r1.y == 0 || (r0.z >= zlo && r0.z + r1.y <= zhi);
+                bool lin = r1.z == 0;
+                int loff = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (db == j && r1.z > 0) {
+                        lin = gst[j];
+                        loff = 8 + gl_off + j * (DTO_WS_GEN_LCAP + 2) + gpar[j] + (r0.w - glo[j]);
+                    }
+                const int srel = r0.x - d2.w;
+                ok = ok && zin && lin && srel >= 0 && srel < 65536 && r0.y < 65536;
+                r = make_int4(srel | (r0.y << 16), zb0 + r0.z, loff, r1.x);
+            }
+            P[160 + lane * DTO_WS_GEN_K + k] = r;
+        }
+        reinterpret_cast<int*>(P + 160 + 32 * DTO_WS_GEN_K)[lane] = ok ? cnt : -1;
+    }
     P[lane] = copy;
     P[32 + lane] = d0;
     P[64 + lane] = d1;
@@ -230,10 +310,9 @@ __global__ void __launch_bounds__(128) plan_kernel(const __grid_constant__ dto_l
     P[128 + lane] = piece;
 }
 
-// Option (off by default, DTO_WS_SPLIT_GEN): on light models leave the general-constraint Hessian entries
-// (dependent table / z / lambda loads from HBM per knot, which stall the two compute warps of a
-// sub-partition) to general_kernel<2> after the knot kernel. Measured slower than the fused single write
-// (car T=201: 306 vs 238 us, profiles/experiments/sweep_r01_y_split_general.jsonl).
+// Option (off by default, DTO_WS_SPLIT_GEN): on light models leave the general-constraint Hessian entries to
+// general_kernel<2> after the knot kernel. Measured slower than the fused single write (car T=201: 306 vs
+// 238 us, profiles/experiments/sweep_r01_y_split_general.jsonl).
 template <class M>
 __host__ __device__ constexpr bool ws_split_general()
 {
@@ -242,8 +321,9 @@ __host__ __device__ constexpr bool ws_split_general()
 
 // setmaxnreg can only hand out what the launch allocated (12 warps x 168 registers): a split that asks
 // for more makes the compute warps spin in setmaxnreg.inc forever (measured: a hung launch)
-static_assert(DTO_WS_HELPERS * DTO_WS_HREG + DTO_WS_COMPUTE * DTO_WS_CREG <= (DTO_WS_HELPERS + DTO_WS_COMPUTE) * 168,
-              "DTO_WS_HREG / DTO_WS_CREG exceed the registers of the launch");
+static_assert(DTO_WS_HELPERS == 4 || DTO_WS_HELPERS == 8, "4 or 8 helper warps");
+static_assert(DTO_WS_HELPERS * DTO_WS_HREG + DTO_WS_COMPUTE * DTO_WS_CREG <= (DTO_WS_HELPERS + DTO_WS_COMPUTE) * (DTO_WS_HELPERS == 4 ? 168 : 128),
+              "DTO_WS_HREG / DTO_WS_CREG exceed the registers of the launch (168 per thread at 384 threads, 128 at 512)");
 static_assert(DTO_WS_HREG % 8 == 0 && DTO_WS_CREG % 8 == 0 && DTO_WS_HREG >= 24 && DTO_WS_CREG <= 256, "setmaxnreg takes multiples of 8 in [24, 256]");
 
 template <class M, int MODE>
@@ -284,6 +364,7 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     __syncthreads();
     const int stride = gridDim.x * DTO_WS_COMPUTE;
     const int4* __restrict__ plan = reinterpret_cast<const int4*>(a.ws_plan);
+    const int G4 = ws_gen_int4<MODE>(a);  // int4 of general-constraint records per plan block / stage
 
     if (warp < DTO_WS_HELPERS) {
         // =============================== helper warp ===============================
@@ -310,7 +391,7 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                     // ---- tile kk-2 is complete in output buffer od: issue its stores (piece list of stage st)
                     mbar_wait(bar0 + 16 + od * 8, nd & 1);
                     const int4 pd = sdesc[96 + lane];
-                    const int b0 = reinterpret_cast<const int*>(sdesc + 128)[0];
+                    const int b0 = reinterpret_cast<const int*>(sdesc + 128 + G4)[0];
                     int len = pd.w;
                     if (len > 0) {
                         double* dst = ws_out_array(a, pd.y, b0) + pd.x;
@@ -337,11 +418,11 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                         // ---- full tile: its records are block (t0, b0 & 1) of the plan table ----
                         int t0;
                         split_item(a, g0, b0, t0);
-                        const int4* P = plan + (size_t)(t0 * 2 + (b0 & 1)) * DTO_WS_PLAN_INT4;
+                        const int4* P = plan + (size_t)(t0 * 2 + (b0 & 1)) * (DTO_WS_PLAN_INT4 + G4);
                         copy = __ldg(P + lane);
                         if (lane == 0) {
-                            mbar_expect_tx(full, 128 * 16);
-                            bulk_load(smem_u32(sdesc), P + 32, 128 * 16, full);
+                            mbar_expect_tx(full, (uint32_t)(128 + G4) * 16u);
+                            bulk_load(smem_u32(sdesc), P + 32, (uint32_t)(128 + G4) * 16u, full);
                         }
                     } else {
                         // ---- ragged last tile (or no plan table): compute the records here ----
@@ -353,12 +434,13 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                         sdesc[32 + lane] = d1;
                         sdesc[64 + lane] = d2;
                         sdesc[96 + lane] = piece;
+                        if (G4) reinterpret_cast<int*>(sdesc + 128 + 32 * DTO_WS_GEN_K)[lane] = -1;  // general entries: table path
                     }
                     if (copy.y > 0) {
                         mbar_expect_tx(full, (uint32_t)copy.y);
                         bulk_load(smem_u32(smc + copy.z + din), ws_in_array(a, copy.w, b0) + copy.x, (uint32_t)copy.y, full);
                     }
-                    if (lane == 0) sdesc[128] = make_int4(b0, 0, 0, 0);
+                    if (lane == 0) sdesc[128 + G4] = make_int4(b0, 0, 0, 0);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full);
                 }
@@ -412,7 +494,7 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                     const double* __restrict__ y = smc + (d0.y & 0xffff);
                     const int kcost = d1.x & 255, kdyn = (d1.x >> 8) & 255, kstage = (d1.x >> 16) & 255;
                     const double* __restrict__ w = smc + ((unsigned)d0.y >> 16);
-                    if (!a.w_flat) w = a.w + (size_t)(dsc[128].x + d2.y) * a.N_w + ((unsigned)d0.y >> 16);
+                    if (!a.w_flat) w = a.w + (size_t)(dsc[128 + G4].x + d2.y) * a.N_w + ((unsigned)d0.y >> 16);
                     const double* __restrict__ lam_d = smc + (d0.z & 0xffff);
                     const double* __restrict__ lam_s = smc + ((unsigned)d0.z >> 16);
                     if (own) {
@@ -447,14 +529,27 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                     M::hg_compute_r(hclass, tc, td, ts, pd, v);
                     M::hg_store(hclass, v, dst);
                     if (a.gen_nhess > 0 && !ws_split_general<M>()) {
-                        const int b = dsc[128].x + d2.y, t = d2.z;
-                        const int p0 = __ldg(a.gh_ptr + t), p1 = __ldg(a.gh_ptr + t + 1);
-                        for (int p = p0; p < p1; ++p) {
-                            const int2 e = __ldg(reinterpret_cast<const int2*>(a.gh_ent) + p);  // slot, instance
-                            const int4 inst = __ldg(reinterpret_cast<const int4*>(a.gen_inst[2]) + e.y);
-                            const double val = M::gen_eval(2, inst.x, a.z + (size_t)b * a.N_z + inst.y, a.w + (size_t)b * a.N_w + inst.z,
-                                                           a.lam + (size_t)b * a.N_c + a.gen_row0 + inst.w);
-                            dst[e.x - d2.w] += val;
+                        // general-constraint entries of this knot's slots: last in the += order (src/moi.jl:112-118)
+                        const int b = dsc[128 + G4].x + d2.y, t = d2.z;
+                        const int gc = reinterpret_cast<const int*>(dsc + 128 + 32 * DTO_WS_GEN_K)[lane];
+                        if (gc >= 0) {  // plan records: z and multipliers are in the stage
+                            const int din = st * stage_sz;
+#pragma unroll
+                            for (int kq = 0; kq < DTO_WS_GEN_K; ++kq)
+                                if (kq < gc) {
+                                    const int4 r = dsc[128 + lane * DTO_WS_GEN_K + kq];
+                                    const double val = M::gen_eval(2, (int)((unsigned)r.x >> 16), smc + r.y + din, a.w + (size_t)b * a.N_w + r.w, smc + r.z + din);
+                                    dst[r.x & 0xffff] += val;
+                                }
+                        } else {  // table path (entries that do not fit the records; ragged last tile)
+                            const int p0 = __ldg(a.gh_ptr + t), p1 = __ldg(a.gh_ptr + t + 1);
+                            for (int p = p0; p < p1; ++p) {
+                                const int2 e = __ldg(reinterpret_cast<const int2*>(a.gh_ent) + p);  // slot, instance
+                                const int4 inst = __ldg(reinterpret_cast<const int4*>(a.gen_inst[2]) + e.y);
+                                const double val = M::gen_eval(2, inst.x, a.z + (size_t)b * a.N_z + inst.y, a.w + (size_t)b * a.N_w + inst.z,
+                                                               a.lam + (size_t)b * a.N_c + a.gen_row0 + inst.w);
+                                dst[e.x - d2.w] += val;
+                            }
                         }
                     }
                 }
@@ -472,12 +567,12 @@ inline int64_t plan_ws(dto_launch_args& b)
 {
     constexpr bool DO_H = (MODE & DTO_MODE_H) != 0;
     if (!DTO_WS || !b.persist_ok || b.nsub_max > 4) return 0;   // (segment row, problem) lane map: 8 rows x 4 problems
-    // Measured selection (profiles/sweep_r01_s_per_kernel.jsonl, sweep_r01_u_plan.jsonl): the gradient /
-    // residual / Jacobian-only passes are light and HBM-bound, the plain kernel's occupancy wins there;
-    // Hessian passes win here when the model is FP64-heavy or when a tile touches at most two problems
-    // (long horizons: car T=201 256 -> 238 us), not for short horizons of light models (pendulum T=11).
+    // Measured selection (profiles/sweep_r01_s_per_kernel.jsonl, sweep_r01_ae_helpers.jsonl): the gradient /
+    // residual / Jacobian-only passes are light and HBM-bound, the plain kernel's occupancy wins there; every
+    // Hessian pass wins here (FP64-heavy models with 4 helpers + 232-register compute warps, light models
+    // with one helper per compute warp: car T=201 256 -> 196 us, pendulum T=11 41 -> 36 us).
     if (!DO_H && !DTO_WS_ALL_MODES) return 0;
-    if (M::OPS_FUSED < DTO_WS_MIN_OPS && !(b.nsub_max <= 2 && DTO_WS_MIN_OPS <= 100)) return 0;
+    if (M::OPS_FUSED < DTO_WS_MIN_OPS) return 0;
     if (DO_H && !(M::HG_NCLASS > 0 && b.use_hclass)) return 0;     // table gather: other kernels
     if (M::N_KINDS_MAX >= 255 || M::HG_NCLASS >= 255) return 0;    // descriptor packs kinds in 8 bits
     if (!b.w_flat && b.N_w > 65535) return 0;
@@ -534,7 +629,7 @@ inline const void* ws_get_plan(const dto_launch_args& b, cudaStream_t st)
         cache.clear();
     }
     void* ptr = nullptr;
-    const size_t bytes = (size_t)2 * b.T * DTO_WS_PLAN_INT4 * sizeof(int4);
+    const size_t bytes = (size_t)2 * b.T * (DTO_WS_PLAN_INT4 + ws_gen_int4<MODE>(b)) * sizeof(int4);
     if (cudaMalloc(&ptr, bytes) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;  // no table: every tile takes the in-kernel path

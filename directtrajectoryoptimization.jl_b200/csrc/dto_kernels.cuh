@@ -73,7 +73,7 @@
 #define DTO_WS_SPLIT_GEN 0 /* 1: ws kernel on light models leaves the general-constraint Hessian to general_kernel<2> (measured slower: car 238 -> 306 us) */
 #endif
 #ifndef DTO_WS_MIN_OPS
-#define DTO_WS_MIN_OPS 100 /* specialised / persistent kernels only for models with at least this many FP64 ops per knot */
+#define DTO_WS_MIN_OPS 0   /* the specialised kernel only for models with at least this many FP64 ops per knot */
 #endif
 #define DTO_SMEM_LIMIT (227 * 1024)
 
@@ -876,7 +876,7 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st, bool* used_ws)
     }
     {
         int64_t psmem = 0;
-        const int nw = plan_persistent<MODE>(b, &psmem, (MODE & DTO_MODE_H) != 0 && M::OPS_FUSED >= DTO_WS_MIN_OPS);
+        const int nw = plan_persistent<MODE>(b, &psmem, (MODE & DTO_MODE_H) != 0 && M::OPS_FUSED >= 100);  // persistent fallback: FP64-heavy models only
         if (nw > 0) {
             static int sms[16] = {0};
             static int64_t attr_smem[16] = {0};
@@ -1012,7 +1012,7 @@ inline int64_t mode_smem_bytes(const dto_launch_args& a)
     const int64_t ws = plan_ws<M, MODE>(b);
     if (ws > 0) return ws;
     int64_t ps = 0;
-    if (plan_persistent<MODE>(b, &ps, (MODE & DTO_MODE_H) != 0 && M::OPS_FUSED >= DTO_WS_MIN_OPS) > 0) return ps;
+    if (plan_persistent<MODE>(b, &ps, (MODE & DTO_MODE_H) != 0 && M::OPS_FUSED >= 100) > 0) return ps;
     return knot_smem_bytes<MODE>(a);
 }
 

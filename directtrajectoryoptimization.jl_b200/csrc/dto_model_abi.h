@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define DTO_MODEL_ABI_VERSION 13
+#define DTO_MODEL_ABI_VERSION 14
 
 /* One element kind (a distinct Dynamics / Cost / Constraint object of the reference). All
  * patterns are 1-based local indices in the element's own variable order
@@ -56,6 +56,9 @@ typedef struct dto_general_desc {
     const int32_t* inst_zbase[3];
     const int32_t* inst_wbase[3];
     const int32_t* inst_lbase[3];
+    /* per Hessian template (class 2): how many consecutive z / w / lambda entries from its base it may read */
+    int32_t n_hess_templates;
+    const int32_t* hess_span; /* [n_hess_templates][3] = zspan, wspan, lspan */
 } dto_general_desc;
 
 /* Per-knot static table entry (device). Entry t describes knot t (0-based); the table
@@ -124,6 +127,9 @@ typedef struct dto_launch_args {
      * knot kernel when use_hclass): entries gh_ptr[t]..gh_ptr[t+1], each = (slot, instance) */
     const int32_t* gh_ptr;  /* [T+1] */
     const int32_t* gh_ent;  /* [gen_nhess][2] */
+    /* the same entries flattened for the ws kernel's tile plans, 2 x int4 per entry in gh_ent order:
+     * {slot, template, zbase, lbase}, {wbase, zspan, lspan, 0} */
+    const int32_t* gh_rec;  /* [gen_nhess][8] */
     /* filled by the model library at launch: how many warp tiles run concurrently on the device; a
      * starting warp prefetches (L2) the inputs of the tile that many positions ahead */
     int32_t tiles_in_flight;

@@ -83,6 +83,7 @@ struct dto_shape {
     std::vector<int32_t> gen_inst[3];            // [n][4]
     std::vector<int32_t> gen_hslot;
     std::vector<int32_t> gh_ptr, gh_ent;         // general Hessian entries grouped by owning knot
+    std::vector<int32_t> gh_rec;                 // the same entries flattened (8 ints each) for the ws kernel's tile plans
     std::vector<double> c_lower, c_upper;
     int32_t seg_cap[6] = {0, 0, 0, 0, 0, 0};
     int32_t seg_pad[6] = {0, 0, 0, 0, 0, 0};
@@ -106,6 +107,7 @@ struct dto_shard {
     int32_t* d_gen_hslot = nullptr;
     int32_t* d_gh_ptr = nullptr;
     int32_t* d_gh_ent = nullptr;
+    int32_t* d_gh_rec = nullptr;
     cudaStream_t pipe[4] = {nullptr, nullptr, nullptr, nullptr};  // chunk pipeline of the one-call host path
 };
 
@@ -560,6 +562,21 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
             s->gh_ent[2 * p] = s->gen_hslot[i];
             s->gh_ent[2 * p + 1] = (int32_t)i;
         }
+        s->gh_rec.assign(gen_terms.size() * 8, 0);
+        for (size_t p = 0; p < gen_terms.size(); ++p) {
+            const int32_t i = s->gh_ent[2 * p + 1];
+            const int32_t tmpl = gen->inst_tmpl[2][i];
+            DTO_REQUIRE(tmpl >= 0 && tmpl < gen->n_hess_templates, "dto_shape_create: general Hessian template %d out of range", tmpl);
+            int32_t* r = &s->gh_rec[8 * p];
+            r[0] = s->gh_ent[2 * p];
+            r[1] = tmpl;
+            r[2] = gen->inst_zbase[2][i];
+            r[3] = gen->inst_lbase[2][i];
+            r[4] = gen->inst_wbase[2][i];
+            r[5] = gen->hess_span[3 * tmpl + 0];
+            r[6] = gen->hess_span[3 * tmpl + 2];
+            r[7] = 0;
+        }
     }
     if (gen) {
         const int n[3] = {gen->num_constraint, gen->nnz_jac, gen->has_hess ? gen->nnz_hess : 0};
@@ -718,6 +735,7 @@ static void fill_args(const dto_shape* s, const dto_shard* sh, dto_launch_args* 
         a->gen_hslot = sh->d_gen_hslot;
         a->gh_ptr = sh->d_gh_ptr;
         a->gh_ent = sh->d_gh_ent;
+        a->gh_rec = sh->d_gh_rec;
     }
     a->gen_nrow = (int32_t)s->n_gen_rows;
     a->gen_njac = (int32_t)s->n_gen_jac;
@@ -800,6 +818,7 @@ extern "C" void dto_batch_destroy(dto_batch* b)
         if (sh.d_gen_hslot) cudaFree(sh.d_gen_hslot);
         if (sh.d_gh_ptr) cudaFree(sh.d_gh_ptr);
         if (sh.d_gh_ent) cudaFree(sh.d_gh_ent);
+        if (sh.d_gh_rec) cudaFree(sh.d_gh_rec);
         if (sh.stream && sh.own_stream) cudaStreamDestroy(sh.stream);
         for (cudaStream_t& ps : sh.pipe)
             if (ps) cudaStreamDestroy(ps);
@@ -864,6 +883,7 @@ extern "C" int dto_batch_create(dto_shape* s, int64_t B, const int* devices, int
             if ((r = upload(&sh.d_gen_hslot, s->gen_hslot, sh.stream))) return r;
             if ((r = upload(&sh.d_gh_ptr, s->gh_ptr, sh.stream))) return r;
             if ((r = upload(&sh.d_gh_ent, s->gh_ent, sh.stream))) return r;
+            if ((r = upload(&sh.d_gh_rec, s->gh_rec, sh.stream))) return r;
             // inputs are allocated eagerly, outputs on first use
             for (int arr : {DTO_ARRAY_Z, DTO_ARRAY_LAMBDA, DTO_ARRAY_SIGMA, DTO_ARRAY_W})
                 if ((r = ensure_array(b, sh, arr))) return r;
