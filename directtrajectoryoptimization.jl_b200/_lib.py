@@ -104,6 +104,20 @@ def lib() -> C.CDLL:
         "dto_algorithmic_bytes_per_problem": (i64, [vp]),
         "dto_kernel_smem_bytes": (i64, [vp, C.c_int]),
         "dto_shape_compiled_gather": (C.c_int, [vp]),
+        "dto_kkt_analyze": (C.c_int, [vp, i64p, i64p]),
+        "dto_kkt_create": (C.c_int, [vp, C.c_double, C.c_double, C.POINTER(vp)]),
+        "dto_kkt_destroy": (None, [vp]),
+        "dto_kkt_dim": (i64, [vp]),
+        "dto_kkt_bandwidth": (i64, [vp]),
+        "dto_kkt_row_width": (i64, [vp]),
+        "dto_kkt_factor_bytes_per_problem": (i64, [vp]),
+        "dto_kkt_permutation": (C.c_int, [vp, i64p]),
+        "dto_kkt_solve": (C.c_int, [vp, vp]),
+        "dto_kkt_launch": (C.c_int, [vp, C.c_int]),
+        "dto_kkt_get": (C.c_int, [vp, C.c_int, vp]),
+        "dto_kkt_matrix": (C.c_int, [vp, i64, vp]),
+        "dto_kkt_factor": (C.c_int, [vp, i64, vp, vp]),
+        "dto_kkt_device_pointer": (vp, [vp, C.c_int, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

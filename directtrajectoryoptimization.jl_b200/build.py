@@ -1,4 +1,5 @@
-"""Builds libdto.so (the C-ABI host runtime, csrc/dto_runtime.cpp) in-tree."""
+"""Builds libdto.so in-tree: the C-ABI host runtime (csrc/dto_runtime.cpp, g++) linked with the
+model-independent KKT kernels (csrc/dto_kkt.cu, nvcc -gencode arch=compute_100a,code=sm_100a)."""
 from __future__ import annotations
 
 import os
@@ -14,16 +15,22 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    srcs = [os.path.join(CSRC, "dto_runtime.cpp"), os.path.join(CSRC, "dto_model_abi.h"),
-            os.path.join(PKG_DIR, "..", "include", "dto.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("dto_runtime.cpp", "dto_model_abi.h", "dto_kkt_host.inc", "dto_kkt_dev.h", "dto_kkt.cu")]
+    srcs.append(os.path.join(PKG_DIR, "..", "include", "dto.h"))
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
 def build_runtime(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
+    obj = os.path.join(PKG_DIR, "dto_kkt.o")
+    nv = [os.path.join(CUDA_HOME, "bin", "nvcc"), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+          "-Xcompiler", "-fPIC", "-cudart", "static", "-c", os.path.join(CSRC, "dto_kkt.cu"), "-o", obj]
+    r = subprocess.run(nv, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building dto_kkt.o (nvcc, sm_100a) failed:\n" + r.stderr[-4000:])
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-Wno-unused-function",
-           "-I", os.path.join(CUDA_HOME, "include"), os.path.join(CSRC, "dto_runtime.cpp"),
+           "-I", os.path.join(CUDA_HOME, "include"), os.path.join(CSRC, "dto_runtime.cpp"), obj,
            "-o", LIB + ".tmp", "-L", os.path.join(CUDA_HOME, "lib64"), "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

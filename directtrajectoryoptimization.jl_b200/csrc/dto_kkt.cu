@@ -1,0 +1,293 @@
+// dto_kkt.cu -- device-side consumer of the callback outputs: the KKT system
+//
+//        K = [ H + primal_reg I      J'          ]        h = [ grad f + J' y ]
+//            [ J                -dual_reg I      ]            [ c             ]
+//
+// that /root/reference/examples/pendulum/pendulum.jl:138-211 assembles from the five callbacks and
+// factors with QDLDL (K = L D L', quasi-definite so no pivoting is needed), for ALL problems of a
+// batch at once, from the device-resident J / H / g / c arrays -- nothing but the solution crosses
+// PCIe.
+//
+// Every problem of a batch has the same sparsity, so the host runtime computes ONE bandwidth-
+// reducing ordering (reverse Cuthill-McKee, dto_kkt_host.inc) and static gather tables; trajectory
+// problems chain knot to knot, so the permuted K is banded (half bandwidth 9-15 for the example
+// models). The kernels:
+//
+//   kkt_rhs_kernel     thread = (problem, row): h in natural order, sums in the reference's loop order
+//                      (ascending constraint row, un-fused multiply/add => bit-exact vs the oracle)
+//   kkt_band_kernel<W,BW> group of W lanes = problem (W = 16: two problems per warp; W = 32: one):
+//                      streaming right-looking banded LDL' with the forward solve fused in, then the
+//                      backward solve. Lane i owns row W*blk + i; a row keeps its W band entries in
+//                      registers indexed by (column mod W), a compile-time index inside the W-step
+//                      unrolled block, so there is no dynamic register indexing. Two row sets
+//                      (current block, next block) cover the rows a step can touch (half bandwidth
+//                      <= BW < W). Per step: pivot broadcast (shuffle), one reciprocal, the column of
+//                      L goes to shared memory (broadcast reads replace 2*BW shuffles) and to HBM
+//                      (one coalesced <= 120-byte store), then BW predicated DFMAs per row set. The
+//                      backward solve re-reads L column-wise (lane = column, slot = row mod W) so a
+//                      retired x_r costs one shuffle + one DFMA instead of a warp reduction.
+//   kkt_assemble_kernel test/inspection export of the assembled band (same gather as the factor kernel)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dto_kkt_dev.h"
+
+namespace {
+
+template <int G>
+__device__ __forceinline__ double shfl_g(double v, int src)
+{
+    return __shfl_sync(0xffffffffu, v, src, G);
+}
+
+// band entries of row (blk*G + i): slot w holds the column c = w (mod W) of [row-W+1, row]; G == W
+template <int W>
+__device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* __restrict__ Hb, const double* __restrict__ JbmH,
+                                          int blk, int i, double (&X)[W])
+{
+    // JbmH = (this problem's J) - nnz_H, so that a table entry s >= nnz_H addresses J[s - nnz_H]
+    const int32_t* src = a.src + ((size_t)blk * W) * W + i;
+    const double reg = a.dreg[(size_t)blk * W + i];
+    int32_t sidx[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) sidx[w] = src[w * W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const int32_t s = sidx[w];
+        const double* bp = (s < a.nnz_H) ? Hb : JbmH;
+        double v = 0.0;
+        if (s >= 0) v = bp[s];
+        // reference: H[i,i] += primal_reg / H[nz+j,nz+j] -= dual_reg after the assignment
+        X[w] = (w == i) ? v + reg : v;
+    }
+}
+
+// One problem per group of G = W lanes (two problems per warp for W = 16). Row block = W rows.
+// BW = compile-time bound on the half bandwidth (<= W - 1).
+template <int W, int BW>
+__global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
+{
+    constexpr int G = W;
+    constexpr int NG = 32 / G;                       // problems per warp
+    __shared__ __align__(16) double lcol_s[4][NG][2][W];  // un-scaled column of the current step, double-buffered
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int grp = lane / G, i = lane % G;
+    const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * NG + grp;
+    const bool valid = b0 < a.B;
+    const int64_t b = valid ? b0 : a.B - 1;          // idle groups shadow the last problem, stores masked
+    const double* Hb = a.H + b * a.nnz_H;
+    const double* Jb = a.J + b * a.nnz_J - a.nnz_H;  // see load_rows
+    const double* hb = a.rhs + b * a.dim;
+    const int nblk = a.nblk;
+    double* Lg = a.L + (size_t)b * a.factor_stride;  // [nblk*W][W]: slot 0 = pivot d_j, slot q = L(j+q, j)
+    double* Yg = Lg + (size_t)nblk * W * W;          // [nblk*W]: D^-1 L^-1 h
+    double (*lcol)[W] = lcol_s[wib][grp];
+
+    double A[W], Bv[W];
+    double ra, rb = 0.0;
+    load_rows<W>(a, Hb, Jb, 0, i, A);
+    {
+        const int32_t ip = a.iperm[i];
+        ra = ip >= 0 ? hb[ip] : 0.0;
+    }
+    if (nblk > 1) {
+        load_rows<W>(a, Hb, Jb, 1, i, Bv);
+        const int32_t ip = a.iperm[W + i];
+        rb = ip >= 0 ? hb[ip] : 0.0;
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) Bv[w] = 0.0;
+    }
+
+    // ---------------- factor (right-looking) + forward solve ----------------
+    // Step j = blk*W + s. v_r = A(r, j) (un-scaled column), l_r = v_r / d_j. The trailing update
+    // A(r, c) -= l_r * v_c is applied to EVERY slot (c mod W) of a row without a lane mask: for c > r
+    // that slot holds A(r, c - W), a column < j whose L value has already been published to HBM
+    // and is never read from the registers again, and rows outside the band have l_r = 0.
+    for (int blk = 0; blk < nblk; ++blk) {
+        double* LA = Lg + (size_t)blk * W * W + i;   // + s*W + (row - j) with immediates
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            const int p = s & (W - 1);
+            const bool inA = i > s && i <= s + BW;
+            const bool hasB = (s + BW >= G);
+            const bool inB = hasB && (i <= s + BW - G);
+            const double vA = inA ? A[p] : 0.0;
+            const double vB = (hasB && inB) ? Bv[p] : 0.0;
+            double* vs = lcol[s & 1];
+            // publish the un-scaled column: position q - 1 = row - j - 1
+            if (inA) vs[i - s - 1] = vA;
+            if (hasB && inB) vs[i + G - s - 1] = vB;
+            const double d = shfl_g<G>(A[p], s);
+            const double dinv = 1.0 / d;
+            const double lA = vA * dinv;
+            const double lB = vB * dinv;
+            if (valid) {
+                if (inA) LA[s * W - s] = lA;
+                if (hasB && inB) LA[s * W - s + G] = lB;
+                if (i == s) LA[s * W - s] = d;
+            }
+            __syncwarp();
+            // forward substitution, then the D solve for row j
+            const double yj = shfl_g<G>(ra, s);
+            ra = fma(-lA, yj, ra);
+            if (hasB) rb = fma(-lB, yj, rb);
+            if (i == s) ra = yj * dinv;
+            const double nlA = -lA, nlB = -lB;
+#pragma unroll
+            for (int q = 1; q <= BW; ++q) {
+                const int c = s + q;
+                const int idx = (p + q) & (W - 1);
+                const double vc = vs[q - 1];
+                if (c < G) A[idx] = fma(nlA, vc, A[idx]);
+                if (hasB) Bv[idx] = fma(nlB, vc, Bv[idx]);
+            }
+        }
+        if (valid) Yg[(size_t)blk * W + i] = ra;
+#pragma unroll
+        for (int w = 0; w < W; ++w) A[w] = Bv[w];
+        ra = rb;
+        if (blk + 2 < nblk) {
+            load_rows<W>(a, Hb, Jb, blk + 2, i, Bv);
+            const int32_t ip = a.iperm[(size_t)(blk + 2) * W + i];
+            rb = ip >= 0 ? hb[ip] : 0.0;
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) Bv[w] = 0.0;
+            rb = 0.0;
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // ---------------- backward solve: x = L^-T y ----------------
+    // Lane i owns COLUMN j = blk*W + i: slot w holds L(r, j) for the row r = w (mod W) of [j+1, j+W-1].
+    // Rows are retired in descending order; the retired x_r is broadcast and the columns that reach it
+    // (same block: i < s; block below: i >= s + W - BW) subtract L(r, j) x_r.
+    auto load_cols = [&](int blk, double (&C)[W], double& acc) {
+        const double* Lblk = Lg + ((size_t)blk * W + i) * W;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int q = (w - i) & (W - 1);
+            C[w] = (q >= 1 && q <= BW) ? Lblk[q] : 0.0;
+        }
+        acc = Yg[(size_t)blk * W + i];
+    };
+    double xa, xp = 0.0;
+    load_cols(nblk - 1, A, xa);
+    if (nblk > 1) {
+        load_cols(nblk - 2, Bv, xp);
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) Bv[w] = 0.0;
+    }
+    double* solb = a.sol + b * a.dim;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+#pragma unroll
+        for (int s = G - 1; s >= 0; --s) {
+            const int p = s & (W - 1);
+            const double xr = shfl_g<G>(xa, s);
+            if (i < s && i >= s - BW) xa = fma(-A[p], xr, xa);
+            if (s - BW < 0) {
+                if (i >= s + G - BW) xp = fma(-Bv[p], xr, xp);
+            }
+        }
+        const int32_t ip = a.iperm[(size_t)blk * W + i];
+        if (ip >= 0 && valid) solb[ip] = xa;
+#pragma unroll
+        for (int w = 0; w < W; ++w) A[w] = Bv[w];
+        xa = xp;
+        if (blk - 2 >= 0) {
+            load_cols(blk - 2, Bv, xp);
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) Bv[w] = 0.0;
+            xp = 0.0;
+        }
+    }
+}
+
+template <int W>
+__global__ void kkt_assemble_kernel(const dto_kkt_args a, int64_t problem, double* __restrict__ out)
+{
+    const int i = threadIdx.x;
+    const int blk = blockIdx.x;
+    const double* Hb = a.H + problem * a.nnz_H;
+    const double* Jb = a.J + problem * a.nnz_J - a.nnz_H;
+    double X[W];
+    load_rows<W>(a, Hb, Jb, blk, i, X);
+#pragma unroll
+    for (int w = 0; w < W; ++w) out[((size_t)blk * W + w) * W + i] = X[w];
+}
+
+// h = [grad f + J' y ; c], natural order. Reference loop (examples/pendulum/pendulum.jl:155-173):
+// for each variable i: cy = sum over constraint rows j ascending of C[j,i]*y[j]; h[i] = grad[i] + cy.
+__global__ void kkt_rhs_kernel(const dto_kkt_args a)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= a.B * a.dim) return;
+    const int64_t b = gid / a.dim;
+    const int i = (int)(gid - b * a.dim);
+    double h;
+    if (i < a.N_z) {
+        const double* Jb = a.J + b * a.nnz_J;
+        const double* yb = a.y + b * a.N_c;
+        double cy = 0.0;
+        for (int k = a.colptr[i]; k < a.colptr[i + 1]; ++k)
+            cy = __dadd_rn(cy, __dmul_rn(Jb[a.colslot[k]], yb[a.colrow[k]]));
+        h = __dadd_rn(a.g[b * a.N_z + i], cy);
+    } else {
+        h = a.c[b * a.N_c + (i - a.N_z)];
+    }
+    a.rhs[gid] = h;
+}
+
+}  // namespace
+
+extern "C" int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream)
+{
+    const int64_t n = a->B * a->dim;
+    if (n == 0) return 0;
+    kkt_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+template <int W, int BW>
+static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
+{
+    const int64_t per_block = 4 * (32 / W);
+    kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, 0, st>>>(*a);
+    return cudaGetLastError();
+}
+
+extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
+{
+    if (a->B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaErrorInvalidValue;
+    const int bw = a->bw;
+    if (a->W == 16) {
+        if (bw <= 6) e = launch_band_t<16, 6>(a, st);
+        else if (bw <= 9) e = launch_band_t<16, 9>(a, st);
+        else if (bw <= 12) e = launch_band_t<16, 12>(a, st);
+        else if (bw <= 15) e = launch_band_t<16, 15>(a, st);
+    } else if (a->W == 32) {
+        if (bw <= 20) e = launch_band_t<32, 20>(a, st);
+        else if (bw <= 31) e = launch_band_t<32, 31>(a, st);
+    }
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+extern "C" int dto_kkt_launch_assemble(const dto_kkt_args* a, int64_t problem, double* out, void* stream)
+{
+    if (a->W == 16)
+        kkt_assemble_kernel<16><<<(unsigned)a->nblk, 16, 0, (cudaStream_t)stream>>>(*a, problem, out);
+    else if (a->W == 32)
+        kkt_assemble_kernel<32><<<(unsigned)a->nblk, 32, 0, (cudaStream_t)stream>>>(*a, problem, out);
+    else
+        return -(int)cudaErrorInvalidValue;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}

@@ -1,0 +1,50 @@
+/* dto_kkt_dev.h -- launch interface between the host runtime (dto_runtime.cpp, g++) and the KKT
+ * kernels (dto_kkt.cu, nvcc). Plain C. */
+#ifndef DTO_KKT_DEV_H
+#define DTO_KKT_DEV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dto_kkt_args {
+    int64_t B;           /* problems of this shard                                            */
+    int32_t dim;         /* N_z + N_c                                                          */
+    int32_t N_z, N_c;
+    int32_t nnz_J, nnz_H;
+    int32_t W;           /* band entries kept per row = rows per block = lanes per problem (16 or 32) */
+    int32_t bw;          /* half bandwidth of the ordered matrix (<= W - 1)                    */
+    int32_t nblk;        /* ceil(dim / W) row blocks                                           */
+    int64_t factor_stride; /* doubles of factor storage per problem: nblk*W*W + nblk*W         */
+    /* callback outputs / inputs of the shard (problem-major) */
+    const double* H;     /* [B][nnz_H]  */
+    const double* J;     /* [B][nnz_J]  */
+    const double* g;     /* [B][N_z]    */
+    const double* c;     /* [B][N_c]    */
+    const double* y;     /* [B][N_c] multipliers (lambda)                                      */
+    /* static tables, shared by all problems */
+    const int32_t* src;    /* [nblk][W][W] value source of band slot (row block, column mod W, row in block):
+                              < nnz_H -> H, else J, -1 structural zero                               */
+    const double* dreg;    /* [nblk*W] diagonal shift: +primal_reg, -dual_reg, 1.0 on padding rows   */
+    const int32_t* iperm;  /* [nblk*W] original (0-based) index of permuted row, -1 on padding       */
+    const int32_t* colptr; /* [N_z+1] Jacobian by column ...                                         */
+    const int32_t* colslot;/* [nnz_J] ... slot in J, rows ascending                                  */
+    const int32_t* colrow; /* [nnz_J] ... constraint row (0-based)                                   */
+    /* work / outputs */
+    double* rhs;         /* [B][dim] h = [grad f + J'y ; c], natural order                     */
+    double* L;           /* [B][factor_stride]: per problem [nblk*W][W] columns of L (slot 0 = pivot d_j,
+                            slot q = L(j+q, j)) followed by [nblk*W] D^-1 L^-1 h                 */
+    double* sol;         /* [B][dim] K^-1 h, natural order                                     */
+} dto_kkt_args;
+
+/* each returns the number of kernels enqueued (>= 0) or -(cudaError_t) */
+int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream);
+int dto_kkt_launch_band(const dto_kkt_args* a, void* stream);
+int dto_kkt_launch_assemble(const dto_kkt_args* a, int64_t problem, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

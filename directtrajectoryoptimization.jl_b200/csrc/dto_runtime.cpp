@@ -150,6 +150,7 @@ extern "C" const char* dto_status_string(int status)
     case DTO_ERR_MODEL: return "model library error";
     case DTO_ERR_NO_HESSIAN: return "Hessian not available";
     case DTO_ERR_STATE: return "invalid state";
+    case DTO_ERR_UNSUPPORTED: return "unsupported shape";
     default: return "unknown status";
     }
 }
@@ -1158,3 +1159,8 @@ extern "C" int dto_sync(dto_batch* b)
     return sync_all(b);
 }
 extern "C" int64_t dto_launch_count(const dto_batch* b) { return b ? b->launches : -1; }
+
+// ------------------------------------------------------------------------------------------
+// device-side KKT consumer
+// ------------------------------------------------------------------------------------------
+#include "dto_kkt_host.inc"

@@ -1,0 +1,103 @@
+"""Device-resident KKT systems of a batch: host mirror of the `dto_kkt_*` entry points of
+include/dto.h.
+
+The reference sketches this consumer of the callbacks in
+/root/reference/examples/pendulum/pendulum.jl:138-211: from g, c, J, H build
+
+    K = [H + primal_reg I, J'; J, -dual_reg I],   h = [g + J'y; c],   F = qdldl(K),   sol = F \\ h
+
+Here that happens for every problem of the batch on the GPU, from the arrays the callback kernels
+left in HBM; only `sol` comes back. All numerics are in libdto.so's CUDA kernels -- this module only
+marshals pointers and raises if the native pieces or a GPU are missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .evaluator import BatchedNLPData, _out, _p
+
+
+def analyze(nlp: BatchedNLPData):
+    """Host-only symbolic phase: (perm, bandwidth). perm[p] is the 1-based index (variables first,
+    then constraint rows) placed at position p of the banded ordering."""
+    n = nlp.num_variables + nlp.num_constraint
+    perm = np.empty(n, dtype=np.int64)
+    bw = C.c_int64()
+    _lib.check(_lib.lib().dto_kkt_analyze(nlp.shape, perm.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(bw)))
+    return perm, int(bw.value)
+
+
+class KKTSystem:
+    """K sol = h for all problems of `nlp` (pendulum.jl:138-211 batched)."""
+
+    def __init__(self, nlp: BatchedNLPData, primal_reg: float = 1.0e-5, dual_reg: float = 1.0e-5):
+        L = _lib.lib()
+        self.nlp = nlp
+        h = C.c_void_p()
+        _lib.check(L.dto_kkt_create(nlp.handle, float(primal_reg), float(dual_reg), C.byref(h)))
+        self._h = h
+        self.dim = int(L.dto_kkt_dim(h))
+        self.bandwidth = int(L.dto_kkt_bandwidth(h))
+        self.row_width = int(L.dto_kkt_row_width(h))
+        self.factor_bytes_per_problem = int(L.dto_kkt_factor_bytes_per_problem(h))
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().dto_kkt_destroy(self._h)
+            self._h = None
+
+    def permutation(self) -> np.ndarray:
+        perm = np.empty(self.dim, dtype=np.int64)
+        _lib.check(_lib.lib().dto_kkt_permutation(self._h, perm.ctypes.data_as(C.POINTER(C.c_int64))))
+        return perm
+
+    def solve(self, solution=None, variables=None, scaling=None, duals=None):
+        """Callbacks at (z, sigma, y) + assembly + LDL' + solve; `solution` [B, dim] is written in
+        place (None: results stay on the device)."""
+        if variables is not None:
+            self.nlp.set_x(variables)
+        if duals is not None:
+            self.nlp.set_duals(1.0 if scaling is None else scaling, duals)
+        if solution is not None:
+            solution = _out(solution, (self.nlp.batch, self.dim), "solution")
+        _lib.check(_lib.lib().dto_kkt_solve(self._h, _p(solution) if solution is not None else None))
+        return solution
+
+    def launch(self, with_callbacks: bool = True) -> None:
+        _lib.check(_lib.lib().dto_kkt_launch(self._h, int(bool(with_callbacks))))
+
+    def rhs(self) -> np.ndarray:
+        out = np.empty((self.nlp.batch, self.dim))
+        _lib.check(_lib.lib().dto_kkt_get(self._h, 0, _p(out)))
+        return out
+
+    def solution(self) -> np.ndarray:
+        out = np.empty((self.nlp.batch, self.dim))
+        _lib.check(_lib.lib().dto_kkt_get(self._h, 1, _p(out)))
+        return out
+
+    def matrix(self, problem: int = 0) -> np.ndarray:
+        out = np.empty((self.dim, self.dim))
+        _lib.check(_lib.lib().dto_kkt_matrix(self._h, int(problem), _p(out)))
+        return out
+
+    def factor(self, problem: int = 0):
+        """(L, D) of P K P' = L D L' as dense arrays, P = permutation()."""
+        W = self.row_width
+        band = np.empty((self.dim, W))
+        D = np.empty(self.dim)
+        _lib.check(_lib.lib().dto_kkt_factor(self._h, int(problem), _p(band), _p(D)))
+        Lm = np.eye(self.dim)
+        for q in range(1, W):
+            idx = np.arange(q, self.dim)
+            Lm[idx, idx - q] = band[q:, q]
+        return Lm, D
+
+    def device_pointer(self, which: int, shard: int = 0) -> int:
+        p = _lib.lib().dto_kkt_device_pointer(self._h, int(which), int(shard))
+        if not p:
+            raise _lib.DtoError(-1, _lib.lib().dto_last_error().decode(errors="replace"))
+        return int(p)

@@ -39,13 +39,15 @@ typedef enum dto_status {
     DTO_ERR_MODEL = -4,        /* model library missing / wrong ABI / not compiled             */
     DTO_ERR_NO_HESSIAN = -5,   /* Hessian requested but a Cost was built without evaluate_hessian
                                   (the reference throws here: src/costs.jl:68)      */
-    DTO_ERR_STATE = -6         /* e.g. evaluation requested before dto_set_x                   */
+    DTO_ERR_STATE = -6,        /* e.g. evaluation requested before dto_set_x                   */
+    DTO_ERR_UNSUPPORTED = -7   /* the shape is outside what a kernel covers (e.g. KKT bandwidth) */
 } dto_status;
 
 typedef struct dto_model dto_model; /* a loaded generated model library (element device code)   */
 typedef struct dto_shape dto_shape; /* static tables of one problem shape (reference: NLPData's
                                        indices/sparsity fields, src/data.jl:106-121)            */
 typedef struct dto_batch dto_batch; /* B problems of one shape resident on 1..n devices         */
+typedef struct dto_kkt dto_kkt;     /* device-resident KKT systems of a batch (consumer of J, H)  */
 
 /* Description of one problem shape in terms of the model library's element kinds.
  * Mirrors the arguments of Solver(dynamics, objective, constraints, bounds; general_constraint,
@@ -173,6 +175,42 @@ int64_t dto_algorithmic_bytes_per_problem(const dto_shape* s);
 int dto_shape_compiled_gather(const dto_shape* s);
 /* dynamic shared memory per CTA of the knot kernel for `kernel_id` */
 int64_t dto_kernel_smem_bytes(const dto_shape* s, int kernel_id);
+
+/* ---- device-side consumer of the callbacks: batched KKT assembly + LDL'  ----
+ * Replaces the reference's own sketch of what is done with the callback outputs,
+ * /root/reference/examples/pendulum/pendulum.jl:138-211: for every problem of the batch
+ *     K = [ H + primal_reg*I   J' ; J   -dual_reg*I ],   h = [ grad f + J' lambda ; c ],
+ * K = L D L' (quasi-definite: no pivoting; the example uses QDLDL), sol = K \ h -- computed from the
+ * device-resident g, c, J, H, so only `sol` (N_z + N_c doubles per problem) crosses PCIe instead of
+ * J and H. All problems share one bandwidth-reducing ordering computed once on the host. */
+/* host-only symbolic analysis (works without a GPU): perm[p] = 1-based original index (variables
+ * 1..N_z, constraint rows N_z+1..N_z+N_c) placed at position p; *bandwidth = half bandwidth of
+ * the permuted matrix. Either output may be NULL. */
+int dto_kkt_analyze(const dto_shape* s, int64_t* perm, int64_t* bandwidth);
+/* fails with DTO_ERR_UNSUPPORTED when the ordered half bandwidth exceeds 31 */
+int dto_kkt_create(dto_batch* b, double primal_reg, double dual_reg, dto_kkt** out);
+void dto_kkt_destroy(dto_kkt* k);
+int64_t dto_kkt_dim(const dto_kkt* k);                       /* N_z + N_c                              */
+int64_t dto_kkt_bandwidth(const dto_kkt* k);                 /* half bandwidth after ordering          */
+int64_t dto_kkt_row_width(const dto_kkt* k);                 /* band entries kept per row: 16 or 32    */
+int64_t dto_kkt_factor_bytes_per_problem(const dto_kkt* k);  /* factor storage written + read per solve */
+int dto_kkt_permutation(const dto_kkt* k, int64_t* perm /* [dim], 1-based */);
+/* gradient + constraint + fused Jacobian/Hessian callbacks at the resident (z, lambda, sigma), then
+ * right-hand side, factorisation and solve; sol[B][dim] in the natural order [z; constraint rows]
+ * (NULL: leave it on the device). pendulum.jl:141-211 in one call. */
+int dto_kkt_solve(dto_kkt* k, double* sol);
+/* the same, enqueued on the shard streams without synchronising; with_callbacks = 0 reuses the
+ * g, c, J, H already on the device */
+int dto_kkt_launch(dto_kkt* k, int with_callbacks);
+/* which = 0: h [B][dim]; 1: sol [B][dim] (device -> host, after a solve) */
+int dto_kkt_get(dto_kkt* k, int which, double* out);
+/* inspection: dense row-major [dim][dim] assembled K of one problem (from the current device J, H,
+ * through the factor kernel's gather tables), and its factor in the permuted order:
+ * Lband[dim][row_width] with Lband[R][q] = L(R, R-q), D[dim]; P K P' = L D L' */
+int dto_kkt_matrix(dto_kkt* k, int64_t problem, double* dense);
+int dto_kkt_factor(dto_kkt* k, int64_t problem, double* Lband, double* D);
+/* which = 0 h, 1 sol, 2 factor storage */
+void* dto_kkt_device_pointer(dto_kkt* k, int which, int shard);
 
 #ifdef __cplusplus
 }
