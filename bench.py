@@ -184,6 +184,50 @@ def run_reference(args):
     return 0
 
 
+def bench_kkt(torch, n, stream, zp, lp, sp_, peak):
+    """Secondary measurement (not the headline): the device-resident consumer of J and H.
+    One step = gradient + constraint + fused Jacobian/Hessian callbacks + KKT right-hand side + banded
+    LDL' factorisation and solve for every problem of the batch (pendulum.jl:124-211 batched)."""
+    from dto_b200 import kkt as PK
+    B = n.batch
+    k = PK.KKTSystem(n)
+    steps = 30
+    out = {}
+    for name, cb in (("ms_kkt_kernels", False), ("ms_step", True)):
+        for _ in range(3):
+            k.launch(cb)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                k.launch(cb)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / steps
+    solp = torch.empty((B, k.dim), dtype=torch.float64).pin_memory().numpy()
+    for _ in range(2):
+        k.solve(solp, variables=zp, scaling=sp_, duals=lp)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        k.solve(solp, variables=zp, scaling=sp_, duals=lp)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / reps
+    alg = 8 * (n.num_jacobian + n.num_hessian + n.num_variables + 2 * n.num_constraint + 3 * k.dim) + 2 * k.factor_bytes_per_problem
+    gbs = alg * B / (out["ms_kkt_kernels"] * 1e-3) / 1e9
+    res = {"what": "device-resident KKT assembly + banded LDL' solve of all problems (consumer of J, H; SURVEY 8f N3)",
+           "dim": k.dim, "half_bandwidth": k.bandwidth, "ms_kkt_kernels": out["ms_kkt_kernels"], "ms_step_callbacks_plus_kkt": out["ms_step"],
+           "kkt_solves_per_s": B / (out["ms_kkt_kernels"] * 1e-3), "newton_steps_per_s": B / (out["ms_step"] * 1e-3),
+           "e2e_ms_host_z_lambda_to_host_solution": e2e_ms, "e2e_d2h_bytes": 8 * B * k.dim,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "algorithmic_bytes_per_problem": alg,
+                        "note": "read J,H,g,c,y once; write+read h; write+read the factor once; write the solution"}}
+    k.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -322,6 +366,8 @@ def run_ours(args):
             fp = _fp64_peak()
             line["fp64"] = {"codegen_ops_per_knot": ops, "achieved_gops": ops * B * T / (ms_per_step * 1e-3) / 1e9,
                             "peak_gdfma": fp / 1e9, "note": "cartpole RK3 is FP64-pipe bound (SURVEY 8d); ops = sympy count_ops"}
+        if world == 1 and not args.no_kkt:
+            line["kkt"] = bench_kkt(torch, n, stream, zp, lp, sp_, peak)
         if world == 1 and not args.no_cpu:
             co, mo = build_c_baseline(T)
             threads = host_threads()
@@ -347,6 +393,7 @@ def main():
     ap.add_argument("--T", type=int, default=101)
     ap.add_argument("--ref-sample", type=int, default=256, dest="ref_sample")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--no-kkt", action="store_true", dest="no_kkt")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200:

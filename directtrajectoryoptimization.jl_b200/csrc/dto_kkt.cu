@@ -40,12 +40,29 @@ __device__ __forceinline__ double shfl_g(double v, int src)
     return __shfl_sync(0xffffffffu, v, src, G);
 }
 
-// band entries of row (blk*G + i): slot w holds the column c = w (mod W) of [row-W+1, row]; G == W
+__device__ __forceinline__ void cp_async8_zfill(void* smem, const void* g, int src_size)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// band entries of row (blk*W + i): slot w holds the column c = w (mod W) of [row-W+1, row].
+// JbmH = (this problem's J) - nnz_H, so that a table entry s >= nnz_H addresses J[s - nnz_H].
 template <int W>
 __device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* __restrict__ Hb, const double* __restrict__ JbmH,
                                           int blk, int i, double (&X)[W])
 {
-    // JbmH = (this problem's J) - nnz_H, so that a table entry s >= nnz_H addresses J[s - nnz_H]
     const int32_t* src = a.src + ((size_t)blk * W) * W + i;
     const double reg = a.dreg[(size_t)blk * W + i];
     int32_t sidx[W];
@@ -62,18 +79,27 @@ __device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* _
     }
 }
 
-// One problem per group of G = W lanes (two problems per warp for W = 16). Row block = W rows.
+template <int W>
+struct KktSmem {
+    static constexpr int NG = 32 / W;                       // problems per warp
+    static constexpr int RING = 3;
+    static constexpr int SLOT = (W * W + W) * 8;            // one block of L columns + its y values
+    static constexpr int PER_GROUP = RING * SLOT + 2 * W * 8;
+    static constexpr int BYTES = 4 * NG * PER_GROUP;        // 4 warps per CTA
+};
+
+// One problem per group of W lanes (two problems per warp for W = 16). Row block = W rows.
 // BW = compile-time bound on the half bandwidth (<= W - 1).
 template <int W, int BW>
-__global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
+__global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const dto_kkt_args a)
 {
     constexpr int G = W;
-    constexpr int NG = 32 / G;                       // problems per warp
-    __shared__ __align__(16) double lcol_s[4][NG][2][W];  // un-scaled column of the current step, double-buffered
+    using SM = KktSmem<W>;
+    extern __shared__ __align__(16) unsigned char kkt_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int grp = lane / G, i = lane % G;
-    const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * NG + grp;
+    const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * SM::NG + grp;
     const bool valid = b0 < a.B;
     const int64_t b = valid ? b0 : a.B - 1;          // idle groups shadow the last problem, stores masked
     const double* Hb = a.H + b * a.nnz_H;
@@ -82,10 +108,13 @@ __global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
     const int nblk = a.nblk;
     double* Lg = a.L + (size_t)b * a.factor_stride;  // [nblk*W][W]: slot 0 = pivot d_j, slot q = L(j+q, j)
     double* Yg = Lg + (size_t)nblk * W * W;          // [nblk*W]: D^-1 L^-1 h
-    double (*lcol)[W] = lcol_s[wib][grp];
+    unsigned char* gsm = kkt_smem + (size_t)(wib * SM::NG + grp) * SM::PER_GROUP;
+    double* stage = reinterpret_cast<double*>(gsm);                              // forward: rows of block blk+2, [w][i]
+    double (*lcol)[W] = reinterpret_cast<double (*)[W]>(gsm + SM::RING * SM::SLOT);  // un-scaled column, double-buffered
 
     double A[W], Bv[W];
-    double ra, rb = 0.0;
+    double ra, rb = 0.0, rc = 0.0, regc = 0.0;
+    int32_t nidx[W];                                  // gather indices of the rows two blocks ahead
     load_rows<W>(a, Hb, Jb, 0, i, A);
     {
         const int32_t ip = a.iperm[i];
@@ -99,13 +128,37 @@ __global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
 #pragma unroll
         for (int w = 0; w < W; ++w) Bv[w] = 0.0;
     }
+    auto load_idx = [&](int blk) {
+        if (blk < nblk) {
+            const int32_t* src = a.src + ((size_t)blk * W) * W + i;
+#pragma unroll
+            for (int w = 0; w < W; ++w) nidx[w] = src[w * W];
+        }
+    };
+    load_idx(2);
 
     // ---------------- factor (right-looking) + forward solve ----------------
     // Step j = blk*W + s. v_r = A(r, j) (un-scaled column), l_r = v_r / d_j. The trailing update
     // A(r, c) -= l_r * v_c is applied to EVERY slot (c mod W) of a row without a lane mask: for c > r
     // that slot holds A(r, c - W), a column < j whose L value has already been published to HBM
     // and is never read from the registers again, and rows outside the band have l_r = 0.
+    // Rows of block blk+2 are gathered from J / H into shared memory by cp.async while block blk is
+    // being eliminated (their table indices were fetched one block earlier still).
     for (int blk = 0; blk < nblk; ++blk) {
+        const bool more = blk + 2 < nblk;
+        if (more) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int32_t sx = nidx[w];
+                const double* bp = (sx < a.nnz_H) ? Hb : Jb;
+                cp_async8_zfill(stage + w * W + i, sx >= 0 ? (const void*)(bp + sx) : (const void*)Hb, sx >= 0 ? 8 : 0);
+            }
+            cp_async_commit();
+            const int32_t ip = a.iperm[(size_t)(blk + 2) * W + i];
+            rc = ip >= 0 ? hb[ip] : 0.0;
+            regc = a.dreg[(size_t)(blk + 2) * W + i];
+            load_idx(blk + 3);
+        }
         double* LA = Lg + (size_t)blk * W * W + i;   // + s*W + (row - j) with immediates
 #pragma unroll
         for (int s = 0; s < G; ++s) {
@@ -148,10 +201,16 @@ __global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
 #pragma unroll
         for (int w = 0; w < W; ++w) A[w] = Bv[w];
         ra = rb;
-        if (blk + 2 < nblk) {
-            load_rows<W>(a, Hb, Jb, blk + 2, i, Bv);
-            const int32_t ip = a.iperm[(size_t)(blk + 2) * W + i];
-            rb = ip >= 0 ? hb[ip] : 0.0;
+        if (more) {
+            cp_async_wait<0>();
+            __syncwarp();
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const double v = stage[w * W + i];
+                Bv[w] = (w == i) ? v + regc : v;
+            }
+            rb = rc;
+            __syncwarp();   // the stage is rewritten at the top of the next block
         } else {
 #pragma unroll
             for (int w = 0; w < W; ++w) Bv[w] = 0.0;
@@ -164,26 +223,48 @@ __global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
     // ---------------- backward solve: x = L^-T y ----------------
     // Lane i owns COLUMN j = blk*W + i: slot w holds L(r, j) for the row r = w (mod W) of [j+1, j+W-1].
     // Rows are retired in descending order; the retired x_r is broadcast and the columns that reach it
-    // (same block: i < s; block below: i >= s + W - BW) subtract L(r, j) x_r.
-    auto load_cols = [&](int blk, double (&C)[W], double& acc) {
-        const double* Lblk = Lg + ((size_t)blk * W + i) * W;
+    // (same block: i < s; block below: i >= s + W - BW) subtract L(r, j) x_r. The factor streams back
+    // from HBM through a 3-slot cp.async ring (one 2 KB block of columns + its y per slot), two blocks
+    // ahead of use.
+    auto issue_cols = [&](int blk) {
+        if (blk >= 0) {
+            unsigned char* dst = gsm + (blk % SM::RING) * SM::SLOT;
+            const unsigned char* srcL = reinterpret_cast<const unsigned char*>(Lg + (size_t)blk * W * W);
+#pragma unroll
+            for (int k = 0; k < W / 2; ++k) cp_async16(dst + (k * W + i) * 16, srcL + (k * W + i) * 16);
+            if (i < W / 2) cp_async16(dst + W * W * 8 + i * 16, reinterpret_cast<const unsigned char*>(Yg + (size_t)blk * W) + i * 16);
+        }
+        cp_async_commit();
+    };
+    auto read_cols = [&](int blk, double (&C)[W], double& acc) {
+        const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
 #pragma unroll
         for (int w = 0; w < W; ++w) {
             const int q = (w - i) & (W - 1);
-            C[w] = (q >= 1 && q <= BW) ? Lblk[q] : 0.0;
+            C[w] = (q >= 1 && q <= BW) ? sl[i * W + q] : 0.0;
         }
-        acc = Yg[(size_t)blk * W + i];
+        acc = sl[W * W + i];
     };
     double xa, xp = 0.0;
-    load_cols(nblk - 1, A, xa);
-    if (nblk > 1) {
-        load_cols(nblk - 2, Bv, xp);
-    } else {
-#pragma unroll
-        for (int w = 0; w < W; ++w) Bv[w] = 0.0;
-    }
+    issue_cols(nblk - 1);
+    issue_cols(nblk - 2);
+    issue_cols(nblk - 3);
+    cp_async_wait<2>();
+    __syncwarp();
+    read_cols(nblk - 1, A, xa);
     double* solb = a.sol + b * a.dim;
     for (int blk = nblk - 1; blk >= 0; --blk) {
+        cp_async_wait<1>();
+        __syncwarp();
+        if (blk >= 1) {
+            read_cols(blk - 1, Bv, xp);
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) Bv[w] = 0.0;
+            xp = 0.0;
+        }
+        __syncwarp();            // slot blk % RING (read one iteration ago) is free again
+        issue_cols(blk - 3);
 #pragma unroll
         for (int s = G - 1; s >= 0; --s) {
             const int p = s & (W - 1);
@@ -198,14 +279,8 @@ __global__ void __launch_bounds__(128) kkt_band_kernel(const dto_kkt_args a)
 #pragma unroll
         for (int w = 0; w < W; ++w) A[w] = Bv[w];
         xa = xp;
-        if (blk - 2 >= 0) {
-            load_cols(blk - 2, Bv, xp);
-        } else {
-#pragma unroll
-            for (int w = 0; w < W; ++w) Bv[w] = 0.0;
-            xp = 0.0;
-        }
     }
+    cp_async_wait<0>();
 }
 
 template <int W>
@@ -258,7 +333,13 @@ template <int W, int BW>
 static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
 {
     const int64_t per_block = 4 * (32 / W);
-    kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, 0, st>>>(*a);
+    static bool configured = false;   // per instantiation; benign race (idempotent attribute)
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W>::BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W>::BYTES, st>>>(*a);
     return cudaGetLastError();
 }
 

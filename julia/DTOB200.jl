@@ -154,4 +154,28 @@ end
 # cost_spec / constraint_spec / general_spec follow the same three lines with the variable lists of
 # src/costs.jl:18-27, src/constraints.jl:27-40, src/general_constraint.jl:23-36.
 
+# ---------------------------------------------------------------- device-resident KKT consumer (dto_kkt_*)
+# What examples/pendulum/pendulum.jl:138-211 does with the callback outputs (assemble
+# [[H + primal_reg I, C'], [C, -dual_reg I]] and h = [grad + C'y; c], qdldl, solve!), for the whole
+# batch on the GPU; only the solution comes back.
+mutable struct BatchedKKT
+    handle::Ptr{Cvoid}
+    nlp::BatchedNLPData
+    dim::Int
+end
+function BatchedKKT(nlp::BatchedNLPData; primal_reg=1.0e-5, dual_reg=1.0e-5)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dto_kkt_create, libdto), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ref{Ptr{Cvoid}}), nlp.batch, primal_reg, dual_reg, h))
+    BatchedKKT(h[], nlp, Int(ccall((:dto_kkt_dim, libdto), Int64, (Ptr{Cvoid},), h[])))
+end
+"sol[dim, B] = K \\ h at (z, y) for every problem (column b = problem b; Julia is column-major, the ABI problem-major)"
+function solve!(sol::Matrix{Float64}, kkt::BatchedKKT, z::Matrix{Float64}, y::Matrix{Float64})
+    nlp = kkt.nlp
+    check(ccall((:dto_set_x, libdto), Cint, (Ptr{Cvoid}, Ptr{Float64}), nlp.batch, z))
+    fill!(nlp.sigma, 1.0)                                               # pendulum.jl:136 evaluates with sigma = 1.0
+    check(ccall((:dto_set_duals, libdto), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), nlp.batch, nlp.sigma, y))
+    check(ccall((:dto_kkt_solve, libdto), Cint, (Ptr{Cvoid}, Ptr{Float64}), kkt.handle, sol))
+    sol
+end
+
 end # module
