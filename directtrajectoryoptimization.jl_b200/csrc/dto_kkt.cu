@@ -23,7 +23,8 @@
 //                      (current block, next block) cover the rows a step can touch (half bandwidth
 //                      <= BW < W). Per step: pivot broadcast (shuffle), one reciprocal, the column of
 //                      L goes to shared memory (broadcast reads replace 2*BW shuffles) and to HBM
-//                      (one coalesced <= 120-byte store), then BW predicated DFMAs per row set. The
+//                      (one coalesced <= 120-byte store; BW+1 values per column, not W), then BW
+//                      DFMAs per row set. Rows two blocks ahead are gathered by cp.async. The
 //                      backward solve re-reads L column-wise (lane = column, slot = row mod W) so a
 //                      retired x_r costs one shuffle + one DFMA instead of a warp reduction.
 //   kkt_assemble_kernel test/inspection export of the assembled band (same gather as the factor kernel)
@@ -79,11 +80,13 @@ __device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* _
     }
 }
 
-template <int W>
+template <int W, int BW>
 struct KktSmem {
     static constexpr int NG = 32 / W;                       // problems per warp
     static constexpr int RING = 3;
-    static constexpr int SLOT = (W * W + W) * 8;            // one block of L columns + its y values
+    static constexpr int LW = (BW + 2) & ~1;                // doubles per stored column (dto_kkt_col_width)
+    static constexpr int SLOT = (W * LW + W) * 8;           // one block of L columns + its y values
+    static_assert(RING * SLOT >= W * W * 8, "the forward row stage lives in the ring area");
     static constexpr int PER_GROUP = RING * SLOT + 2 * W * 8;
     static constexpr int BYTES = 4 * NG * PER_GROUP;        // 4 warps per CTA
 };
@@ -94,7 +97,8 @@ template <int W, int BW>
 __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const dto_kkt_args a)
 {
     constexpr int G = W;
-    using SM = KktSmem<W>;
+    using SM = KktSmem<W, BW>;
+    constexpr int LW = SM::LW;
     extern __shared__ __align__(16) unsigned char kkt_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -106,8 +110,8 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const 
     const double* Jb = a.J + b * a.nnz_J - a.nnz_H;  // see load_rows
     const double* hb = a.rhs + b * a.dim;
     const int nblk = a.nblk;
-    double* Lg = a.L + (size_t)b * a.factor_stride;  // [nblk*W][W]: slot 0 = pivot d_j, slot q = L(j+q, j)
-    double* Yg = Lg + (size_t)nblk * W * W;          // [nblk*W]: D^-1 L^-1 h
+    double* Lg = a.L + (size_t)b * a.factor_stride;  // [nblk*W][LW]: slot 0 = pivot d_j, slot q = L(j+q, j)
+    double* Yg = Lg + (size_t)nblk * W * LW;         // [nblk*W]: D^-1 L^-1 h
     unsigned char* gsm = kkt_smem + (size_t)(wib * SM::NG + grp) * SM::PER_GROUP;
     double* stage = reinterpret_cast<double*>(gsm);                              // forward: rows of block blk+2, [w][i]
     double (*lcol)[W] = reinterpret_cast<double (*)[W]>(gsm + SM::RING * SM::SLOT);  // un-scaled column, double-buffered
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const 
             regc = a.dreg[(size_t)(blk + 2) * W + i];
             load_idx(blk + 3);
         }
-        double* LA = Lg + (size_t)blk * W * W + i;   // + s*W + (row - j) with immediates
+        double* LA = Lg + (size_t)blk * W * LW + i;  // + s*LW + (row - j) with immediates
 #pragma unroll
         for (int s = 0; s < G; ++s) {
             const int p = s & (W - 1);
@@ -176,11 +180,9 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const 
             const double dinv = 1.0 / d;
             const double lA = vA * dinv;
             const double lB = vB * dinv;
-            if (valid) {
-                if (inA) LA[s * W - s] = lA;
-                if (hasB && inB) LA[s * W - s + G] = lB;
-                if (i == s) LA[s * W - s] = d;
-            }
+            // (row - j) = i - s for set A (0 = the pivot slot), i + G - s for set B
+            if (valid && i >= s && i <= s + BW) LA[s * LW - s] = (i == s) ? d : lA;
+            if (hasB && inB && valid) LA[s * LW - s + G] = lB;
             __syncwarp();
             // forward substitution, then the D solve for row j
             const double yj = shfl_g<G>(ra, s);
@@ -229,10 +231,10 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const 
     auto issue_cols = [&](int blk) {
         if (blk >= 0) {
             unsigned char* dst = gsm + (blk % SM::RING) * SM::SLOT;
-            const unsigned char* srcL = reinterpret_cast<const unsigned char*>(Lg + (size_t)blk * W * W);
+            const unsigned char* srcL = reinterpret_cast<const unsigned char*>(Lg + (size_t)blk * W * LW);
 #pragma unroll
-            for (int k = 0; k < W / 2; ++k) cp_async16(dst + (k * W + i) * 16, srcL + (k * W + i) * 16);
-            if (i < W / 2) cp_async16(dst + W * W * 8 + i * 16, reinterpret_cast<const unsigned char*>(Yg + (size_t)blk * W) + i * 16);
+            for (int k = 0; k < LW / 2; ++k) cp_async16(dst + (k * W + i) * 16, srcL + (k * W + i) * 16);
+            if (i < W / 2) cp_async16(dst + W * LW * 8 + i * 16, reinterpret_cast<const unsigned char*>(Yg + (size_t)blk * W) + i * 16);
         }
         cp_async_commit();
     };
@@ -241,9 +243,9 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const 
 #pragma unroll
         for (int w = 0; w < W; ++w) {
             const int q = (w - i) & (W - 1);
-            C[w] = (q >= 1 && q <= BW) ? sl[i * W + q] : 0.0;
+            C[w] = (q >= 1 && q <= BW) ? sl[i * LW + q] : 0.0;   // (LW-1) odd => conflict-free over the lanes
         }
-        acc = sl[W * W + i];
+        acc = sl[W * LW + i];
     };
     double xa, xp = 0.0;
     issue_cols(nblk - 1);
@@ -335,11 +337,11 @@ static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
     const int64_t per_block = 4 * (32 / W);
     static bool configured = false;   // per instantiation; benign race (idempotent attribute)
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W>::BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W>::BYTES, st>>>(*a);
+    kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
     return cudaGetLastError();
 }
 
@@ -349,14 +351,15 @@ extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
     const int bw = a->bw;
+    const int bound = dto_kkt_bw_bound(a->W, bw);
     if (a->W == 16) {
-        if (bw <= 6) e = launch_band_t<16, 6>(a, st);
-        else if (bw <= 9) e = launch_band_t<16, 9>(a, st);
-        else if (bw <= 12) e = launch_band_t<16, 12>(a, st);
-        else if (bw <= 15) e = launch_band_t<16, 15>(a, st);
+        if (bound == 6) e = launch_band_t<16, 6>(a, st);
+        else if (bound == 9) e = launch_band_t<16, 9>(a, st);
+        else if (bound == 12) e = launch_band_t<16, 12>(a, st);
+        else e = launch_band_t<16, 15>(a, st);
     } else if (a->W == 32) {
-        if (bw <= 20) e = launch_band_t<32, 20>(a, st);
-        else if (bw <= 31) e = launch_band_t<32, 31>(a, st);
+        if (bound == 20) e = launch_band_t<32, 20>(a, st);
+        else e = launch_band_t<32, 31>(a, st);
     }
     return e == cudaSuccess ? 1 : -(int)e;
 }

@@ -17,7 +17,7 @@ typedef struct dto_kkt_args {
     int32_t W;           /* band entries kept per row = rows per block = lanes per problem (16 or 32) */
     int32_t bw;          /* half bandwidth of the ordered matrix (<= W - 1)                    */
     int32_t nblk;        /* ceil(dim / W) row blocks                                           */
-    int64_t factor_stride; /* doubles of factor storage per problem: nblk*W*W + nblk*W         */
+    int64_t factor_stride; /* doubles of factor storage per problem: nblk*W*LW + nblk*W, LW = dto_kkt_col_width */
     /* callback outputs / inputs of the shard (problem-major) */
     const double* H;     /* [B][nnz_H]  */
     const double* J;     /* [B][nnz_J]  */
@@ -34,10 +34,19 @@ typedef struct dto_kkt_args {
     const int32_t* colrow; /* [nnz_J] ... constraint row (0-based)                                   */
     /* work / outputs */
     double* rhs;         /* [B][dim] h = [grad f + J'y ; c], natural order                     */
-    double* L;           /* [B][factor_stride]: per problem [nblk*W][W] columns of L (slot 0 = pivot d_j,
+    double* L;           /* [B][factor_stride]: per problem [nblk*W][LW] columns of L (slot 0 = pivot d_j,
                             slot q = L(j+q, j)) followed by [nblk*W] D^-1 L^-1 h                 */
     double* sol;         /* [B][dim] K^-1 h, natural order                                     */
 } dto_kkt_args;
+
+/* The factor kernel is instantiated for a few bounds BW on the half bandwidth; a column of L is stored
+ * as LW = BW + 1 doubles rounded up to even (pivot, then L(j+1..j+BW, j)), so both sides must agree: */
+static inline int dto_kkt_bw_bound(int W, int bw)
+{
+    if (W == 16) return bw <= 6 ? 6 : bw <= 9 ? 9 : bw <= 12 ? 12 : 15;
+    return bw <= 20 ? 20 : 31;
+}
+static inline int dto_kkt_col_width(int W, int bw) { return (dto_kkt_bw_bound(W, bw) + 2) & ~1; }
 
 /* each returns the number of kernels enqueued (>= 0) or -(cudaError_t) */
 int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream);
