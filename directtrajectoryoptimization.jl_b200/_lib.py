@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "dto_kkt_factor_bytes_per_problem": (i64, [vp]),
         "dto_kkt_permutation": (C.c_int, [vp, i64p]),
         "dto_kkt_solve": (C.c_int, [vp, vp]),
+        "dto_kkt_solve_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int]),
         "dto_kkt_launch": (C.c_int, [vp, C.c_int]),
         "dto_kkt_get": (C.c_int, [vp, C.c_int, vp]),
         "dto_kkt_matrix": (C.c_int, [vp, i64, vp]),

@@ -54,9 +54,21 @@ class KKTSystem:
         _lib.check(_lib.lib().dto_kkt_permutation(self._h, perm.ctypes.data_as(C.POINTER(C.c_int64))))
         return perm
 
-    def solve(self, solution=None, variables=None, scaling=None, duals=None):
+    def solve(self, solution=None, variables=None, scaling=None, duals=None, chunks: int = 0):
         """Callbacks at (z, sigma, y) + assembly + LDL' + solve; `solution` [B, dim] is written in
-        place (None: results stay on the device)."""
+        place (None: results stay on the device). With host `variables`, `duals` and `solution` all
+        given, the call is one chunk-pipelined host call (copies overlap the kernels)."""
+        if variables is not None and duals is not None and solution is not None:
+            from .evaluator import _f64
+            nlp = self.nlp
+            z = _f64(variables, (nlp.batch, nlp.num_variables), "variables")
+            lam = _f64(duals, (nlp.batch, nlp.num_constraint), "duals")
+            sg = None
+            if scaling is not None:
+                sg = np.ascontiguousarray(np.broadcast_to(np.asarray(scaling, dtype=np.float64), (nlp.batch,)))
+            sol = _out(solution, (nlp.batch, self.dim), "solution")
+            _lib.check(_lib.lib().dto_kkt_solve_host(self._h, _p(z), _p(sg) if sg is not None else None, _p(lam), _p(sol), int(chunks)))
+            return solution
         if variables is not None:
             self.nlp.set_x(variables)
         if duals is not None:

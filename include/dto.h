@@ -199,6 +199,11 @@ int dto_kkt_permutation(const dto_kkt* k, int64_t* perm /* [dim], 1-based */);
  * right-hand side, factorisation and solve; sol[B][dim] in the natural order [z; constraint rows]
  * (NULL: leave it on the device). pendulum.jl:141-211 in one call. */
 int dto_kkt_solve(dto_kkt* k, double* sol);
+/* the same as ONE pipelined host call: host z, lambda (and sigma; NULL = 1.0 for every problem, as in
+ * pendulum.jl:136) in -- host sol out. Each shard is cut into `nchunks` (<= 0: library default)
+ * sub-batches whose copy-in, kernels and copy-out overlap over several streams; page-locked host
+ * buffers are needed for the overlap to happen. */
+int dto_kkt_solve_host(dto_kkt* k, const double* z, const double* sigma, const double* lambda, double* sol, int nchunks);
 /* the same, enqueued on the shard streams without synchronising; with_callbacks = 0 reuses the
  * g, c, J, H already on the device */
 int dto_kkt_launch(dto_kkt* k, int with_callbacks);
