@@ -392,11 +392,23 @@ class Solver:
         actions = [z[us[t] - 1: us[t] - 1 + nu[t]].copy() for t in range(self.nlp.T - 1)]
         return states, actions
 
-    def solve(self):
-        """solve!(solver) = MOI.optimize!(Ipopt) (src/solver.jl:45-47). Ipopt stays on the CPU and is the
-        CALLER of this package's hot path; it is not part of it and is not available in this image."""
-        raise RuntimeError("solve!: libipopt is not available here; this package provides the batched NLP callbacks "
-                           "(solver.nlp.eval_*) that an Ipopt driver calls. See INTEGRATION.md.")
+    def solve(self, options: Optional[dict] = None, record_iterates: bool = False):
+        """solve!(solver) (src/solver.jl:45-47) for every problem of the batch: B per-problem NLP solvers
+        run in lock step and their callbacks rendezvous into batched GPU calls (driver.py).
+        The reference's caller is Ipopt, which is not available in this image; the per-problem solver is
+        SciPy's `trust-constr` (same five callbacks, same sparsity structures, same bounds). Returns the
+        per-problem solver results; `get_trajectory(problem)` then returns the final iterate."""
+        from .driver import solve_batch
+        opts = dict(options or {})
+        ref_opts = self.options if isinstance(self.options, dict) else {}
+        if "tol" in ref_opts and "gtol" not in opts:        # Options.tol (src/options.jl:7)
+            opts["gtol"] = float(ref_opts["tol"])
+        if "max_iter" in ref_opts and "maxiter" not in opts:  # Options.max_iter (src/options.jl:9)
+            opts["maxiter"] = int(ref_opts["max_iter"])
+        Z, results, broker, iterates = solve_batch(self.nlp, self._initial, options=opts, record_iterates=record_iterates)
+        self.nlp.set_x(Z)   # get_trajectory returns the evaluator's last z (src/solver.jl:41-43)
+        self.results, self.broker, self.iterates = results, broker, iterates
+        return results
 
 
 def initialize_states(solver: Solver, states):

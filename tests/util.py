@@ -88,3 +88,45 @@ def assert_close(name, got, ref, rtol=RTOL, atol=ATOL):
         worst = np.nanmax(np.where(np.abs(ref) > 0, err / np.maximum(np.abs(ref), 1e-300), 0))
         raise AssertionError(f"{name}: {len(idx)} of {got.size} values differ beyond rtol={rtol}/atol={atol}; "
                              f"first at {i}: got {got[i]!r} ref {ref[i]!r}; worst rel {worst:.3e}")
+
+
+class OracleBatch:
+    """The CPU oracle behind the batched evaluator interface (B problems evaluated one by one): the
+    reference arm for driver tests -- same solver above, oracle callbacks below."""
+
+    def __init__(self, osolver, batch: int):
+        self.o = osolver.nlp
+        self.batch = batch
+        self.num_variables = self.o.num_variables
+        self.num_constraint = self.o.num_constraint
+        self.num_jacobian = self.o.num_jacobian
+        self.num_hessian = len(self.o.hessian_lagrangian_sparsity)
+        self.variable_bounds = self.o.variable_bounds
+        self.constraint_bounds = self.o.constraint_bounds
+
+    def jacobian_structure_arrays(self):
+        s = self.o.jacobian_structure()
+        return np.array([i for i, _ in s], dtype=np.int64), np.array([j for _, j in s], dtype=np.int64)
+
+    def hessian_lagrangian_structure_arrays(self):
+        s = self.o.hessian_lagrangian_structure()
+        return np.array([i for i, _ in s], dtype=np.int64), np.array([j for _, j in s], dtype=np.int64)
+
+    def eval_objective(self, Z):
+        return np.array([self.o.eval_objective(Z[b]) for b in range(self.batch)])
+
+    def eval_objective_gradient(self, G, Z):
+        for b in range(self.batch):
+            self.o.eval_objective_gradient(G[b], Z[b])
+
+    def eval_constraint(self, Cv, Z):
+        for b in range(self.batch):
+            self.o.eval_constraint(Cv[b], Z[b])
+
+    def eval_constraint_jacobian(self, J, Z):
+        for b in range(self.batch):
+            self.o.eval_constraint_jacobian(J[b], Z[b])
+
+    def eval_hessian_lagrangian(self, H, Z, sigma, lam):
+        for b in range(self.batch):
+            self.o.eval_hessian_lagrangian(H[b], Z[b], float(sigma[b]), lam[b])
