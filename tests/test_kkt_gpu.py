@@ -184,6 +184,55 @@ def test_kkt_heterogeneous_shape():
     pn.close()
 
 
+def test_kkt_two_devices():
+    """Row (e): problems are independent, a shard per device, no collective -- the KKT consumer follows the
+    batch's shards. Needs 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    name, kw, B = "cartpole", dict(T=101), 301
+    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, 2)
+    k1 = PK.KKTSystem(pn)
+    sol1 = np.empty((B, k1.dim))
+    k1.solve(sol1, variables=z, scaling=sigma, duals=lam)
+    k1.close(); pn.close()
+    pn2 = D.solver_from(M.BUILDERS[name](D, **kw), batch=B, devices=[0, 1]).nlp
+    pn2.set_parameters(w)
+    k2 = PK.KKTSystem(pn2)
+    sol2 = np.empty((B, k2.dim))
+    k2.solve(sol2, variables=z, scaling=sigma, duals=lam)
+    assert np.array_equal(sol1, sol2)
+    sol3 = np.empty_like(sol2)
+    k2.solve(sol3)                      # resident path on both devices
+    assert np.array_equal(sol1, sol3)
+    k2.close(); pn2.close()
+
+
+def test_kkt_nan_and_singular_pass_through():
+    """Reference behaviour: non-finite values are passed on unchecked. A NaN in one problem's
+    z makes that problem's solution non-finite and leaves the other problems' solutions bit-identical; a
+    zero pivot (no regularisation, all-zero multipliers and a zero Hessian block) produces Inf/NaN, no hang."""
+    name, kw, B = "pendulum", dict(), 6
+    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, 1)
+    kkt = PK.KKTSystem(pn)
+    sol = np.empty((B, kkt.dim))
+    kkt.solve(sol, variables=z, scaling=sigma, duals=lam)
+    z2 = z.copy()
+    z2[3, 5] = np.nan
+    sol2 = np.empty_like(sol)
+    kkt.solve(sol2, variables=z2, scaling=sigma, duals=lam)
+    assert not np.all(np.isfinite(sol2[3]))
+    keep = [b for b in range(B) if b != 3]
+    assert np.array_equal(sol2[keep], sol[keep])
+    kkt.close()
+    k0 = PK.KKTSystem(pn, primal_reg=0.0, dual_reg=0.0)
+    sol3 = np.empty_like(sol)
+    k0.solve(sol3, variables=z, scaling=sigma, duals=lam)   # must return (finite or not), never hang
+    assert sol3.shape == sol.shape
+    k0.close()
+    pn.close()
+
+
 def test_kkt_state_errors():
     pn = D.solver_from(M.BUILDERS["pendulum"](D), batch=2).nlp
     kkt = PK.KKTSystem(pn)
