@@ -55,6 +55,30 @@ def test_oracle_pendulum_script_check():
     assert np.array_equal(h[nz:], out["c"])
 
 
+def test_oracle_reproduces_kkt_golden():
+    """tests/golden/kkt_*.npz (make_golden_kkt.py): same code, same inputs => bit-identical; and the frozen
+    solutions satisfy the script's own check against a dense LU solve."""
+    import os
+    from golden.make_golden import tag
+    from golden.make_golden_kkt import KKT_GOLDEN, REG
+    from util import oracle_parameters
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    for name, kw, _ in KKT_GOLDEN:
+        fx = np.load(os.path.join(here, tag(name, kw) + ".npz"))
+        gk = np.load(os.path.join(here, "kkt_" + tag(name, kw) + ".npz"))
+        model = M.BUILDERS[name](O, **kw)
+        solver = O.solver_from(model)
+        for b in range(fx["z"].shape[0]):
+            p = oracle_parameters(model, fx["w"][b])
+            if p is not None:
+                solver.set_parameters(p)
+            r = OK.kkt_solve(solver.nlp, fx["z"][b], fx["lam"][b], REG, REG)
+            assert np.array_equal(r["K"], gk["K"][b]) and np.array_equal(r["h"], gk["h"][b])
+            assert np.array_equal(r["sol"], gk["sol"][b])
+            ref = np.linalg.solve(gk["K"][b], gk["h"][b])
+            assert np.max(np.abs(gk["sol"][b] - ref)) <= 1e-6 * max(1.0, np.max(np.abs(ref)))
+
+
 def test_oracle_qdldl_with_permutation():
     r = np.random.default_rng(7)
     n1, n2 = 9, 5

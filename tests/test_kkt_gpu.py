@@ -103,6 +103,33 @@ def test_kkt_matches_oracle(name, kw, B, config, reg):
     pn.close()
 
 
+def test_kkt_matches_golden_fixtures():
+    """Product vs the committed fixtures tests/golden/kkt_*.npz (oracle outputs frozen by
+    make_golden_kkt.py): K and h to 1e-12, solution within cond-scaled rounding."""
+    import os
+    from golden.make_golden import tag
+    from golden.make_golden_kkt import KKT_GOLDEN, REG
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    for name, kw, _ in KKT_GOLDEN:
+        fx = np.load(os.path.join(here, tag(name, kw) + ".npz"))
+        gk = np.load(os.path.join(here, "kkt_" + tag(name, kw) + ".npz"))
+        B = fx["z"].shape[0]
+        pn = D.solver_from(M.BUILDERS[name](D, **kw), batch=B).nlp
+        if pn.num_parameter:
+            pn.set_parameters(fx["w"])
+        kkt = PK.KKTSystem(pn, REG, REG)
+        sol = np.empty((B, kkt.dim))
+        kkt.solve(sol, variables=fx["z"], scaling=np.ones(B), duals=fx["lam"])
+        h = kkt.rhs()
+        for b in range(B):
+            assert_close(f"{name} K[{b}]", kkt.matrix(b), gk["K"][b])
+            assert_close(f"{name} h[{b}]", h[b], gk["h"][b], rtol=1e-12, atol=1e-13)
+            tol = 50 * np.linalg.cond(gk["K"][b]) * np.finfo(float).eps
+            assert np.max(np.abs(sol[b] - gk["sol"][b])) <= tol * max(1.0, np.max(np.abs(gk["sol"][b])))
+        kkt.close()
+        pn.close()
+
+
 def test_kkt_full_size_properties():
     """cartpole T=101, B=512: every problem's solution satisfies K x = h to rounding (K rebuilt on the
     host from the GPU's J, H), results do not depend on sharding, and a second solve is bit-identical."""
