@@ -41,15 +41,21 @@ def main():
         fx = np.load(os.path.join(HERE, tag(name, kw) + ".npz"))
         model = M.BUILDERS[name](O, **kw)
         solver = O.solver_from(model)
-        Ks, hs, sols = [], [], []
+        Ks, hs, sols, refs = [], [], [], []
         for b in range(fx["z"].shape[0]):
             p = oracle_parameters(model, fx["w"][b])
             if p is not None:
                 solver.set_parameters(p)
             r = OK.kkt_solve(solver.nlp, fx["z"][b], fx["lam"][b], REG, REG)
             Ks.append(r["K"]); hs.append(r["h"]); sols.append(r["sol"])
+            # accurate reference: dense LU with partial pivoting + one step of iterative refinement (the
+            # natural-ordering no-pivot factorisation above loses up to 5e-7 on the acrobot systems,
+            # which are not quasi-definite for random multipliers)
+            x = np.linalg.solve(r["K"], r["h"])
+            x = x + np.linalg.solve(r["K"], r["h"] - r["K"] @ x)
+            refs.append(x)
         path = os.path.join(HERE, "kkt_" + tag(name, kw) + ".npz")
-        np.savez_compressed(path, K=np.array(Ks), h=np.array(hs), sol=np.array(sols), reg=REG)
+        np.savez_compressed(path, K=np.array(Ks), h=np.array(hs), sol=np.array(sols), sol_lu=np.array(refs), reg=REG)
         print("wrote", path, np.array(Ks).shape)
 
 
