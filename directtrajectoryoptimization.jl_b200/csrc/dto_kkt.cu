@@ -335,11 +335,11 @@ template <int W, int BW>
 static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
 {
     const int64_t per_block = 4 * (32 / W);
-    static bool configured = false;   // per instantiation; benign race (idempotent attribute)
-    if (!configured) {
+    // the opt-in is per device and a batch may span several: set it on every launch (a cheap driver call
+    // next to a >= 100 us kernel) instead of caching it per process
+    if (KktSmem<W, BW>::BYTES > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
     return cudaGetLastError();

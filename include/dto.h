@@ -187,7 +187,8 @@ int64_t dto_kernel_smem_bytes(const dto_shape* s, int kernel_id);
  * 1..N_z, constraint rows N_z+1..N_z+N_c) placed at position p; *bandwidth = half bandwidth of
  * the permuted matrix. Either output may be NULL. */
 int dto_kkt_analyze(const dto_shape* s, int64_t* perm, int64_t* bandwidth);
-/* fails with DTO_ERR_UNSUPPORTED when the ordered half bandwidth exceeds 31 */
+/* fails with DTO_ERR_UNSUPPORTED when the ordered half bandwidth exceeds 31. The handle borrows the
+ * batch: destroy it BEFORE dto_batch_destroy(b); like the batch it is used from one host thread at a time. */
 int dto_kkt_create(dto_batch* b, double primal_reg, double dual_reg, dto_kkt** out);
 void dto_kkt_destroy(dto_kkt* k);
 int64_t dto_kkt_dim(const dto_kkt* k);                       /* N_z + N_c                              */

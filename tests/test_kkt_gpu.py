@@ -224,14 +224,19 @@ def test_kkt_two_devices():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 CUDA devices")
-    name, kw, B = "cartpole", dict(T=101), 301
-    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, 2)
+    _two_device_case("cartpole", dict(T=101), 301, 2)
+    _two_device_case("acrobot", dict(T=9), 70, 3)     # half bandwidth 14: > 48 KB shared memory, opt-in per device
+
+
+def _two_device_case(name, kw, B, config):
+    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, config)
     k1 = PK.KKTSystem(pn)
     sol1 = np.empty((B, k1.dim))
     k1.solve(sol1, variables=z, scaling=sigma, duals=lam)
     k1.close(); pn.close()
     pn2 = D.solver_from(M.BUILDERS[name](D, **kw), batch=B, devices=[0, 1]).nlp
-    pn2.set_parameters(w)
+    if pn2.num_parameter:
+        pn2.set_parameters(w)
     k2 = PK.KKTSystem(pn2)
     sol2 = np.empty((B, k2.dim))
     k2.solve(sol2, variables=z, scaling=sigma, duals=lam)
