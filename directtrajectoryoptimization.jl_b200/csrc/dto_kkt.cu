@@ -91,6 +91,77 @@ struct KktSmem {
     static constexpr int BYTES = 4 * NG * PER_GROUP;        // 4 warps per CTA
 };
 
+// ---------------- backward solve: x = L^-T y (shared by both factor kernels) ----------------
+template <int W, int BW>
+__device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned char* gsm, const double* Lg, const double* Yg, int nblk, int i,
+                                             bool valid, int64_t b)
+{
+    constexpr int G = W;
+    using SM = KktSmem<W, BW>;
+    constexpr int LW = SM::LW;
+    double A[W], Bv[W];
+    // Lane i owns COLUMN j = blk*W + i: slot w holds L(r, j) for the row r = w (mod W) of [j+1, j+W-1].
+    // Rows are retired in descending order; the retired x_r is broadcast and the columns that reach it
+    // (same block: i < s; block below: i >= s + W - BW) subtract L(r, j) x_r. The factor streams back
+    // from HBM through a 3-slot cp.async ring (one 2 KB block of columns + its y per slot), two blocks
+    // ahead of use.
+    auto issue_cols = [&](int blk) {
+        if (blk >= 0) {
+            unsigned char* dst = gsm + (blk % SM::RING) * SM::SLOT;
+            const unsigned char* srcL = reinterpret_cast<const unsigned char*>(Lg + (size_t)blk * W * LW);
+#pragma unroll
+            for (int k = 0; k < LW / 2; ++k) cp_async16(dst + (k * W + i) * 16, srcL + (k * W + i) * 16);
+            if (i < W / 2) cp_async16(dst + W * LW * 8 + i * 16, reinterpret_cast<const unsigned char*>(Yg + (size_t)blk * W) + i * 16);
+        }
+        cp_async_commit();
+    };
+    auto read_cols = [&](int blk, double (&C)[W], double& acc) {
+        const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int q = (w - i) & (W - 1);
+            C[w] = (q >= 1 && q <= BW) ? sl[i * LW + q] : 0.0;   // (LW-1) odd => conflict-free over the lanes
+        }
+        acc = sl[W * LW + i];
+    };
+    double xa, xp = 0.0;
+    issue_cols(nblk - 1);
+    issue_cols(nblk - 2);
+    issue_cols(nblk - 3);
+    cp_async_wait<2>();
+    __syncwarp();
+    read_cols(nblk - 1, A, xa);
+    double* solb = a.sol + b * a.dim;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        cp_async_wait<1>();
+        __syncwarp();
+        if (blk >= 1) {
+            read_cols(blk - 1, Bv, xp);
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) Bv[w] = 0.0;
+            xp = 0.0;
+        }
+        __syncwarp();            // slot blk % RING (read one iteration ago) is free again
+        issue_cols(blk - 3);
+#pragma unroll
+        for (int s = G - 1; s >= 0; --s) {
+            const int p = s & (W - 1);
+            const double xr = shfl_g<G>(xa, s);
+            if (i < s && i >= s - BW) xa = fma(-A[p], xr, xa);
+            if (s - BW < 0) {
+                if (i >= s + G - BW) xp = fma(-Bv[p], xr, xp);
+            }
+        }
+        const int32_t ip = a.iperm[(size_t)blk * W + i];
+        if (ip >= 0 && valid) solb[ip] = xa;
+#pragma unroll
+        for (int w = 0; w < W; ++w) A[w] = Bv[w];
+        xa = xp;
+    }
+    cp_async_wait<0>();
+}
+
 // One problem per group of W lanes (two problems per warp for W = 16). Row block = W rows.
 // BW = compile-time bound on the half bandwidth (<= W - 1).
 template <int W, int BW>
@@ -222,67 +293,148 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const 
     __syncwarp();
     __threadfence_block();
 
-    // ---------------- backward solve: x = L^-T y ----------------
-    // Lane i owns COLUMN j = blk*W + i: slot w holds L(r, j) for the row r = w (mod W) of [j+1, j+W-1].
-    // Rows are retired in descending order; the retired x_r is broadcast and the columns that reach it
-    // (same block: i < s; block below: i >= s + W - BW) subtract L(r, j) x_r. The factor streams back
-    // from HBM through a 3-slot cp.async ring (one 2 KB block of columns + its y per slot), two blocks
-    // ahead of use.
-    auto issue_cols = [&](int blk) {
-        if (blk >= 0) {
-            unsigned char* dst = gsm + (blk % SM::RING) * SM::SLOT;
-            const unsigned char* srcL = reinterpret_cast<const unsigned char*>(Lg + (size_t)blk * W * LW);
+    kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-row-set factor kernel (half bandwidth BW <= W - M, M in {4, 8}).
+// A lane's row of block blk is finished right after step s = i, and its row of block blk+1 is first
+// touched at step i + (W - BW) >= i + M, so ONE register row per lane is enough if lanes hand over to
+// their next row in batches of M: at step t = M, 2M, .., W the lanes [t - M, t) store their finished
+// y value and take their next row from the shared-memory stage that cp.async filled one block earlier.
+// Per elimination step every lane then has at most one live row: one select, one multiply by 1/d, one
+// shared-memory store of the un-scaled column entry (slot (i - s - 1) mod W; the pivot lane uses the
+// free slot W - 1 to broadcast its right-hand-side entry), one predicated store of the L entry, and BW
+// DFMAs -- about half the instructions of the two-set kernel above.
+template <int W, int BW>
+struct KktSmemS {
+    using B = KktSmem<W, BW>;
+    static constexpr int AREA = (B::RING * B::SLOT > 2 * W * W * 8) ? B::RING * B::SLOT : 2 * W * W * 8;
+    static constexpr int PER_GROUP = AREA + 2 * W * 8;
+    static constexpr int BYTES = 4 * B::NG * PER_GROUP;
+};
+
+template <int W, int BW, int M>
+__global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(const dto_kkt_args a)
+{
+    static_assert(M <= W - BW && W % M == 0 && BW <= W - 3, "hand-over period must not exceed W - BW; slot W-1 must be free");
+    constexpr int G = W;
+    using SM = KktSmem<W, BW>;
+    using SS = KktSmemS<W, BW>;
+    constexpr int LW = SM::LW;
+    extern __shared__ __align__(16) unsigned char kkt_smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int grp = lane / G, i = lane % G;
+    const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * SM::NG + grp;
+    const bool valid = b0 < a.B;
+    const int64_t b = valid ? b0 : a.B - 1;
+    const double* Hb = a.H + b * a.nnz_H;
+    const double* Jb = a.J + b * a.nnz_J - a.nnz_H;  // see load_rows
+    const double* hb = a.rhs + b * a.dim;
+    const int nblk = a.nblk;
+    double* Lg = a.L + (size_t)b * a.factor_stride;
+    double* Yg = Lg + (size_t)nblk * W * LW;
+    unsigned char* gsm = kkt_smem + (size_t)(wib * SM::NG + grp) * SS::PER_GROUP;
+    double* stage = reinterpret_cast<double*>(gsm);                        // [2][W][W]: rows of blocks blk+1 / blk+2
+    double (*lcol)[W] = reinterpret_cast<double (*)[W]>(gsm + SS::AREA);   // un-scaled column, double-buffered
+
+    double R[W];
+    double rr;
+    double rn1 = 0.0, regn1 = 1.0, rn2 = 0.0, regn2 = 1.0;   // rhs / diagonal shift of this lane's rows in blocks blk+1, blk+2
+    int32_t nidx[W];
+    load_rows<W>(a, Hb, Jb, 0, i, R);
+    {
+        const int32_t ip = a.iperm[i];
+        rr = ip >= 0 ? hb[ip] : 0.0;
+    }
+    auto load_idx = [&](int blk) {
+        if (blk < nblk) {
+            const int32_t* src = a.src + ((size_t)blk * W) * W + i;
 #pragma unroll
-            for (int k = 0; k < LW / 2; ++k) cp_async16(dst + (k * W + i) * 16, srcL + (k * W + i) * 16);
-            if (i < W / 2) cp_async16(dst + W * LW * 8 + i * 16, reinterpret_cast<const unsigned char*>(Yg + (size_t)blk * W) + i * 16);
+            for (int w = 0; w < W; ++w) nidx[w] = src[w * W];
+        }
+    };
+    // gather the rows of block `blk` (indices in nidx) into stage[blk & 1]; always commits one group
+    auto issue_rows = [&](int blk, double& rn, double& regn) {
+        if (blk < nblk) {
+            double* st = stage + (blk & 1) * W * W;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int32_t sx = nidx[w];
+                const double* bp = (sx < a.nnz_H) ? Hb : Jb;
+                cp_async8_zfill(st + w * W + i, sx >= 0 ? (const void*)(bp + sx) : (const void*)Hb, sx >= 0 ? 8 : 0);
+            }
+            const int32_t ip = a.iperm[(size_t)blk * W + i];
+            rn = ip >= 0 ? hb[ip] : 0.0;
+            regn = a.dreg[(size_t)blk * W + i];
         }
         cp_async_commit();
     };
-    auto read_cols = [&](int blk, double (&C)[W], double& acc) {
-        const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
+    load_idx(1);
+    issue_rows(1, rn1, regn1);
+    load_idx(2);
+
+    for (int blk = 0; blk < nblk; ++blk) {
+        issue_rows(blk + 2, rn2, regn2);          // consumed during block blk + 1
+        load_idx(blk + 3);
+        const bool has_next = blk + 1 < nblk;
+        double* stn = stage + ((blk + 1) & 1) * W * W + i;
+        double* LA = Lg + (size_t)blk * W * LW;
+        bool staged = false;
 #pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const int q = (w - i) & (W - 1);
-            C[w] = (q >= 1 && q <= BW) ? sl[i * LW + q] : 0.0;   // (LW-1) odd => conflict-free over the lanes
-        }
-        acc = sl[W * LW + i];
-    };
-    double xa, xp = 0.0;
-    issue_cols(nblk - 1);
-    issue_cols(nblk - 2);
-    issue_cols(nblk - 3);
-    cp_async_wait<2>();
-    __syncwarp();
-    read_cols(nblk - 1, A, xa);
-    double* solb = a.sol + b * a.dim;
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        cp_async_wait<1>();
-        __syncwarp();
-        if (blk >= 1) {
-            read_cols(blk - 1, Bv, xp);
-        } else {
-#pragma unroll
-            for (int w = 0; w < W; ++w) Bv[w] = 0.0;
-            xp = 0.0;
-        }
-        __syncwarp();            // slot blk % RING (read one iteration ago) is free again
-        issue_cols(blk - 3);
-#pragma unroll
-        for (int s = G - 1; s >= 0; --s) {
+        for (int s = 0; s < G; ++s) {
             const int p = s & (W - 1);
-            const double xr = shfl_g<G>(xa, s);
-            if (i < s && i >= s - BW) xa = fma(-A[p], xr, xa);
-            if (s - BW < 0) {
-                if (i >= s + G - BW) xp = fma(-Bv[p], xr, xp);
+            // lanes below the last hand-over point already hold their row of block blk+1
+            const bool live = (i > s) || (i < (s & ~(M - 1)));
+            const double v = live ? R[p] : 0.0;
+            double* vs = lcol[s & 1];
+            vs[(i - s - 1) & (W - 1)] = v;                       // lane s (v = 0) lands on the free slot W-1 ...
+            if (i == s) vs[W - 1] = rr;                          // ... which carries y_j instead
+            const double d = shfl_g<G>(R[p], s);
+            const double dinv = 1.0 / d;
+            const double l = v * dinv;
+            const int qi = (i - s) & (W - 1);                   // row - j
+            if (valid && qi >= 1 && qi <= BW) LA[s * LW + qi] = l;
+            if (valid && i == s) LA[s * LW] = d;
+            __syncwarp();
+            const double yj = vs[W - 1];
+            rr = fma(-l, yj, rr);
+            if (i == s) rr = yj * dinv;
+            const double nl = -l;
+#pragma unroll
+            for (int q = 1; q <= BW; ++q) R[(p + q) & (W - 1)] = fma(nl, vs[q - 1], R[(p + q) & (W - 1)]);
+            if (((s + 1) & (M - 1)) == 0) {
+                // hand-over: lanes [s + 1 - M, s] have finished their row of this block
+                if (!staged) {
+                    cp_async_wait<1>();                          // this lane's copies of block blk+1 have landed
+                    __syncwarp();
+                    // reference: K[i,i] += primal_reg / -= dual_reg after the assignment; each lane fixes the
+                    // diagonal entry of ITS row in the stage (slot w = i), or clears its row past the last block
+                    if (has_next) {
+                        stn[i * W] += regn1;
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; ++w) stage[((blk + 1) & 1) * W * W + w * W + i] = 0.0;
+                    }
+                    staged = true;
+                }
+                if (i >= s + 1 - M && i <= s) {
+                    if (valid) Yg[(size_t)blk * W + i] = rr;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) R[w] = stn[w * W];
+                    rr = has_next ? rn1 : 0.0;
+                }
             }
         }
-        const int32_t ip = a.iperm[(size_t)blk * W + i];
-        if (ip >= 0 && valid) solb[ip] = xa;
-#pragma unroll
-        for (int w = 0; w < W; ++w) A[w] = Bv[w];
-        xa = xp;
+        rn1 = rn2;
+        regn1 = regn2;
+        __syncwarp();   // every lane has taken its row: stage[(blk+1)&1] may be refilled (block blk+3) next iteration
     }
     cp_async_wait<0>();
+    __syncwarp();
+    __threadfence_block();
+    kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
 }
 
 template <int W>
@@ -345,20 +497,34 @@ static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <int W, int BW, int M>
+static cudaError_t launch_band_s(const dto_kkt_args* a, cudaStream_t st)
+{
+    const int64_t per_block = 4 * (32 / W);
+    if (KktSmemS<W, BW>::BYTES > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel_s<W, BW, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmemS<W, BW>::BYTES);
+        if (e != cudaSuccess) return e;
+    }
+    kkt_band_kernel_s<W, BW, M><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmemS<W, BW>::BYTES, st>>>(*a);
+    return cudaGetLastError();
+}
+
+// variant: 0 = default (two-row-set kernel), 2 = single-row-set kernel where the bandwidth allows it (measured
+// slower: cartpole 0.399 vs 0.346 ms, car 2.79 vs 2.35 ms -- profiles/kkt_r01_history.jsonl tags v7 / v7two)
 extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
 {
     if (a->B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
-    const int bw = a->bw;
-    const int bound = dto_kkt_bw_bound(a->W, bw);
+    const int bound = dto_kkt_bw_bound(a->W, a->bw);
+    const bool two = a->variant != 2;
     if (a->W == 16) {
-        if (bound == 6) e = launch_band_t<16, 6>(a, st);
-        else if (bound == 9) e = launch_band_t<16, 9>(a, st);
-        else if (bound == 12) e = launch_band_t<16, 12>(a, st);
+        if (bound == 6) e = two ? launch_band_t<16, 6>(a, st) : launch_band_s<16, 6, 8>(a, st);
+        else if (bound == 9) e = two ? launch_band_t<16, 9>(a, st) : launch_band_s<16, 9, 4>(a, st);
+        else if (bound == 12) e = two ? launch_band_t<16, 12>(a, st) : launch_band_s<16, 12, 4>(a, st);
         else e = launch_band_t<16, 15>(a, st);
     } else if (a->W == 32) {
-        if (bound == 20) e = launch_band_t<32, 20>(a, st);
+        if (bound == 20) e = two ? launch_band_t<32, 20>(a, st) : launch_band_s<32, 20, 8>(a, st);
         else e = launch_band_t<32, 31>(a, st);
     }
     return e == cudaSuccess ? 1 : -(int)e;

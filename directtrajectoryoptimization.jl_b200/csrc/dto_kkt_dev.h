@@ -17,6 +17,7 @@ typedef struct dto_kkt_args {
     int32_t W;           /* band entries kept per row = rows per block = lanes per problem (16 or 32) */
     int32_t bw;          /* half bandwidth of the ordered matrix (<= W - 1)                    */
     int32_t nblk;        /* ceil(dim / W) row blocks                                           */
+    int32_t variant;     /* 0: default (two-row-set factor kernel); 2: single-row-set kernel   */
     int64_t factor_stride; /* doubles of factor storage per problem: nblk*W*LW + nblk*W, LW = dto_kkt_col_width */
     /* callback outputs / inputs of the shard (problem-major) */
     const double* H;     /* [B][nnz_H]  */

@@ -218,6 +218,28 @@ def test_kkt_heterogeneous_shape():
     pn.close()
 
 
+@pytest.mark.parametrize("name,kw,B,config", [("pendulum", dict(), 9, 1), ("cartpole", dict(T=101), 67, 2),
+                                              ("car", dict(T=12, obstacle="general"), 5, 4),
+                                              ("acrobot_hessian_test", dict(), 5, 6)])
+def test_kkt_factor_kernel_variants_agree(name, kw, B, config, monkeypatch):
+    """The two-row-set factor kernel (default) and the single-row-set kernel (DTO_KKT_VARIANT=single, used
+    where the half bandwidth allows it) perform the same operations on the same operands: bit-identical
+    factors and solutions."""
+    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, config)
+    outs = []
+    for variant in ("", "single"):
+        monkeypatch.setenv("DTO_KKT_VARIANT", variant)
+        kkt = PK.KKTSystem(pn)
+        sol = np.empty((B, kkt.dim))
+        kkt.solve(sol, variables=z, scaling=sigma, duals=lam)
+        Lm, Dv = kkt.factor(B - 1)
+        outs.append((sol, Lm, Dv))
+        kkt.close()
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][0], outs[1][0])
+    pn.close()
+
+
 def test_kkt_two_devices():
     """Row (e): problems are independent, a shard per device, no collective -- the KKT consumer follows the
     batch's shards. Needs 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
