@@ -58,6 +58,14 @@ def _ncu_traffic():
     return None
 
 
+def _kkt_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic_kkt_r01.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def _fp64_peak():
     p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
     if os.path.exists(p):
@@ -222,7 +230,8 @@ def bench_kkt(torch, n, stream, zp, lp, sp_, peak):
            "kkt_solves_per_s": B / (out["ms_kkt_kernels"] * 1e-3), "newton_steps_per_s": B / (out["ms_step"] * 1e-3),
            "e2e_ms_host_z_lambda_to_host_solution": e2e_ms, "e2e_d2h_bytes": 8 * B * k.dim,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                        "algorithmic_bytes_per_problem": alg,
+                        "algorithmic_bytes_per_problem": alg, "traffic": _kkt_traffic().get("dram_bytes_per_launch"),
+                        "traffic_source": _kkt_traffic().get("source"),
                         "note": "read J,H,g,c,y once; write+read h; write+read the factor once; write the solution"}}
     k.close()
     return res
