@@ -389,7 +389,11 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                 const int od = (kk - 2) & (NOUT - 1), nd = (kk - 2) >> (NOUT - 1);  // output buffer / use count of tile kk-2 (NOUT is 1 or 2)
                 if (have_drain) {
                     // ---- tile kk-2 is complete in output buffer od: issue its stores (piece list of stage st)
+#if defined(DTO_WS_HINT_NS) && DTO_WS_HINT_NS > 0
+                    mbar_wait_hint(bar0 + 16 + od * 8, nd & 1, DTO_WS_HINT_NS);
+#else
                     mbar_wait(bar0 + 16 + od * 8, nd & 1);
+#endif
                     const int4 pd = sdesc[96 + lane];
                     const int b0 = reinterpret_cast<const int*>(sdesc + 128 + G4)[0];
                     int len = pd.w;

@@ -379,6 +379,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "memory");
     } while (!ok);
 }
+// the same with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the hint
+// expires instead of re-issuing try_wait every ~50 cycles -- for warps whose reaction time does not matter
+// (the ws kernel's helpers), so that their polling does not take issue slots from the compute warps
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity), "r"(ns)
+                     : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
