@@ -164,8 +164,10 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
 
 // One problem per group of W lanes (two problems per warp for W = 16). Row block = W rows.
 // BW = compile-time bound on the half bandwidth (<= W - 1).
-template <int W, int BW>
-__global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel(const dto_kkt_args a)
+// MINB = resident CTAs per SM asked of the compiler: 4 (<= 128 registers, no spills) or 5 (<= 96 registers, a few
+// spilled values; pays off only when the launch has more than 16 warps per SM to offer, i.e. B > ~4700)
+template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
+__global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args a)
 {
     constexpr int G = W;
     using SM = KktSmem<W, BW>;
@@ -483,17 +485,17 @@ extern "C" int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream)
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-template <int W, int BW>
+template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
 static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
 {
     const int64_t per_block = 4 * (32 / W);
     // the opt-in is per device and a batch may span several: set it on every launch (a cheap driver call
     // next to a >= 100 us kernel) instead of caching it per process
     if (KktSmem<W, BW>::BYTES > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
         if (e != cudaSuccess) return e;
     }
-    kkt_band_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
+    kkt_band_kernel<W, BW, MINB><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
     return cudaGetLastError();
 }
 
@@ -518,6 +520,12 @@ extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
     cudaError_t e = cudaErrorInvalidValue;
     const int bound = dto_kkt_bw_bound(a->W, a->bw);
     const bool two = a->variant != 2;
+    // experiment (DTO_KKT_VARIANT=occ5): 5 CTAs per SM, 96 registers, a few spills -- measured slower on every
+    // shape (cartpole 0.485 vs 0.346 ms, car 3.09 vs 2.35 ms; profiles/kkt_r01_history.jsonl tags v8 / v8occ5)
+    if (a->variant == 3 && a->W == 16 && (bound == 9 || bound == 15)) {
+        e = bound == 9 ? launch_band_t<16, 9, 5>(a, st) : launch_band_t<16, 15, 5>(a, st);
+        return e == cudaSuccess ? 1 : -(int)e;
+    }
     if (a->W == 16) {
         if (bound == 6) e = two ? launch_band_t<16, 6>(a, st) : launch_band_s<16, 6, 8>(a, st);
         else if (bound == 9) e = two ? launch_band_t<16, 9>(a, st) : launch_band_s<16, 9, 4>(a, st);
