@@ -122,3 +122,26 @@ def test_kkt_create_needs_a_device():
     with pytest.raises(Exception) as e:
         PK.KKTSystem(pn)
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_kkt_abi_error_codes_without_gpu():
+    import ctypes as C
+    from dto_b200 import _lib
+    L = _lib.lib()
+    assert L.dto_status_string(-7) == b"unsupported shape"
+    assert L.dto_kkt_analyze(None, None, None) == -1            # DTO_ERR_BAD_ARG
+    assert b"null shape" in L.dto_last_error()
+    h = C.c_void_p()
+    assert L.dto_kkt_create(None, 1e-5, 1e-5, C.byref(h)) == -1 and not h.value
+    assert L.dto_kkt_solve(None, None) == -1
+    assert L.dto_kkt_solve_host(None, None, None, None, None, 0) == -1
+    assert L.dto_kkt_dim(None) == -1 and L.dto_kkt_bandwidth(None) == -1
+    L.dto_kkt_destroy(None)                                     # no-op
+
+
+def test_kkt_ordering_of_a_cyclic_coupling():
+    """A general constraint tying the first knot to the last one (a cycle in the KKT graph) still orders into a
+    narrow band: reverse Cuthill-McKee interleaves the two arms of the cycle."""
+    pn = D.solver_from(M.BUILDERS["heterogeneous"](D), batch=1).nlp
+    perm, bw = PK.analyze(pn)
+    assert 15 < bw <= 31      # the 32-lane kernel's range (tests/test_kkt_gpu.py::test_kkt_heterogeneous_shape)
