@@ -110,8 +110,12 @@ def _scipy_task(broker: CallbackBroker, b: int, z0, structures, bounds, options,
     import scipy.sparse as sp
     from scipy.optimize import Bounds, NonlinearConstraint, minimize
 
-    (jr, jc), (hr, hc), nz, nc = structures
+    (jr, jc), (hr, hc), nz, nc, use_hessian = structures
     (zl, zu), (cl, cu) = bounds
+    if not use_hessian:
+        # features_available without :Hess (src/moi.jl:122): the reference lets Ipopt fall back to its
+        # limited-memory quasi-Newton approximation; the stand-in solver does the same with BFGS updates
+        from scipy.optimize import BFGS
 
     def fun(z):
         return broker.request(b, "f", z)
@@ -134,7 +138,7 @@ def _scipy_task(broker: CallbackBroker, b: int, z0, structures, bounds, options,
         def hess_con(z, v):  # sum_i v_i Hessian(c_i): the Lagrangian callback with sigma = 0
             return sp.csr_matrix((broker.request(b, "H", z, 0.0, v), (hr, hc)), shape=(nz, nz))
 
-        cons = [NonlinearConstraint(con, cl, cu, jac=jac, hess=hess_con)]
+        cons = [NonlinearConstraint(con, cl, cu, jac=jac, hess=hess_con if use_hessian else BFGS())]
     kw = {}
     if np.isfinite(zl).any() or np.isfinite(zu).any():
         kw["bounds"] = Bounds(zl, zu)
@@ -144,7 +148,7 @@ def _scipy_task(broker: CallbackBroker, b: int, z0, structures, bounds, options,
             record.append(np.array(xk, copy=True))
             return False
     try:
-        return minimize(fun, z0, jac=grad, hess=hess_obj, constraints=cons, method="trust-constr", options=options,
+        return minimize(fun, z0, jac=grad, hess=hess_obj if use_hessian else BFGS(), constraints=cons, method="trust-constr", options=options,
                         callback=cb, **kw)
     finally:
         broker.finish(b)
@@ -156,8 +160,12 @@ def solve_batch(nlp, z0: np.ndarray, options: Optional[dict] = None, record_iter
     Returns (Z[B, N_z] final iterates, list of per-problem solver results, broker, iterates or None)."""
     B = nlp.batch
     jr, jc = nlp.jacobian_structure_arrays()
-    hr, hc = nlp.hessian_lagrangian_structure_arrays()
-    structures = ((jr - 1, jc - 1), (hr - 1, hc - 1), nlp.num_variables, nlp.num_constraint)
+    use_hessian = bool(getattr(nlp, "hessian_lagrangian", True))
+    if use_hessian:
+        hr, hc = nlp.hessian_lagrangian_structure_arrays()
+    else:
+        hr = hc = np.ones(0, dtype=np.int64)
+    structures = ((jr - 1, jc - 1), (hr - 1, hc - 1), nlp.num_variables, nlp.num_constraint, use_hessian)
     bounds = (nlp.variable_bounds, nlp.constraint_bounds)
     opts = {"gtol": 1e-8, "xtol": 1e-10, "maxiter": 1000, "verbose": 0}
     opts.update(options or {})

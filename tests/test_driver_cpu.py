@@ -68,3 +68,19 @@ def test_error_in_batched_call_reaches_every_task():
     with pytest.raises(Exception) as e:
         driver.solve_batch(nlp, _pendulum_guesses(mo, nlp, 2), options={"maxiter": 5})
     assert "failed" in str(e.value)
+
+
+def test_solve_without_hessian_uses_quasi_newton():
+    """evaluate_hessian=False: features_available has no :Hess (src/moi.jl:122) and the Hessian callback must never
+    be requested; the stand-in solver runs on BFGS updates, like Ipopt's limited-memory mode."""
+    mo = M.BUILDERS["pendulum"](O, evaluate_hessian=False)
+    osolver = O.solver_from(mo)
+    assert ":Hess" not in [str(f) for f in osolver.nlp.features_available()] and "Hess" not in str(osolver.nlp.features_available())
+    nlp = OracleBatch(osolver, 2)
+    assert nlp.hessian_lagrangian is False
+    Z, res, broker, _ = driver.solve_batch(nlp, _pendulum_guesses(mo, nlp, 2), options={"maxiter": 500})
+    assert broker.requests["H"] == 0
+    c = np.zeros(nlp.num_constraint)
+    for b in range(2):
+        osolver.nlp.eval_constraint(c, Z[b])
+        assert np.max(np.abs(c)) < 1e-5

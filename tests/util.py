@@ -103,6 +103,7 @@ class OracleBatch:
         self.num_hessian = len(self.o.hessian_lagrangian_sparsity)
         self.variable_bounds = self.o.variable_bounds
         self.constraint_bounds = self.o.constraint_bounds
+        self.hessian_lagrangian = bool(getattr(self.o, "hessian_lagrangian", True))
 
     def jacobian_structure_arrays(self):
         s = self.o.jacobian_structure()
