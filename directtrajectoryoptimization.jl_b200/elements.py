@@ -81,7 +81,7 @@ class Dynamics:
         self.spec = ElementSpec(role="dyn", n_out=num_next_state, nx=num_state, nu=num_action, nw=num_parameter,
                                 args={"y": list(y), "x": list(x), "u": list(u), "w": list(w), "lam": list(lam)},
                                 evaluate=evaluate, jac_rows=jr, jac_cols=jc, has_hess=bool(evaluate_hessian),
-                                hess_rows=hr, hess_cols=hc, vars=xuy, lam=list(lam), _jac=jv)
+                                hess_rows=hr, hess_cols=hc, vars=xuy, lam=list(lam), _jac=jv, user_jac=jv is not None)
 
 
 class Constraint:

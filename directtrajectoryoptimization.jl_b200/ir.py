@@ -197,6 +197,85 @@ class Graph:
             acc = self.add(acc, x)
         return acc
 
+    def clone(self) -> "Graph":
+        """Independent copy (node ids preserved): the cut search differentiates many trial copies."""
+        h = Graph.__new__(Graph)
+        h.op, h.args, h.val = list(self.op), list(self.args), list(self.val)
+        h._memo = dict(self._memo)
+        h.ZERO, h.ONE = self.ZERO, self.ONE
+        return h
+
+    def subst(self, n: int, mapping: Dict[int, int], memo: Optional[dict] = None) -> int:
+        """Rebuild node n with the nodes in `mapping` replaced (through the smart constructors)."""
+        memo = {} if memo is None else memo
+        order = [(n, False)]
+        while order:
+            m, done = order.pop()
+            if m in memo:
+                continue
+            if m in mapping:
+                memo[m] = mapping[m]
+                continue
+            op, a = self.op[m], self.args[m]
+            if op in ("const", "in"):
+                memo[m] = m
+                continue
+            if not done:
+                order.append((m, True))
+                order.extend((x, False) for x in a if x not in memo)
+                continue
+            b = [memo[x] for x in a]
+            if all(x == y for x, y in zip(a, b)):
+                r = m
+            elif op == "add":
+                r = self.add(b[0], b[1])
+            elif op == "mul":
+                r = self.mul(b[0], b[1])
+            elif op == "neg":
+                r = self.neg(b[0])
+            elif op == "rcp":
+                r = self.rcp(b[0])
+            elif op == "powi":
+                r = self.powi(b[0], self.val[m])
+            elif op == "powc":
+                r = self.powc(b[0], self.val[m])
+            else:
+                r = self.func(op, b[0])
+            memo[m] = r
+        return memo[n]
+
+    def evaluate(self, nodes: Sequence[int], inputs: Dict[Tuple[str, int], float]) -> List[float]:
+        """Numeric value of `nodes` (host-side check of the derivative synthesis; tests only)."""
+        need, stack = set(), list(nodes)
+        while stack:
+            m = stack.pop()
+            if m in need:
+                continue
+            need.add(m)
+            stack.extend(self.args[m])
+        v: Dict[int, float] = {}
+        for m in sorted(need):
+            op, a = self.op[m], self.args[m]
+            if op == "const":
+                v[m] = self.val[m]
+            elif op == "in":
+                v[m] = float(inputs[self.val[m]])
+            elif op == "add":
+                v[m] = v[a[0]] + v[a[1]]
+            elif op == "mul":
+                v[m] = v[a[0]] * v[a[1]]
+            elif op == "neg":
+                v[m] = -v[a[0]]
+            elif op == "rcp":
+                v[m] = 1.0 / v[a[0]]
+            elif op == "powi":
+                v[m] = v[a[0]] ** self.val[m]
+            elif op == "powc":
+                v[m] = v[a[0]] ** self.val[m]
+            else:
+                v[m] = getattr(math, op)(v[a[0]])
+        return [v[m] for m in nodes]
+
     # ---- sympy -> DAG
     def from_sympy(self, e: sp.Expr, sym: Dict[sp.Symbol, int], memo: Optional[dict] = None) -> int:
         memo = {} if memo is None else memo
@@ -280,7 +359,8 @@ class Graph:
 
 
 class Derivatives:
-    """Sparse second-order forward propagation over a Graph w.r.t. `wrt` (input node ids)."""
+    """Sparse second-order forward propagation over a Graph w.r.t. `wrt`: input nodes, or any
+    intermediate nodes declared as leaves (the traversal stops there; used by `hierarchical`)."""
 
     def __init__(self, g: Graph, wrt: Sequence[int], second: bool = True):
         self.g = g
@@ -310,6 +390,10 @@ class Derivatives:
         while stack:
             n, done = stack.pop()
             if n in self._grad:
+                continue
+            if n in self.index:  # a leaf of this differentiation (input or cut node)
+                self._grad[n] = {self.index[n]: g.ONE}
+                self._hess[n] = {}
                 continue
             if not done:
                 stack.append((n, True))
@@ -393,6 +477,187 @@ class Derivatives:
                                 self._acc(H, (i, j), g.mul(d2vi, vj))
         self._grad[n] = G
         self._hess[n] = H
+
+
+# ----------------------------------------------------------------------------- hierarchical derivatives
+def _reach(g: Graph, roots: Iterable[int], stop: set) -> set:
+    seen, st = set(), list(roots)
+    while st:
+        n = st.pop()
+        if n in seen:
+            continue
+        seen.add(n)
+        if n in stop:
+            continue
+        st.extend(g.args[n])
+    return seen
+
+
+def hierarchical(g: Graph, outs: Sequence[int], L: Optional[int], wrt: Sequence[int], cuts: Sequence[int] = (),
+                 second: bool = True) -> Tuple[List[Dict[int, int]], Dict[Tuple[int, int], int]]:
+    """First derivatives of `outs` and the Hessian of the scalar `L` w.r.t. the inputs `wrt`, with the
+    intermediate nodes `cuts` used as LOCAL differentiation variables.
+
+    Plain forward propagation carries, at every node, a gradient / Hessian in the GLOBAL variables; after
+    an RK stage or a midpoint these are dense (cartpole: 3 + 6 entries per node) although the node
+    depends on one or two stage quantities. Here the DAG is split at the cut nodes: a cut node c_k is a
+    function phi_k of the inputs and of earlier cuts, and so is L. Per level of cuts:
+      * local first/second derivatives of phi_k w.r.t. its own leaves (sparse in those),
+      * global tangents by the chain rule,   T(c_k) = sum_leaf dphi_k/dleaf * T(leaf),
+      * adjoints by one reverse sweep over the cut nodes,   cbar_k = dL/dc_k,
+      * Hessian = sum over levels of  T' M T,  M = local Hessian of  sum_k cbar_k * phi_k  (the adjoints
+        enter as placeholders while differentiating and are substituted afterwards), which is the
+        second-order chain rule contracted with the adjoint BEFORE the congruence.
+    With no cuts this is exactly the plain forward propagation. Returns ([{var index: node}] per output,
+    {(i, j), i <= j: node})."""
+    cuts = sorted(set(cuts))
+    cutset = set(cuts)
+    wset = set(wrt)
+    level: Dict[int, int] = {}
+    for c in cuts:
+        anc = _reach(g, g.args[c], cutset)
+        level[c] = 1 + max([level[a] for a in anc if a in cutset], default=0)
+    nlev = max(level.values(), default=0)
+    groups: List[Optional[List[int]]] = [[c for c in cuts if level[c] == lv] for lv in range(1, nlev + 1)]
+    gidx = {n: i for i, n in enumerate(wrt)}
+    T: Dict[int, Dict[int, int]] = {n: {gidx[n]: g.ONE} for n in wrt}
+
+    def chain(gloc: Dict[int, int], leaves: List[int]) -> Dict[int, int]:
+        out: Dict[int, int] = {}
+        for li, d in sorted(gloc.items()):
+            for i, t in T[leaves[li]].items():
+                v = g.mul(d, t)
+                out[i] = v if i not in out else g.add(out[i], v)
+        return {i: v for i, v in out.items() if v != g.ZERO}
+
+    info = []
+    nph = 0
+    jac: List[Dict[int, int]] = []
+    for grp in groups + [None]:
+        roots = list(grp) if grp is not None else list(outs) + ([L] if L is not None else [])
+        rr: set = set()
+        for c in roots:
+            rr |= _reach(g, g.args[c] if grp is not None else [c], cutset)
+        leaves = sorted(n for n in rr if n in cutset or n in wset)
+        LD = Derivatives(g, leaves, second=second)
+        if grp is not None:
+            gloc = {c: dict(LD.grad(c)) for c in grp}
+            for c in grp:
+                T[c] = chain(gloc[c], leaves)
+            hloc, ph = {}, []
+            if second:
+                ph = [g.inp("__adj", nph + k) for k in range(len(grp))]
+                nph += len(grp)
+                hloc = LD.hess(g.sum(g.mul(p, c) for p, c in zip(ph, grp)))
+            info.append((grp, leaves, gloc, hloc, ph))
+        else:
+            jac = [chain(dict(LD.grad(o)), leaves) for o in outs]
+            if second and L is not None:
+                info.append((None, leaves, {L: dict(LD.grad(L))}, LD.hess(L), None))
+    if not second or L is None:
+        return jac, {}
+    # adjoints of the cut nodes: reverse sweep over the levels
+    cbar: Dict[int, int] = {}
+    for grp, leaves, gloc, hloc, ph in reversed(info):
+        for c in ([L] if grp is None else grp):
+            wgt = g.ONE if grp is None else cbar.get(c, g.ZERO)
+            if wgt == g.ZERO:
+                continue
+            for li, d in sorted(gloc[c].items()):
+                leaf = leaves[li]
+                if leaf in cutset:
+                    v = g.mul(wgt, d)
+                    cbar[leaf] = v if leaf not in cbar else g.add(cbar[leaf], v)
+    # Hessian: congruence of every level's adjoint-weighted local Hessian with the global tangents
+    H: Dict[Tuple[int, int], int] = {}
+    for grp, leaves, gloc, hloc, ph in info:
+        if grp is not None:
+            mp = {p: cbar.get(c, g.ZERO) for p, c in zip(ph, grp)}
+            memo: dict = {}
+            hloc = {k: g.subst(v, mp, memo) for k, v in hloc.items()}
+        N: Dict[int, Dict[int, int]] = {}
+        for (a, b), m in sorted(hloc.items()):
+            if m == g.ZERO:
+                continue
+            for p, q in (((a, b),) if a == b else ((a, b), (b, a))):
+                row = N.setdefault(p, {})
+                for j, t in T[leaves[q]].items():
+                    v = g.mul(m, t)
+                    row[j] = v if j not in row else g.add(row[j], v)
+        for a, row in sorted(N.items()):
+            for i, ti in T[leaves[a]].items():
+                for j, nj in sorted(row.items()):
+                    if i <= j:
+                        v = g.mul(ti, nj)
+                        H[(i, j)] = v if (i, j) not in H else g.add(H[(i, j)], v)
+    return jac, {k: v for k, v in H.items() if v != g.ZERO}
+
+
+def _total_ops(g: Graph, nodes: Sequence[int]) -> int:
+    return sum(count_ops(g, nodes).values())
+
+
+def choose_cuts(g: Graph, outs: Sequence[int], L: int, wrt: Sequence[int], select, max_evals: int = 4000,
+                min_ops: int = 60) -> Tuple[List[int], Dict[str, int]]:
+    """Cut nodes for `hierarchical` by local search on the exact operation count of the fused program.
+    `select(jac, H, graph)` returns the output nodes whose cost counts. Candidates: intermediate nodes
+    that depend on >= 2 differentiation variables. Greedy single additions / removals, then pairs, within
+    an evaluation budget (deterministic: the result depends on the model only)."""
+    def cost(cc) -> int:
+        h = g.clone()
+        jac, H = hierarchical(h, outs, L, wrt, sorted(cc))
+        return _total_ops(h, select(jac, H, h))
+
+    base = cost(())
+    stats = {"plain": base, "evals": 1}
+    if base < min_ops:
+        stats["ops"] = base
+        return [], stats
+    wset = set(wrt)
+    sup: Dict[int, frozenset] = {}
+    for n in sorted(_reach(g, list(outs) + [L], set())):
+        if g.op[n] == "in":
+            sup[n] = frozenset([n]) if n in wset else frozenset()
+        elif g.op[n] == "const":
+            sup[n] = frozenset()
+        else:
+            s_: frozenset = frozenset()
+            for a in g.args[n]:
+                s_ |= sup[a]
+            sup[n] = s_
+    cands = [n for n in sorted(sup) if g.op[n] not in ("in", "const", "neg") and len(sup[n]) >= 2 and n != L and n not in outs]
+    cur: set = set()
+    best = base
+    evals = 1
+    pos = {c: i for i, c in enumerate(cands)}
+    # pairs, nearest first: related quantities (the components of one stage vector) are created together
+    pairs = sorted(((c, d) for x, c in enumerate(cands) for d in cands[x + 1:]), key=lambda cd: (pos[cd[1]] - pos[cd[0]], cd))
+    while evals < max_evals:
+        improved = False
+        for c in cands:  # single additions / removals, first improvement
+            trial = (cur - {c}) if c in cur else (cur | {c})
+            v = cost(trial)
+            evals += 1
+            if v < best:
+                best, cur, improved = v, trial, True
+            if evals >= max_evals:
+                break
+        if improved:
+            continue
+        for c, d in pairs:  # no single move helps: first improving pair addition, then singles again
+            if c in cur or d in cur:
+                continue
+            v = cost(cur | {c, d})
+            evals += 1
+            if v < best:
+                best, cur, improved = v, cur | {c, d}, True
+                break
+            if evals >= max_evals:
+                break
+        if not improved:
+            break
+    stats.update(ops=best, evals=evals, cuts=len(cur))
+    return sorted(cur), stats
 
 
 # ----------------------------------------------------------------------------- emission

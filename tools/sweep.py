@@ -40,7 +40,7 @@ with torch.cuda.stream(st):
     e1.record(st); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 200
 byt = n0.algorithmic_bytes_per_problem() * n0.batch
-print(json.dumps({"tune": os.environ.get("DTO_TUNE", ""), "kernel": KID, "model": %r, "ms": ms, "GBs": byt / ms / 1e6,
+print(json.dumps({"tune": os.environ.get("DTO_TUNE", ""), "deriv": os.environ.get("DTO_DERIV", ""), "kernel": KID, "model": %r, "ms": ms, "GBs": byt / ms / 1e6,
                   "evals_per_s": n0.batch * n0.T / ms * 1e3, "smem": n0.kernel_smem_bytes(KID)}))
 """
 
@@ -68,7 +68,14 @@ def main():
         if a.startswith("--tunes="):
             tunes = a.split("=", 1)[1].split(";")
     for t in tunes:
-        env = dict(os.environ, DTO_TUNE=t)
+        # "DERIV=dag|bf=1,emit=2": derivative mode (DTO_DERIV) in front of the DTO_TUNE string
+        env = dict(os.environ)
+        if "|" in t:
+            pre, t = t.split("|", 1)
+            for kv in pre.split(","):
+                k, v = kv.split("=")
+                env["DTO_" + k] = v
+        env["DTO_TUNE"] = t
         code = CHILD % (ROOT, ROOT, build_only, kid, model, kw, B, model, model + repr(kw))
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
         out = (r.stdout.strip().splitlines() or [""])[-1]
