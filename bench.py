@@ -48,14 +48,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the one
-    committed `ncu --set full` capture of this workload (profiles/traffic_r01.json)."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+def _ncu_headline():
+    """Counters of the one committed `ncu --set full` capture of the shipped headline kernel
+    (profiles/ncu_headline.json, written by tools/ncu_to_json.py): DRAM bytes per launch, executed FP64
+    instructions per knot (SASS) and the FP64-pipe utilisation counter."""
+    p = os.path.join(ROOT, "profiles", "ncu_headline.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
-    return None
+    return {}
 
 
 def _kkt_traffic():
@@ -131,6 +132,31 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def bind_near_gpu(device: int):
+    """Pin this process to the host cores NVML reports as local to `device` BEFORE any pinned host buffer is
+    allocated (first touch puts the pages on that NUMA node): with one process per GPU the 8 ranks' D2H/H2D
+    streams then land on the memory controllers next to their own PCIe root instead of all on node 0.
+    Returns a short description for the JSON line; silently does nothing where NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            with open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:  # noqa: BLE001
+            pass
+        return {"cpus": len(after), "of": before, "numa_node": node}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:80]}
+
+
 def build_c_baseline(T: int, verbose=False):
     from examples import models as M
     from oracle import api as O, cgen
@@ -167,7 +193,7 @@ def run_reference(args):
     from util import make_inputs
     co, mo = build_c_baseline(args.T)
     threads = host_threads()
-    Bs = args.ref_sample
+    Bs = args.ref_sample if args.ref_sample > 0 else args.batch
     z, lam, sigma, w = make_inputs("cartpole", mo, co.NZ, co.NC, co.NW, Bs, config=2, shard=0)
     what = 8 | 16
     for _ in range(args.warmup):
@@ -185,7 +211,7 @@ def run_reference(args):
                    "note": "the Julia reference cannot run here (no Julia/Ipopt); this arm times the oracle's C twin of the "
                            "reference callbacks (no-CSE element code, reference loop structure) on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{Bs} problems x T={args.T} per step (of B={args.batch}), gcc -O2 -fopenmp, no-CSE element code"},
+                         "sample": f"{Bs} problems x T={args.T} per step (B={args.batch}), gcc -O2 -fopenmp, no-CSE element code"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -247,6 +273,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    binding = None if args.no_bind else bind_near_gpu(local)
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator is created: keep stdout
         # for the one JSON line by pointing fd 1 at stderr until the communicator exists
@@ -267,7 +294,15 @@ def run_ours(args):
     from examples import models as M
     from util import make_inputs
 
-    B, T = args.batch, args.T
+    T = args.T
+    strong = args.scaling == "strong"
+    if strong:  # the global batch is fixed: contiguous shards of ceil(B/N) problems (sharding.partition)
+        from dto_b200 import sharding
+        B = sharding.partition(args.batch, world)[rank][1]
+        B_total = args.batch
+    else:
+        B = args.batch
+        B_total = args.batch * world
     model = M.build_cartpole(D, T=T, evaluate_hessian=True, parameterized=True)
     solver = D.solver_from(model, batch=B, devices=[local])
     nlp0 = solver.nlp
@@ -319,7 +354,7 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
     ms_per_step = ms / args.steps
-    value = world * B * T / (ms_per_step * 1e-3)
+    value = B_total * T / (ms_per_step * 1e-3)
 
     # ---- end to end through the public host API, pinned host buffers
     n = nlps[0]
@@ -341,44 +376,70 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
     dt = float(tdt.item())
-    e2e_value = world * B * T * e2e_steps / dt
+    e2e_value = B_total * T * e2e_steps / dt
     h2d = 8 * B * (n.num_variables + n.num_constraint + 1)
     d2h = 8 * B * (n.num_jacobian + n.num_hessian)
+
+    # ---- secondary: device-resident KKT consumer (30 MB instead of 99 MB back over PCIe), at every N
+    kkt = None
+    if not args.no_kkt:
+        peak, _ = _peaks()
+        kkt = bench_kkt(torch, n, stream, zp, lp, sp_, peak)
+        tk = torch.tensor([kkt["ms_kkt_kernels"], kkt["ms_step_callbacks_plus_kkt"], kkt["e2e_ms_host_z_lambda_to_host_solution"]],
+                          dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        kkt["ms_kkt_kernels"], kkt["ms_step_callbacks_plus_kkt"], kkt["e2e_ms_host_z_lambda_to_host_solution"] = [float(x) for x in tk.tolist()]
+        kkt["kkt_solves_per_s"] = B_total / (kkt["ms_kkt_kernels"] * 1e-3)
+        kkt["newton_steps_per_s"] = B_total / (kkt["ms_step_callbacks_plus_kkt"] * 1e-3)
+        kkt["e2e_newton_steps_per_s"] = B_total / (kkt["e2e_ms_host_z_lambda_to_host_solution"] * 1e-3)
+        kkt["e2e_knot_evals_per_s"] = B_total * T / (kkt["e2e_ms_host_z_lambda_to_host_solution"] * 1e-3)
+        kkt["n_gpus"] = world
+        kkt["timing"] = "max over ranks"
 
     line = None
     if rank == 0:
         peak, peak_src = _peaks()
         bytes_per_launch = n.algorithmic_bytes_per_problem() * B
         achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
-        ops = None
-        try:
-            ops = int(open(n.model.path.replace(".so", ".log")).read().split("'ops_fused_per_knot': ")[1].split("}")[0].split(",")[0])
-        except Exception:  # noqa: BLE001
-            pass
+        ncu = _ncu_headline()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"cartpole swing-up T={T}, B={B} per GPU, fused Jacobian+Hessian callbacks",
+            "config": {"workload": (f"cartpole swing-up T={T}, B={args.batch} per GPU, fused Jacobian+Hessian callbacks" if not strong else
+                                    f"cartpole swing-up T={T}, B={args.batch} in total over {world} GPUs, fused Jacobian+Hessian callbacks"),
                        "l2": f"{R} rotating input/output sets ({R * bytes_per_launch / 1e6:.0f} MB) > 126 MB L2",
-                       "parallelism": f"{world} independent shards, no collective"},
+                       "parallelism": f"{world} independent shards, no collective",
+                       "host_binding": binding},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+                    "pcie_gbs_per_gpu": (h2d + d2h) / (dt / e2e_steps) / 1e9},
             "gpu_launches": int(n1 - n0),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (_ncu_traffic() or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                         "traffic_source": (_ncu_traffic() or {}).get("source"),
+                         "traffic": (ncu.get("traffic") or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                         "traffic_source": (ncu.get("traffic") or {}).get("source"),
                          "algorithmic_bytes_per_launch": bytes_per_launch},
         }
-        if ops:
+        f64 = ncu.get("fp64")
+        if f64:
+            # FP64 pipe: executed DFMA/DMUL/DADD per knot from the committed ncu capture of the shipped kernel x the
+            # knots of this run / the live kernel time, against the measured DFMA issue peak; next to it the
+            # pipe-utilisation counter ncu itself reported for that capture
             fp = _fp64_peak()
-            line["fp64"] = {"codegen_ops_per_knot": ops, "achieved_gops": ops * B * T / (ms_per_step * 1e-3) / 1e9,
-                            "peak_gdfma": fp / 1e9, "note": "cartpole RK3 is FP64-pipe bound (SURVEY 8d); ops = sympy count_ops"}
-        if world == 1 and not args.no_kkt:
-            line["kkt"] = bench_kkt(torch, n, stream, zp, lp, sp_, peak)
+            rate = f64["sass_fp64_thread_instructions_per_knot"] * B * T / (ms_per_step * 1e-3)
+            line["fp64"] = {"sass_fp64_per_knot": f64["sass_fp64_thread_instructions_per_knot"], "mix_per_knot": f64["mix_per_knot"],
+                            "achieved_ginst": rate / 1e9, "peak_ginst": fp / 1e9, "frac_of_fp64_issue_peak": rate / fp,
+                            "ncu_pipe_fp64_pct": f64["ncu_pipe_fp64_pct"], "source": f64["source"]}
+        if kkt is not None:
+            line["kkt"] = kkt
         if world == 1 and not args.no_cpu:
             co, mo = build_c_baseline(T)
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU baseline uses every host core again
+            except OSError:
+                pass
             threads = host_threads()
             v, Bs, reps, dtc = time_cpu(co, z, lam, sigma, w, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -400,7 +461,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--T", type=int, default=101)
-    ap.add_argument("--ref-sample", type=int, default=256, dest="ref_sample")
+    ap.add_argument("--ref-sample", type=int, default=0, dest="ref_sample", help="problems per step of the reference arm (0 = the whole batch)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch problems per GPU; strong: --batch problems in total, split over the GPUs")
+    ap.add_argument("--no-bind", action="store_true", dest="no_bind", help="do not bind the process to the GPU-local host cores")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-kkt", action="store_true", dest="no_kkt")
     args = ap.parse_args()

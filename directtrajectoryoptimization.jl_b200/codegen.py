@@ -48,7 +48,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 0, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 0, "ws_split_gen": 0, "ws_hint": 0}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 2, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 1, "ws_split_gen": 0, "ws_hint": 0}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -825,14 +825,15 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}: the CUDA model library cannot be built (no CPU fallback exists)")
     tune = _tuning()
-    # light (HBM-bound) models: the ws kernel's compute warps need few registers and finish a tile quickly, so
-    # the per-tile work of a helper warp would bound the kernel: one helper per compute warp instead of one per
-    # two (unless DTO_TUNE says otherwise)
-    light = stats.get("ops_fused_per_knot", 0) < 100
+    # One helper warp per compute warp (16 warps per CTA, 128 registers per thread at launch; setmaxnreg then
+    # gives helpers 40 and compute warps 216). Light models always needed it (a helper's ~300 latency-bound
+    # integer instructions per tile would bound the kernel); since the hierarchical derivatives cut the
+    # FP64 work per knot the heavy models do too: with one helper per TWO compute warps the cartpole compute
+    # warps waited 22 % of their time for inputs (profiles/ncu_ws_r02_a.txt), 37.0 -> 33.5 us with 8 helpers.
     if tune["ws_helpers"] == 0:  # 0 = automatic
-        tune["ws_helpers"] = 8 if light else 4
+        tune["ws_helpers"] = 8
     if tune["ws_creg"] == 0:
-        tune["ws_creg"] = 168 if tune["ws_helpers"] == 8 else 232
+        tune["ws_creg"] = 216 if tune["ws_helpers"] == 8 else 232
     cmd = [NVCC, *NVCC_ARCH, f"-DDTO_WARPS={tune['warps']}", f"-DDTO_MIN_CTAS={tune['min_ctas']}",
            f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", f"-DDTO_L2_PREFETCH={tune['l2_prefetch']}",
            f"-DDTO_PERSIST={tune['persist']}", f"-DDTO_PWARPS={tune['pwarps']}", f"-DDTO_PCTAS={tune['pctas']}",

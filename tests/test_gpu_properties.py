@@ -174,10 +174,12 @@ def test_nan_inf_pass_through():
     pn.close()
 
 
-def test_symbolic_derivative_mode_matches(monkeypatch):
+@pytest.mark.parametrize("mode", ["sympy", "dag"])
+def test_symbolic_derivative_mode_matches(mode, monkeypatch):
     """DTO_DERIV=sympy lowers the expanded symbolic derivative expressions (the literal form the
-    reference's closures hold); it must agree with the oracle like the default DAG mode does."""
-    monkeypatch.setenv("DTO_DERIV", "sympy")
+    reference's closures hold), DTO_DERIV=dag the plain forward propagation without cut nodes; both must
+    agree with the oracle like the default hierarchical mode does."""
+    monkeypatch.setenv("DTO_DERIV", mode)
     for name, kw, B, config in [("pendulum", dict(), 4, 1), ("cartpole", dict(T=11), 3, 2)]:
         fx = np.load(os.path.join(HERE, tag(name, kw) + ".npz"))
         pn = D.solver_from(M.BUILDERS[name](D, **kw), batch=B).nlp
@@ -205,7 +207,8 @@ def test_table_gather_fallback_matches(monkeypatch):
     assert pn.compiled_gather()
 
 
-KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0,ws_all=1", "ws_min_ops=0,ws_plan=0", "ws_min_ops=0,bf=1"]
+KERNEL_VARIANTS = ["ws=0,persist=0", "ws=0,ws_min_ops=0", "ws_min_ops=0,ws_all=1", "ws_min_ops=0,ws_plan=0", "ws_min_ops=0,bf=0,emit=0",
+                   "ws_min_ops=0,ws_helpers=4"]
 VARIANT_MODELS = [("pendulum", dict(), 1), ("cartpole", dict(T=11), 2), ("acrobot", dict(T=9), 3),
                   ("car", dict(T=12, obstacle="general"), 4)]
 
@@ -239,9 +242,10 @@ def test_kernel_variants_match_golden_and_each_other(tune, monkeypatch):
         monkeypatch.delenv("DTO_TUNE", raising=False)
         for k in ("f", "g", "c", "J", "H"):
             assert_close(f"{tune} {name} {k}", res[tune][k][:B0], fx[k])
-        # same element code in every kernel: a few ulps; bf=1 swaps the sin/cos/reciprocal implementation
-        # (each < 1 ulp, but not the library's bits), so it is held to the oracle tolerance instead
-        rt, at = (1e-12, 1e-14) if "bf=1" in tune else (1e-14, 1e-16)
+        # same element code in every kernel: a few ulps; bf=0 swaps the branch-free sin/cos/reciprocal of the
+        # default build for the library's (each < 1 ulp, but not the same bits), so it is held to the oracle
+        # tolerance instead
+        rt, at = (1e-12, 1e-14) if "bf=0" in tune else (1e-14, 1e-16)
         for k in ("g", "c", "J", "H", "J2", "H2"):
             assert_close(f"{tune} vs default {name} {k}", res[tune][k], res[""][k], rtol=rt, atol=at)
         assert_close(f"{tune} fused J {name}", res[tune]["J2"], res[tune]["J"], rtol=1e-14, atol=1e-16)
@@ -249,8 +253,8 @@ def test_kernel_variants_match_golden_and_each_other(tune, monkeypatch):
 
 
 def test_branch_free_math_falls_back_outside_its_domain(monkeypatch):
-    """DTO_TUNE=bf=1 replaces sin/cos/reciprocal inside the generated element programs by branch-free
-    versions (one basic block); arguments outside their domain (|angle| >= 2^31, NaN, Inf, reciprocals of
+    """The default build (DTO_TUNE bf=1) replaces sin/cos/reciprocal inside the generated element programs by
+    branch-free versions (one basic block); arguments outside their domain (|angle| >= 2^31, NaN, Inf, reciprocals of
     denormal / huge values) must re-evaluate with the library functions and give the default path's
     values, problem by problem."""
     name, kw = "cartpole", dict(T=11)
@@ -262,7 +266,7 @@ def test_branch_free_math_falls_back_outside_its_domain(monkeypatch):
     z[4, 11] = np.inf
     z[5, 1] = 2.0 ** 31    # boundary of the fast path
     res = {}
-    for t in ("", "ws_min_ops=0,bf=1"):
+    for t in ("ws_min_ops=0,bf=0,emit=0", ""):
         if t:
             monkeypatch.setenv("DTO_TUNE", t)
         else:
@@ -272,8 +276,9 @@ def test_branch_free_math_falls_back_outside_its_domain(monkeypatch):
         pn.close()
     monkeypatch.delenv("DTO_TUNE", raising=False)
     for k in ("c", "J", "H"):
-        a, b = res["ws_min_ops=0,bf=1"][k], res[""][k]
+        a, b = res[""][k], res["ws_min_ops=0,bf=0,emit=0"][k]
         assert np.array_equal(np.isnan(a), np.isnan(b)), f"{k}: NaN pattern differs"
         fin = np.isfinite(b)
         assert_close(f"bf=1 {k}", a[fin], b[fin], rtol=1e-12, atol=1e-14)
     assert np.isfinite(res[""]["J"][1]).all() and np.isfinite(res[""]["H"][2]).all()
+    assert "dto_sincos_bf" in open(D.solver_from(M.BUILDERS[name](D, **kw), batch=1).model.path.replace(".so", ".cu")).read()
