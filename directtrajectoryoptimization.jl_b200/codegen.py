@@ -818,6 +818,20 @@ def build_model(spec: ModelSpec, verbose: bool = False, force: bool = False) -> 
     so, cu = base + ".so", base + ".cu"
     if os.path.exists(so) and not force:
         return so
+    # one builder at a time per library: the ranks of a torchrun launch that all miss the same model must not
+    # race on the .cu / .so.tmp files (seen on an 8-GPU box); the others wait and then find the finished .so
+    import fcntl
+    with open(base + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if os.path.exists(so) and not force:
+                return so
+            return _build_model_locked(spec, hsh, base, so, cu, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_model_locked(spec: ModelSpec, hsh: str, base: str, so: str, cu: str, verbose: bool) -> str:
     t0 = time.time()
     src, stats = emit_model(spec, hsh)
     with open(cu, "w") as f:

@@ -26,28 +26,34 @@ hout.fill_(0)
 din = torch.empty(H2D, dtype=torch.uint8, device="cuda")
 dout = torch.ones(D2H, dtype=torch.uint8, device="cuda")
 s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-res = {}
-for mode in ("d2h", "h2d", "both"):
-    for it in range(2):  # warm-up pass, timed pass
-        torch.cuda.synchronize()
+for n_active in (1, 2, 4, 8):
+    if n_active > world:
+        break
+    active = rank < n_active  # the other ranks only join the barriers
+    res = {}
+    for mode in ("d2h", "h2d", "both"):
+        for it in range(2):  # warm-up pass, timed pass
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            if active:
+                for _ in range(20):
+                    if mode in ("h2d", "both"):
+                        with torch.cuda.stream(s_in):
+                            din.copy_(hin, non_blocking=True)
+                    if mode in ("d2h", "both"):
+                        with torch.cuda.stream(s_out):
+                            hout.copy_(dout, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 20
+        t = torch.tensor([dt if active else 0.0], dtype=torch.float64)
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(20):
-            if mode in ("h2d", "both"):
-                with torch.cuda.stream(s_in):
-                    din.copy_(hin, non_blocking=True)
-            if mode in ("d2h", "both"):
-                with torch.cuda.stream(s_out):
-                    hout.copy_(dout, non_blocking=True)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / 20
-    t = torch.tensor([dt], dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    byt = (H2D if mode != "d2h" else 0) + (D2H if mode != "h2d" else 0)
-    res[mode] = {"ms_max_over_ranks": 1e3 * float(t), "GBs_per_gpu": byt / float(t) / 1e9, "GBs_aggregate": world * byt / float(t) / 1e9}
-if rank == 0:
-    print(json.dumps({"n_gpus": world, "bind": "--bind" in sys.argv, "binding_rank0": binding, "host_cpus": os.cpu_count(), **res}), flush=True)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        byt = (H2D if mode != "d2h" else 0) + (D2H if mode != "h2d" else 0)
+        res[mode] = {"ms_max_over_ranks": 1e3 * float(t), "GBs_per_gpu": byt / float(t) / 1e9, "GBs_aggregate": n_active * byt / float(t) / 1e9}
+    if rank == 0:
+        print(json.dumps({"n_gpus": n_active, "launched": world, "bind": "--bind" in sys.argv, "binding_rank0": binding,
+                          "host_cpus": os.cpu_count(), **res}), flush=True)
 if world > 1:
     dist.destroy_process_group()
