@@ -186,6 +186,13 @@ def cstr(e: sp.Expr, names: Dict[sp.Symbol, str]) -> str:
             k = int(float(p))
             return f"(1.0/{_pow_c(b, -k, names)})" if k < 0 else _pow_c(b, k, names)
         return f"pow({cstr(b, names)}, {cstr(p, names)})"
+    if isinstance(e, sp.Piecewise):
+        out = "0.0"
+        for val, cond in reversed(e.args):
+            out = cstr(val, names) if cond is sp.true else f"(({cstr(cond, names)}) ? {cstr(val, names)} : {out})"
+        return out
+    if e.is_Relational:
+        return f"({cstr(e.lhs, names)} {e.rel_op} {cstr(e.rhs, names)})"
     if e.is_Function:
         fn = _CFUN.get(e.func.__name__)
         if fn is None:

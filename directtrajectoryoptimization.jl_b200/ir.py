@@ -24,6 +24,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import sympy as sp
 
 UNARY = ("sin", "cos", "tan", "exp", "log", "sqrt", "atan", "sinh", "cosh", "tanh")
+CMP = {"lt": "<", "le": "<=", "gt": ">", "ge": ">=", "eq": "==", "ne": "!="}  # boolean nodes (a, b)
 
 
 class Graph:
@@ -183,6 +184,16 @@ class Graph:
                 return self._mk(name, (self.neg(a),))
         return self._mk(name, (a,))
 
+    def cmp(self, op: str, a: int, b: int) -> int:
+        """boolean node a <op> b (only ever the condition of a `sel`)"""
+        return self._mk(op, (a, b))
+
+    def sel(self, c: int, a: int, b: int) -> int:
+        """ifelse(c, a, b)"""
+        if a == b:
+            return a
+        return self._mk("sel", (c, a, b))
+
     def powc(self, a: int, p: float) -> int:
         """a ** p for a non-integer constant exponent."""
         if p == 0.5:
@@ -239,6 +250,10 @@ class Graph:
                 r = self.powi(b[0], self.val[m])
             elif op == "powc":
                 r = self.powc(b[0], self.val[m])
+            elif op in CMP:
+                r = self.cmp(op, b[0], b[1])
+            elif op == "sel":
+                r = self.sel(b[0], b[1], b[2])
             else:
                 r = self.func(op, b[0])
             memo[m] = r
@@ -272,6 +287,11 @@ class Graph:
                 v[m] = v[a[0]] ** self.val[m]
             elif op == "powc":
                 v[m] = v[a[0]] ** self.val[m]
+            elif op in CMP:
+                x_, y_ = v[a[0]], v[a[1]]
+                v[m] = {"lt": x_ < y_, "le": x_ <= y_, "gt": x_ > y_, "ge": x_ >= y_, "eq": x_ == y_, "ne": x_ != y_}[op]
+            elif op == "sel":
+                v[m] = v[a[1]] if v[a[0]] else v[a[2]]
             else:
                 v[m] = getattr(math, op)(v[a[0]])
         return [v[m] for m in nodes]
@@ -308,6 +328,17 @@ class Graph:
             else:
                 # a^b = exp(b log a)
                 r = self.func("exp", self.mul(self._conv(p, sym, memo), self.func("log", self._conv(b, sym, memo))))
+        elif isinstance(e, sp.Piecewise):
+            (val, cond) = e.args[-1]
+            if cond is not sp.true:
+                raise NotImplementedError("Piecewise without an otherwise branch")
+            r = self._conv(val, sym, memo)
+            for val, cond in reversed(e.args[:-1]):
+                if not cond.is_Relational:
+                    raise NotImplementedError(f"no DAG lowering for condition {cond}")
+                op = {"<": "lt", "<=": "le", ">": "gt", ">=": "ge", "==": "eq", "!=": "ne"}[cond.rel_op]
+                c = self.cmp(op, self._conv(cond.lhs, sym, memo), self._conv(cond.rhs, sym, memo))
+                r = self.sel(c, self._conv(val, sym, memo), r)
         elif e.is_Function and len(e.args) == 1 and e.func.__name__ in UNARY:
             r = self.func(e.func.__name__, self._conv(e.args[0], sym, memo))
         else:
@@ -458,6 +489,17 @@ class Derivatives:
                             self._acc(H, (i, i), g.mul(g.const(2.0), t))
                         else:
                             self._acc(H, (i, j) if i < j else (j, i), t)
+        elif op in CMP:
+            pass  # a condition: piecewise constant, no derivative
+        elif op == "sel":
+            c, a, b = g.args[n]
+            ga, gb = self._grad[a], self._grad[b]
+            for k in sorted(set(ga) | set(gb)):
+                self._acc(G, k, g.sel(c, ga.get(k, g.ZERO), gb.get(k, g.ZERO)))
+            if self.second:
+                ha, hb = self._hess[a], self._hess[b]
+                for k in sorted(set(ha) | set(hb)):
+                    self._acc(H, k, g.sel(c, ha.get(k, g.ZERO), hb.get(k, g.ZERO)))
         else:  # unary function of args[0]
             a = g.args[n][0]
             ga = self._grad[a]
@@ -625,7 +667,8 @@ def choose_cuts(g: Graph, outs: Sequence[int], L: int, wrt: Sequence[int], selec
             for a in g.args[n]:
                 s_ |= sup[a]
             sup[n] = s_
-    cands = [n for n in sorted(sup) if g.op[n] not in ("in", "const", "neg") and len(sup[n]) >= 2 and n != L and n not in outs]
+    cands = [n for n in sorted(sup) if g.op[n] not in ("in", "const", "neg") and g.op[n] not in CMP and len(sup[n]) >= 2
+             and n != L and n not in outs]
     cur: set = set()
     best = base
     evals = 1
@@ -766,6 +809,12 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
         elif op == "powc":
             name[n] = nm
             lines.append(f"{indent}const double {nm} = pow({ref(a[0])}, {_lit(g.val[n])});")
+        elif op in CMP:
+            name[n] = nm
+            lines.append(f"{indent}const bool {nm} = {ref(a[0])} {CMP[op]} {ref(a[1])};")
+        elif op == "sel":
+            name[n] = nm
+            lines.append(f"{indent}const double {nm} = {ref(a[0])} ? {ref(a[1])} : {ref(a[2])};")
         elif op in ("sin", "cos") and a[0] in paired:
             s, c = sin_of[a[0]], cos_of[a[0]]
             name[s], name[c] = f"{prefix}{s}", f"{prefix}{c}"

@@ -30,7 +30,6 @@ package's own structural detection and a mismatch is reported.
 from __future__ import annotations
 
 import json
-import re
 import sys
 from typing import Dict, List
 
@@ -66,21 +65,76 @@ def expr_to_text(e: sp.Expr) -> str:
 
 
 def text_to_expr(text: str, symbols: Dict[str, sp.Symbol]) -> sp.Expr:
-    t = text.replace("^", "**")
-    def lit(m):
-        tok = m.group(1)
-        return f"_F({tok!r})" if any(c in tok for c in ".eE") else f"_I({tok})"
+    """Julia-printed (or C) expression text -> sympy, through the recursive-descent parser of exprparse.py:
+    juxtaposed coefficients (0.5x1, 2sin(x2), -0.5(x1 + y1)), `//` rationals, unicode subscripts, inv, abs2,
+    ifelse and comparisons are understood; nothing is `eval`-ed."""
+    from .exprparse import parse_expr
+    return parse_expr(text, symbols)
 
-    t = re.sub(r"(?<![\w.])(\d+\.?\d*(?:[eE][+-]?\d+)?)", lit, t)
-    env = dict(_FUNCS)
-    env.update(symbols)
-    env["_F"] = lambda tok: sp.Float(float(tok))   # the double nearest to the literal, 53-bit
-    env["_I"] = sp.Integer
-    return sp.sympify(eval(t, {"__builtins__": {}}, env))  # noqa: S307 - restricted namespace, numeric grammar only
+
+def expr_to_c(e: sp.Expr, ref: Dict[sp.Symbol, str]) -> str:
+    """One right-hand side the way the Symbolics C target prints it: Julia's Expr printer
+    (binary operators with spaces, shortest-repr literals, `1//2` rationals) with `^` rewritten to pow(a, b)
+    and variables as zero-based references into the C arguments (`x[1]`)."""
+    e = sp.sympify(e)
+    if e.is_Symbol:
+        return ref[e]
+    if e.is_Integer:
+        return str(int(e))
+    if e.is_Rational:
+        return f"{int(e.p)}//{int(e.q)}"
+    if e.is_Number or e.is_NumberSymbol:
+        return repr(float(e))
+    if e.is_Add:
+        out = ""
+        for k, a in enumerate(e.args):
+            neg = a.could_extract_minus_sign() and k > 0
+            t = expr_to_c(-a if neg else a, ref)
+            if (-a if neg else a).is_Add:
+                t = f"({t})"
+            out = t if k == 0 else f"{out} {'-' if neg else '+'} {t}"
+        return out
+    if e.is_Mul:
+        parts = []
+        for a in e.args:
+            t = expr_to_c(a, ref)
+            if a.is_Add or (a.is_Number and a < 0) or (a.is_Rational and not a.is_Integer):
+                t = f"({t})"
+            parts.append(t)
+        return " * ".join(parts)
+    if e.is_Pow:
+        return f"pow({expr_to_c(e.args[0], ref)}, {expr_to_c(e.args[1], ref)})"
+    if isinstance(e, sp.Piecewise):
+        (a, c), (b, _) = e.args[0], e.args[1]
+        return f"ifelse({expr_to_c(c, ref)}, {expr_to_c(a, ref)}, {expr_to_c(b, ref)})"
+    if e.is_Relational:
+        return f"{expr_to_c(e.lhs, ref)} {e.rel_op} {expr_to_c(e.rhs, ref)}"
+    if e.is_Function:
+        name = {"Abs": "abs"}.get(e.func.__name__, e.func.__name__)
+        return name + "(" + ", ".join(expr_to_c(a, ref) for a in e.args) + ")"
+    raise NotImplementedError(type(e))
+
+
+def c_function(fname: str, exprs, args: Dict[str, List[sp.Symbol]], lhsname: str = "out") -> str:
+    """`build_function(exprs, args...; target = Symbolics.CTarget(), fname, lhsname, rhsnames)` as text."""
+    ref = {s: f"{n}[{i}]" for n, syms in args.items() for i, s in enumerate(syms)}
+    sig = ", ".join([f"double* {lhsname}"] + [f"const double* {n}" for n, syms in args.items() if len(syms)])  # no empty arrays in C
+    body = "\n".join(f"  {lhsname}[{i}] = {expr_to_c(e, ref)};" for i, e in enumerate(exprs))
+    return f"#include <math.h>\nvoid {fname}({sig}) {{\n{body}\n}}\n"
 
 
 def _syms(prefix: str, n: int) -> List[sp.Symbol]:
     return [sp.Symbol(f"{prefix}{i + 1}") for i in range(n)]
+
+
+def _evaluate(d: dict, table: Dict[str, sp.Symbol], cargs: Dict[str, List[sp.Symbol]]) -> List[sp.Expr]:
+    """The element's expressions: "evaluate_c" = one Symbolics C-target function over the arguments `cargs`
+    (what julia/DTOB200.jl writes), or "evaluate" = Julia-printed text per output over x1.. u1.. names."""
+    if "evaluate_c" in d:
+        from .exprparse import parse_c_function
+        return parse_c_function(d["evaluate_c"], cargs)[2]
+    ev = d["evaluate"]
+    return [text_to_expr(t, table) for t in ([ev] if isinstance(ev, str) else ev)]
 
 
 def _element(role: str, d: dict) -> ElementSpec:
@@ -91,17 +145,17 @@ def _element(role: str, d: dict) -> ElementSpec:
         ny = d["num_next_state"]
         y = _syms("y", ny)
         table.update({s.name: s for s in y})
-        ev = [text_to_expr(t, table) for t in d["evaluate"]]
+        ev = _evaluate(d, table, {"y": y, "x": x, "u": u, "w": w})
         vars_ = x + u + y
         lam = _syms("lam", ny)
         args = {"y": y, "x": x, "u": u, "w": w, "lam": lam}
         n_out = ny
     elif role == "cost":
-        ev = [text_to_expr(d["evaluate"] if isinstance(d["evaluate"], str) else d["evaluate"][0], table)]
+        ev = _evaluate(d, table, {"x": x, "u": u, "w": w})[:1]
         vars_, lam, n_out = x + u, [], 1
         args = {"x": x, "u": u, "w": w}
     else:
-        ev = [text_to_expr(t, table) for t in d["evaluate"]]
+        ev = _evaluate(d, table, {"x": x, "u": u, "w": w})
         vars_ = x + u
         lam = _syms("lam", len(ev))
         args = {"x": x, "u": u, "w": w, "lam": lam}
@@ -129,7 +183,7 @@ def _general(d: dict) -> GeneralSpec:
     nz, nw = d["num_variables"], d.get("num_parameter", 0)
     z, w = _syms("z", nz), _syms("w", nw)
     table = {s.name: s for s in z + w}
-    ev = [text_to_expr(t, table) for t in d["evaluate"]]
+    ev = _evaluate(d, table, {"z": z, "w": w})
     lam = _syms("lam", len(ev))
     jr, jc = [list(v) for v in d["jacobian_sparsity"]]
     jv = S.jacobian_values(ev, z, jr, jc)
@@ -162,17 +216,25 @@ def load_spec(doc: dict) -> ModelSpec:
     return spec
 
 
-def dump_spec(spec: ModelSpec, shape: dict = None) -> dict:
-    """ModelSpec -> JSON document (what the Julia glue writes)."""
+def dump_spec(spec: ModelSpec, shape: dict = None, style: str = "text") -> dict:
+    """ModelSpec -> JSON document (what the Julia glue writes). style "text": one infix string per output;
+    "ctarget": one Symbolics-C-target function per element ("evaluate_c")."""
+    def put(d, name, exprs, cargs, single=False):
+        if style == "ctarget":
+            d["evaluate_c"] = c_function(name, exprs, cargs)
+        else:
+            d["evaluate"] = expr_to_text(exprs[0]) if single else [expr_to_text(x) for x in exprs]
+
     def el(e: ElementSpec) -> dict:
         d = {"num_state": e.nx, "num_action": e.nu, "num_parameter": e.nw, "evaluate_hessian": e.has_hess,
              "hessian_sparsity": [list(e.hess_rows), list(e.hess_cols)]}
         if e.role == "dyn":
             d["num_next_state"] = e.n_out
+        cargs = {k: list(v) for k, v in e.args.items() if k != "lam"}
         if e.role == "cost":
-            d["evaluate"] = expr_to_text(e.evaluate[0])
+            put(d, "cost_evaluate", e.evaluate, cargs, single=True)
         else:
-            d["evaluate"] = [expr_to_text(x) for x in e.evaluate]
+            put(d, f"{e.role}_evaluate", e.evaluate, cargs)
             d["jacobian_sparsity"] = [list(e.jac_rows), list(e.jac_cols)]
             d["indices_inequality"] = list(e.ineq)
         return d
@@ -182,9 +244,9 @@ def dump_spec(spec: ModelSpec, shape: dict = None) -> dict:
     if spec.general is not None:
         g = spec.general
         doc["general"] = {"num_variables": g.num_variables, "num_parameter": g.num_parameter,
-                          "evaluate": [expr_to_text(x) for x in g.evaluate],
                           "jacobian_sparsity": [list(g.jac_rows), list(g.jac_cols)], "evaluate_hessian": g.has_hess,
                           "hessian_sparsity": [list(g.hess_rows), list(g.hess_cols)], "indices_inequality": list(g.ineq)}
+        put(doc["general"], "general_evaluate", g.evaluate, {"z": list(g.args["z"]), "w": list(g.args["w"])})
     return doc
 
 

@@ -166,6 +166,14 @@ def _shapes(e: sp.Expr, var_index: Dict[sp.Symbol, int], memo: Dict[sp.Expr, obj
             r = base if e.args[1] == 1 else _times(base, base)
         else:
             r = _binary_nonlinear(base if base is not None else _SCALAR, expo if expo is not None else _SCALAR)
+    elif isinstance(e, sp.Piecewise):
+        # ifelse(c, a, b): the branches combine like a sum, the condition carries no curvature (the rule
+        # Symbolics applies to IfElse.ifelse as far as recorded in SURVEY App. C; no reference model uses it)
+        r = _SCALAR
+        for val, _cond in e.args:
+            c = _shapes(val, var_index, memo)
+            if c is not None:
+                r = _plus(r, c)
     elif e.is_Function:
         cs = [_shapes(arg, var_index, memo) for arg in e.args]
         if len(cs) == 1:

@@ -45,6 +45,14 @@ def dot(a, b):
     return s
 
 
+def ifelse(cond, a, b):
+    """IfElse.ifelse (imported by the reference, src/DirectTrajectoryOptimization.jl:5): symbolic when the
+    condition is, plain python otherwise."""
+    if _sym(cond):
+        return sp.Piecewise((a, cond), (b, True))
+    return a if cond else b
+
+
 def arr(*v):
     return np.array(v, dtype=object)
 
@@ -438,6 +446,85 @@ def build_heterogeneous(api, evaluate_hessian=True):
     )
 
 
+def build_user_jacobian(api, T=11, nonlinear=False):
+    """test/solve.jl:140-225: double integrator whose dynamics Jacobian is SUPPLIED by the user
+    (second Dynamics constructor, src/dynamics.jl:59-101): dense column-major pattern, no Hessian, state
+    end points pinned by bounds. `nonlinear=True` (not in the reference) makes f and the user Jacobian
+    state dependent and the Jacobian deliberately NOT the exact derivative (entry (2,1) is scaled by 3),
+    so a parity test can tell "lowered the user's expressions" from "differentiated f"."""
+    n, m = 2, 1
+
+    def f(y, x, u, w):
+        A = np.array([[1.0, 1.0], [0.0, 1.0]], dtype=object)
+        Bm = arr(0.0, 1.0)
+        r = y - (A @ x + Bm * u[0])
+        if nonlinear:
+            r = r - arr(0.0, 0.1 * sin(x[0]) * u[0])
+        return r
+
+    def fz(J, y, x, u, w):
+        J[:, :] = 0.0
+        J[0, 0], J[0, 1] = -1.0, -1.0
+        J[1, 1] = -1.0
+        J[1, 2] = -1.0
+        J[0, 3], J[1, 4] = 1.0, 1.0
+        if nonlinear:
+            J[1, 0] = -3.0 * 0.1 * cos(x[0]) * u[0]
+            J[1, 2] = -1.0 - 0.1 * sin(x[0])
+
+    dt = api.Dynamics(f, fz, n, n, m)
+    ot = lambda x, u, w: 0.1 * dot(x, x) + 0.1 * dot(u, u)
+    oT = lambda x, u, w: 0.1 * dot(x, x)
+    ct = api.Cost(ot, n, m, num_parameter=0)
+    cT = api.Cost(oT, n, 0, num_parameter=0)
+    x1 = np.array([0.0, 0.0])
+    xT = np.array([1.0, 0.0])
+    return dict(
+        name="user_jacobian", T=T, n=n, m=m,
+        dynamics=[dt] * (T - 1), objective=[ct] * (T - 1) + [cT],
+        constraints=[api.Constraint() for _ in range(T)],
+        bounds=[api.Bound(n, m, state_lower=x1, state_upper=x1)] + [api.Bound(n, m)] * (T - 2)
+        + [api.Bound(n, 0, state_lower=xT, state_upper=xT)],
+        general=None, evaluate_hessian=False, x1=x1, xT=xT,
+    )
+
+
+def build_piecewise(api, T=9, evaluate_hessian=True):
+    """Not from the reference's examples: exercises `ifelse` in every element role (the reference imports
+    IfElse, src/DirectTrajectoryOptimization.jl:5, but no model of it uses it) -- a pendulum whose torque
+    saturates smoothly on one side and whose damping switches with the sign of the velocity, a cost with a
+    one-sided penalty, and a stage constraint with a switched branch."""
+    n, m = 2, 1
+    h = 0.05
+
+    def f(x, u, w):
+        torque = ifelse(u[0] > 0.5, 0.5 + 0.25 * sin(2.0 * (u[0] - 0.5)), u[0])
+        damp = ifelse(x[1] >= 0.0, 0.1 * x[1] + 0.05 * x[1] ** 2, 0.1 * x[1] - 0.05 * x[1] ** 2)
+        return arr(x[1], 4.0 * torque - 19.62 * sin(x[0]) - 4.0 * damp)
+
+    def dyn(y, x, u, w):
+        return y - (x + h * f(0.5 * (x + y), u, w))
+
+    dt = api.Dynamics(dyn, n, n, m, evaluate_hessian=evaluate_hessian)
+    ot = lambda x, u, w: 0.1 * dot(x, x) + 0.1 * dot(u, u) + ifelse(x[0] > 1.0, 2.0 * (x[0] - 1.0) ** 3, 0.0 * x[0])
+    oT = lambda x, u, w: 0.1 * dot(x, x)
+    ct = api.Cost(ot, n, m, evaluate_hessian=evaluate_hessian)
+    cT = api.Cost(oT, n, 0, evaluate_hessian=evaluate_hessian)
+    x1 = np.array([0.0, 0.0])
+    xT = np.array([math.pi, 0.0])
+    con1 = api.Constraint(lambda x, u, w: x - x1, n, m, evaluate_hessian=evaluate_hessian)
+    cont = api.Constraint(lambda x, u, w: arr(ifelse(x[1] < 0.0, x[1] ** 2 - 9.0, x[1] * u[0] - 9.0)), n, m,
+                          indices_inequality=[1], evaluate_hessian=evaluate_hessian)
+    conT = api.Constraint(lambda x, u, w: x - xT, n, 0, evaluate_hessian=evaluate_hessian)
+    return dict(
+        name="piecewise", T=T, n=n, m=m,
+        dynamics=[dt] * (T - 1), objective=[ct] * (T - 1) + [cT],
+        constraints=[con1] + [cont for _ in range(2, T)] + [conT],
+        bounds=[api.Bound(n, m)] * (T - 1) + [api.Bound(n, 0)],
+        general=None, evaluate_hessian=evaluate_hessian, x1=x1, xT=xT,
+    )
+
+
 BUILDERS = {
     "pendulum": build_pendulum,
     "cartpole": build_cartpole,
@@ -446,4 +533,6 @@ BUILDERS = {
     "acrobot_hessian_test": build_acrobot_hessian_test,
     "linear_general": build_linear_general,
     "heterogeneous": build_heterogeneous,
+    "user_jacobian": build_user_jacobian,
+    "piecewise": build_piecewise,
 }

@@ -2,27 +2,44 @@
 #
 # Written against DirectTrajectoryOptimization.jl as vendored at /root/reference
 # (Julia 1.6, Symbolics 0.1.29-0.1.32, MathOptInterface 1.3, Ipopt.jl 1.0.2; Project.toml:16-23).
-# NOT EXECUTED in this repository's CI: the build image has no Julia. It is kept small and literal:
-# every ccall below binds one entry point of include/dto.h, and the evaluator methods mirror
-# /root/reference/src/moi.jl one for one.
+# NOT EXECUTED in this repository's CI: the build image has no Julia. It is kept small and literal: every
+# ccall binds one entry point of include/dto.h, the evaluator methods mirror /root/reference/src/moi.jl one
+# for one, and the text it hands to the code generator is covered by fixtures that ARE tested here
+# (tests/fixtures_ctarget/*.json, tests/test_frontend_cpu.py).
 #
-# What it does
-#   1. `export_spec(solver)`  re-traces nothing: it re-builds the Symbolics expressions exactly like
-#      the reference constructors do (src/dynamics.jl:23-35, src/costs.jl:18-27,
-#      src/constraints.jl:27-40, src/general_constraint.jl:23-36), prints them as infix text and
-#      writes the JSON model spec that `python -m dto_b200.spec_io spec.json` compiles to a CUDA model
-#      library (content-addressed: the reference's "#TODO: option to load/save methods").
-#   2. `BatchedNLPData` <: MOI.AbstractNLPEvaluator wraps a dto_batch handle. With batch = 1 it is a
-#      drop-in for the reference's NLPData inside MOI.NLPBlockData (src/data.jl:233-234); with
-#      batch = B it serves B lock-step Ipopt instances (see INTEGRATION.md, "Batched Ipopt driver").
+# What a user changes in a script written for the reference:
+#
+#     using DirectTrajectoryOptimization            # unchanged
+#     using DTOB200                                 # + this module
+#     dt   = DTOB200.Dynamics(f, ny, nx, nu; evaluate_hessian=true)      # same arguments as the reference's
+#     ct   = DTOB200.Cost(ot, nx, nu; evaluate_hessian=true)             #   constructors (src/dynamics.jl:18,
+#     con  = DTOB200.Constraint(c, nx, nu; indices_inequality=[1])       #   src/costs.jl:13, src/constraints.jl:21,
+#     gen  = DTOB200.GeneralConstraint(g, nz, nw)                        #   src/general_constraint.jl:18)
+#     solver = DTOB200.Solver(dynamics, objective, constraints, bounds;  # same arguments as src/solver.jl:6-10 ...
+#                             evaluate_hessian=true, batch=1, devices=[0])   # ... plus batch / devices
+#     initialize_states!(solver, x_guess); initialize_controls!(solver, u_guess)
+#     solve!(solver); x, u = get_trajectory(solver)
+#
+# The constructors build the reference element (so everything of the reference keeps working on it) AND record
+# the element's Symbolics expressions, emitted through Symbolics' C target (`build_function(...;
+# target=Symbolics.CTarget())`), in a registry keyed by the element object. `Solver` collects them into the
+# JSON model spec, has `python -m dto_b200.spec_io` compile it to a CUDA model library for sm_100a
+# (content-addressed cache: the reference's "#TODO: option to load/save methods", src/dynamics.jl:22) and hands
+# Ipopt a `BatchedNLPData` evaluator instead of the reference's NLPData (src/data.jl:233-234).
 module DTOB200
 
 using MathOptInterface
 const MOI = MathOptInterface
 using Symbolics
+using SparseArrays: findnz
 using LinearAlgebra: dot
+import Ipopt
+import DirectTrajectoryOptimization
+const DTO = DirectTrajectoryOptimization
 
 const libdto = get(ENV, "DTO_LIB", "libdto.so")
+const python = get(ENV, "DTO_PYTHON", "python")
+const repo   = get(ENV, "DTO_REPO", normpath(joinpath(@__DIR__, "..")))
 
 # ---------------------------------------------------------------- thin ccall layer (include/dto.h)
 check(status::Cint) = status == 0 || error("dto: " * unsafe_string(ccall((:dto_last_error, libdto), Cstring, ())))
@@ -72,6 +89,20 @@ function structure(f::Symbol, s, n)
     collect(zip(r, c))                  # Vector{Tuple{Int,Int}}, 1-based, reference order
 end
 
+function constraint_bounds(s)
+    n = num_constraint(s)
+    lo = Vector{Float64}(undef, n); up = Vector{Float64}(undef, n)
+    check(ccall((:dto_constraint_bounds, libdto), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), s, lo, up))
+    lo, up
+end
+
+"z-layout of the shape (src/dynamics.jl:188-195): 1-based index ranges of x_t and u_t"
+function knot_layout(s, T)
+    xs = Vector{Int64}(undef, T); nx = Vector{Int32}(undef, T); us = Vector{Int64}(undef, T); nu = Vector{Int32}(undef, T)
+    check(ccall((:dto_knot_layout, libdto), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}), s, xs, nx, us, nu))
+    [collect(xs[t]:xs[t] + nx[t] - 1) for t in 1:T], [collect(us[t]:us[t] + nu[t] - 1) for t in 1:T]
+end
+
 # ---------------------------------------------------------------- evaluator
 mutable struct BatchedNLPData <: MOI.AbstractNLPEvaluator
     model::Ptr{Cvoid}
@@ -95,6 +126,7 @@ function BatchedNLPData(model_path, T, kd, kc, ks; use_general=false, pdim=zeros
 end
 
 set_x!(nlp, z) = check(ccall((:dto_set_x, libdto), Cint, (Ptr{Cvoid}, Ptr{Float64}), nlp.batch, z))
+set_parameters!(nlp, w) = check(ccall((:dto_set_parameters, libdto), Cint, (Ptr{Cvoid}, Ptr{Float64}), nlp.batch, w))
 
 # the five callbacks, method for method as /root/reference/src/moi.jl:1-120 (batch = 1: z is a Vector;
 # batch = B: z, outputs are B x n row-major, i.e. Julia matrices of size (n, B))
@@ -127,32 +159,225 @@ MOI.initialize(nlp::BatchedNLPData, features) = nothing
 MOI.jacobian_structure(nlp::BatchedNLPData) = nlp.jacobian_sparsity
 MOI.hessian_lagrangian_structure(nlp::BatchedNLPData) = nlp.hessian_lagrangian_sparsity
 
-# ---------------------------------------------------------------- spec export (Symbolics -> JSON text)
-ascii_name(prefix, i) = string(prefix, i)
-function plain_variables(prefix, n)      # @variables x[1:n] but with ASCII names x1..xn
-    [Symbolics.variable(Symbol(ascii_name(prefix, i))) for i in 1:n]
+# ---------------------------------------------------------------- expression export (Symbolics C target)
+"`@variables name[1:n]` as the reference's constructors write it (src/dynamics.jl:23): a Vector{Num}"
+symbolic_vector(name::Symbol, n::Int) = n == 0 ? Num[] : collect(first(Symbolics.@variables $name[1:n]))
+
+"One C function `void fname(double* out, const double* a1, ...)` for the expressions `ex` over the argument
+vectors `args` named `names` -- Symbolics' own C target, zero-based references, `pow` for `^` (SURVEY App. C).
+Arguments of length zero are dropped from the signature (C has no empty arrays); the parser is told the same."
+function ctarget(fname::String, ex, names::Vector{Symbol}, args)
+    keep = [i for i in eachindex(args) if length(args[i]) > 0]
+    Symbolics.build_function(collect(ex), args[keep]...; target=Symbolics.CTarget(), fname=Symbol(fname),
+                             lhsname=:out, rhsnames=names[keep], expression=Val{true})
 end
-totext(e) = replace(string(e), "π" => string(Float64(pi)))   # Julia infix: + - * / ^, sin cos tan ...
+
+sparsity_lists(S) = (I = findnz(S)[1]; J = findnz(S)[2]; [collect(Int, I), collect(Int, J)])   # CSC order, 1-based
 
 "Re-trace `f` like Dynamics(f, ny, nx, nu; ...) does (src/dynamics.jl:23-35) and describe it for the code generator."
 function dynamics_spec(f, ny, nx, nu; num_parameter=0, evaluate_hessian=false)
-    y, x, u, w = plain_variables("y", ny), plain_variables("x", nx), plain_variables("u", nu), plain_variables("w", num_parameter)
+    y, x, u, w = symbolic_vector(:y, ny), symbolic_vector(:x, nx), symbolic_vector(:u, nu), symbolic_vector(:w, num_parameter)
     ev = f(y, x, u, w)
-    jac = Symbolics.sparsejacobian(ev, [x; u; y])
-    I, J, _ = findnz(jac)
-    d = Dict("num_next_state" => ny, "num_state" => nx, "num_action" => nu, "num_parameter" => num_parameter,
-             "evaluate" => totext.(ev), "jacobian_sparsity" => [I, J], "evaluate_hessian" => evaluate_hessian,
-             "hessian_sparsity" => [Int[], Int[]])
+    d = Dict{String,Any}("num_next_state" => ny, "num_state" => nx, "num_action" => nu, "num_parameter" => num_parameter,
+             "evaluate_c" => ctarget("dyn_evaluate", ev, [:y, :x, :u, :w], [y, x, u, w]),
+             "jacobian_sparsity" => sparsity_lists(Symbolics.jacobian_sparsity(ev, [x; u; y])),
+             "evaluate_hessian" => evaluate_hessian, "hessian_sparsity" => [Int[], Int[]])
     if evaluate_hessian
-        λ = plain_variables("lam", ny)
-        Hs = Symbolics.hessian_sparsity(dot(λ, ev), [x; u; y])
-        HI, HJ, _ = findnz(Hs)
-        d["hessian_sparsity"] = [HI, HJ]
+        λ = symbolic_vector(:lam, ny)
+        d["hessian_sparsity"] = sparsity_lists(Symbolics.hessian_sparsity(dot(λ, ev), [x; u; y]))
     end
     d
 end
-# cost_spec / constraint_spec / general_spec follow the same three lines with the variable lists of
-# src/costs.jl:18-27, src/constraints.jl:27-40, src/general_constraint.jl:23-36.
+
+"src/costs.jl:18-27: scalar cost over [x; u]; the gradient is dense (no pattern to hand over)."
+function cost_spec(f, nx, nu; num_parameter=0, evaluate_hessian=false)
+    x, u, w = symbolic_vector(:x, nx), symbolic_vector(:u, nu), symbolic_vector(:w, num_parameter)
+    ev = [f(x, u, w)]
+    d = Dict{String,Any}("num_state" => nx, "num_action" => nu, "num_parameter" => num_parameter,
+             "evaluate_c" => ctarget("cost_evaluate", ev, [:x, :u, :w], [x, u, w]),
+             "evaluate_hessian" => evaluate_hessian, "hessian_sparsity" => [Int[], Int[]])
+    evaluate_hessian && (d["hessian_sparsity"] = sparsity_lists(Symbolics.hessian_sparsity(ev[1], [x; u])))
+    d
+end
+
+"src/constraints.jl:27-40: stage constraint c(x, u, w) over [x; u]; inequality rows are local row numbers."
+function constraint_spec(f, nx, nu; num_parameter=0, indices_inequality=Int[], evaluate_hessian=false)
+    x, u, w = symbolic_vector(:x, nx), symbolic_vector(:u, nu), symbolic_vector(:w, num_parameter)
+    ev = f(x, u, w)
+    d = Dict{String,Any}("num_state" => nx, "num_action" => nu, "num_parameter" => num_parameter,
+             "evaluate_c" => ctarget("stage_evaluate", ev, [:x, :u, :w], [x, u, w]),
+             "jacobian_sparsity" => sparsity_lists(Symbolics.jacobian_sparsity(ev, [x; u])),
+             "indices_inequality" => collect(Int, indices_inequality),
+             "evaluate_hessian" => evaluate_hessian, "hessian_sparsity" => [Int[], Int[]])
+    if evaluate_hessian
+        λ = symbolic_vector(:lam, length(ev))
+        d["hessian_sparsity"] = sparsity_lists(Symbolics.hessian_sparsity(dot(λ, ev), [x; u]))
+    end
+    d
+end
+
+"src/general_constraint.jl:23-36: g(z, w) over the whole trajectory z and the flat parameter vector."
+function general_spec(f, nz, nw; indices_inequality=Int[], evaluate_hessian=false)
+    z, w = symbolic_vector(:z, nz), symbolic_vector(:w, nw)
+    ev = f(z, w)
+    d = Dict{String,Any}("num_variables" => nz, "num_parameter" => nw,
+             "evaluate_c" => ctarget("general_evaluate", ev, [:z, :w], [z, w]),
+             "jacobian_sparsity" => sparsity_lists(Symbolics.jacobian_sparsity(ev, z)),
+             "indices_inequality" => collect(Int, indices_inequality),
+             "evaluate_hessian" => evaluate_hessian, "hessian_sparsity" => [Int[], Int[]])
+    if evaluate_hessian
+        λ = symbolic_vector(:lam, length(ev))
+        d["hessian_sparsity"] = sparsity_lists(Symbolics.hessian_sparsity(dot(λ, ev), z))
+    end
+    d
+end
+
+# ---------------------------------------------------------------- drop-in constructors: reference element + its spec
+const SPECS = IdDict{Any,Dict{String,Any}}()     # reference element object  =>  its spec for the code generator
+
+function Dynamics(f::Function, ny::Int, nx::Int, nu::Int; num_parameter::Int=0, evaluate_hessian=false)
+    el = DTO.Dynamics(f, ny, nx, nu; num_parameter=num_parameter, evaluate_hessian=evaluate_hessian)
+    SPECS[el] = dynamics_spec(f, ny, nx, nu; num_parameter=num_parameter, evaluate_hessian=evaluate_hessian)
+    el
+end
+function Cost(f::Function, nx::Int, nu::Int; num_parameter::Int=0, evaluate_hessian=false)
+    el = DTO.Cost(f, nx, nu; num_parameter=num_parameter, evaluate_hessian=evaluate_hessian)
+    SPECS[el] = cost_spec(f, nx, nu; num_parameter=num_parameter, evaluate_hessian=evaluate_hessian)
+    el
+end
+function Constraint(f::Function, nx::Int, nu::Int; num_parameter::Int=0, indices_inequality=collect(1:0), evaluate_hessian=false)
+    el = DTO.Constraint(f, nx, nu; num_parameter=num_parameter, indices_inequality=indices_inequality, evaluate_hessian=evaluate_hessian)
+    SPECS[el] = constraint_spec(f, nx, nu; num_parameter=num_parameter, indices_inequality=indices_inequality,
+                                evaluate_hessian=evaluate_hessian)
+    el
+end
+Constraint() = DTO.Constraint()                   # empty (src/constraints.jl:66-78): kind -1, nothing to generate
+function GeneralConstraint(f::Function, nz::Int, nw::Int; indices_inequality=collect(1:0), evaluate_hessian=false)
+    el = DTO.GeneralConstraint(f, nz, nw; indices_inequality=indices_inequality, evaluate_hessian=evaluate_hessian)
+    SPECS[el] = general_spec(f, nz, nw; indices_inequality=indices_inequality, evaluate_hessian=evaluate_hessian)
+    el
+end
+GeneralConstraint() = DTO.GeneralConstraint()
+const Bound = DTO.Bound
+
+spec_of(el) = haskey(SPECS, el) ? SPECS[el] :
+    error("DTOB200: this element was built with the reference's constructor; the CUDA backend needs its expressions -- " *
+          "build it with DTOB200.Dynamics / Cost / Constraint / GeneralConstraint (arbitrary closures cannot run on the GPU, " *
+          "there is no CPU fallback)")
+
+"Distinct element objects of one role -> (kind per knot (0-based, -1 = empty), list of their specs)"
+function kinds(els; empty = el -> false)
+    seen = IdDict{Any,Int}(); specs = Dict{String,Any}[]; kind = Int32[]
+    for el in els
+        if empty(el)
+            push!(kind, -1); continue
+        end
+        haskey(seen, el) || (push!(specs, spec_of(el)); seen[el] = length(specs) - 1)
+        push!(kind, seen[el])
+    end
+    kind, specs
+end
+
+"The JSON model spec of a problem (spec_io.py's format) from the arguments of Solver(...) (src/solver.jl:6-10)."
+function export_spec(dynamics, objective, constraints; general_constraint=DTO.GeneralConstraint(), name="model")
+    T = length(objective)
+    kd, sd = kinds(dynamics)
+    kc, sc = kinds(objective)
+    ks, ss = kinds(constraints; empty = c -> c.num_constraint == 0)
+    gen = general_constraint.num_constraint == 0 ? nothing : spec_of(general_constraint)
+    Dict{String,Any}("name" => name, "dynamics" => sd, "costs" => sc, "constraints" => ss, "general" => gen,
+         "shape" => Dict("T" => T, "dynamics_kind" => kd, "cost_kind" => kc, "stage_kind" => ks))
+end
+
+# minimal JSON writer (no JSON.jl dependency in the reference's Project.toml)
+json(x::AbstractString) = "\"" * replace(replace(replace(x, "\\" => "\\\\"), "\"" => "\\\""), "\n" => "\\n") * "\""
+json(x::Bool) = x ? "true" : "false"
+json(x::Nothing) = "null"
+json(x::Real) = string(x)
+json(x::AbstractVector) = "[" * join(json.(x), ",") * "]"
+json(x::AbstractDict) = "{" * join([json(string(k)) * ":" * json(v) for (k, v) in x], ",") * "}"
+
+"Compile (or find in the content-addressed cache) the CUDA model library of a spec; returns the path of the .so"
+function build_model(spec::AbstractDict)
+    path = tempname() * ".json"
+    write(path, json(spec))
+    strip(read(setenv(`$python -m dto_b200.spec_io $path`; dir=repo), String))
+end
+
+# ---------------------------------------------------------------- Solver: same arguments as src/solver.jl:6-10 + batch, devices
+struct Solver
+    nlp::BatchedNLPData
+    optimizer::Ipopt.Optimizer                 # batch == 1: the one Ipopt instance (src/data.jl:237)
+    variables::Vector{MOI.VariableIndex}
+    state_indices::Vector{Vector{Int}}
+    action_indices::Vector{Vector{Int}}
+    z::Vector{Float64}                          # host mirror for get_trajectory (src/solver.jl:41-43)
+end
+
+function Solver(dynamics, objective, constraints, bounds;
+    evaluate_hessian=false,
+    general_constraint=DTO.GeneralConstraint(),
+    options=DTO.Options(),
+    parameters=[[zeros(d.num_parameter) for d in dynamics]..., zeros(0)],
+    batch::Int=1, devices=Cint[0], name="model")
+
+    T = length(objective)
+    spec = export_spec(dynamics, objective, constraints; general_constraint=general_constraint, name=name)
+    so = build_model(spec)
+    sh = spec["shape"]
+    pdim = Int32[t <= length(dynamics) ? dynamics[t].num_parameter : 0 for t in 1:T]
+    nlp = BatchedNLPData(String(so), T, sh["dynamics_kind"], sh["cost_kind"], sh["stage_kind"];
+                         use_general=general_constraint.num_constraint > 0, pdim=pdim, batch=batch,
+                         devices=Cint.(devices), evaluate_hessian=evaluate_hessian)
+    w = vcat(parameters...)                                    # src/data.jl:218 layout, one copy per problem
+    length(w) > 0 && set_parameters!(nlp, repeat(w, batch))
+    xi, ui = knot_layout(nlp.shape, T)
+
+    # variable bounds exactly as primal_bounds (src/data.jl:123-133)
+    n = num_variables(nlp.shape)
+    lower, upper = fill(-Inf, n), fill(Inf, n)
+    for (t, bnd) in enumerate(bounds)
+        length(bnd.state_lower)  > 0 && (lower[xi[t]] = bnd.state_lower)
+        length(bnd.state_upper)  > 0 && (upper[xi[t]] = bnd.state_upper)
+        length(bnd.action_lower) > 0 && (lower[ui[t]] = bnd.action_lower)
+        length(bnd.action_upper) > 0 && (upper[ui[t]] = bnd.action_upper)
+    end
+
+    # SolverData (src/data.jl:222-255) with the batched evaluator in the NLP block
+    clo, cup = constraint_bounds(nlp.shape)
+    block = MOI.NLPBlockData(MOI.NLPBoundsPair.(clo, cup), nlp, true)
+    optimizer = Ipopt.Optimizer()
+    for fld in fieldnames(typeof(options))
+        optimizer.options[String(fld)] = getfield(options, fld)
+    end
+    z = MOI.add_variables(optimizer, n)
+    for i = 1:n
+        MOI.add_constraint(optimizer, z[i], MOI.LessThan(upper[i]))
+        MOI.add_constraint(optimizer, z[i], MOI.GreaterThan(lower[i]))
+    end
+    MOI.set(optimizer, MOI.NLPBlock(), block)
+    MOI.set(optimizer, MOI.ObjectiveSense(), MOI.MIN_SENSE)
+    Solver(nlp, optimizer, z, xi, ui, zeros(n))
+end
+
+# src/solver.jl:23-47, unchanged semantics (batch == 1; the lock-step driver for batch > 1 is INTEGRATION.md §4)
+function DTO.initialize_states!(solver::Solver, states)
+    for (t, xt) in enumerate(states), i in eachindex(xt)
+        MOI.set(solver.optimizer, MOI.VariablePrimalStart(), solver.variables[solver.state_indices[t][i]], xt[i])
+    end
+end
+function DTO.initialize_controls!(solver::Solver, actions)
+    for (t, ut) in enumerate(actions), j in eachindex(ut)
+        MOI.set(solver.optimizer, MOI.VariablePrimalStart(), solver.variables[solver.action_indices[t][j]], ut[j])
+    end
+end
+DTO.solve!(solver::Solver) = MOI.optimize!(solver.optimizer)
+"the last z any callback was handed (the reference returns its internal per-knot buffers, src/solver.jl:41-43)"
+function DTO.get_trajectory(solver::Solver)
+    check(ccall((:dto_get_last_x, libdto), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), solver.nlp.batch, 0, solver.z))
+    T = length(solver.state_indices)
+    [solver.z[solver.state_indices[t]] for t in 1:T], [solver.z[solver.action_indices[t]] for t in 1:T-1]
+end
 
 # ---------------------------------------------------------------- device-resident KKT consumer (dto_kkt_*)
 # What examples/pendulum/pendulum.jl:138-211 does with the callback outputs (assemble

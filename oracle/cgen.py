@@ -58,6 +58,13 @@ def _c(e: sp.Expr, names: Dict[sp.Symbol, str]) -> str:
                 return f"(1.0/{bs})"
             return f"powi({bs}, {k})"
         return f"pow({_c(b, names)}, {_c(p, names)})"
+    if isinstance(e, sp.Piecewise):  # ifelse(c, a, b)
+        out = "0.0"
+        for val, cond in reversed(e.args):
+            out = _c(val, names) if cond is sp.true else f"(({_c(cond, names)}) ? {_c(val, names)} : {out})"
+        return out
+    if e.is_Relational:
+        return f"({_c(e.lhs, names)} {e.rel_op} {_c(e.rhs, names)})"
     if e.is_Function:
         return _CF[e.func.__name__] + "(" + ", ".join(_c(a, names) for a in e.args) + ")"
     raise NotImplementedError(type(e))

@@ -140,9 +140,18 @@ def hessian_indices_objective(objective, key, num_state, num_action):
 class Dynamics:
     """src/dynamics.jl:1-57. Variables ordered [x; u; y]; closures take (out, y, x, u, w[, λ])."""
 
-    def __init__(self, f: Callable, num_next_state: int, num_state: int, num_action: int,
-                 num_parameter: int = 0, evaluate_hessian: bool = False,
+    def __init__(self, f: Callable, *rest, num_parameter: int = 0, evaluate_hessian: bool = False,
                  jacobian: Optional[Callable] = None):
+        if rest and callable(rest[0]):
+            # Dynamics(f, jacobian, ny, nx, nu) (src/dynamics.jl:59): value-returning python functions are
+            # wrapped into the in-place closures the reference's second constructor stores
+            user_f, user_j, rest = f, rest[0], rest[1:]
+
+            def f(out, y, x, u, w, _f=user_f):  # noqa: F811
+                out[:] = np.asarray(_f(y, x, u, w), dtype=float)
+
+            jacobian = user_j
+        num_next_state, num_state, num_action = rest
         self.num_next_state, self.num_state, self.num_action = num_next_state, num_state, num_action
         self.num_parameter = num_parameter
         if jacobian is not None:

@@ -209,6 +209,16 @@ def _propagate(e: sp.Expr, index: Dict[sp.Symbol, int], memo: dict):
             a = base if base is not None else TermCombination.one()
             b = expo if expo is not None else TermCombination.one()
             r = _combine_terms_2(_LINEARITY_2["default"], a, b)
+    elif isinstance(e, sp.Piecewise):
+        # IfElse.ifelse(c, a, b) (imported at /root/reference/src/DirectTrajectoryOptimization.jl:5, used by no
+        # reference model): RECOLLECTION of the Symbolics rule `ifelse(c, x, y) => x + y` -- the branches
+        # combine linearly, the condition contributes nothing. Unverifiable here.
+        acc = TermCombination.one()
+        for (val, _cond) in e.args:
+            c = _propagate(val, index, memo)
+            if c is not None:
+                acc = acc + c
+        r = acc
     elif isinstance(e, sp.Function) or e.is_Function:
         args = [_propagate(a, index, memo) for a in e.args]
         if len(args) == 1:
@@ -300,6 +310,13 @@ def _pystr(e: sp.Expr, names: Dict[sp.Symbol, str]) -> str:
                 return f"(1.0/({bs}**{-k}))"
             return f"({bs}**{k})"
         return f"({_pystr(b, names)}**{_pystr(p, names)})"
+    if isinstance(e, sp.Piecewise):
+        out = "0.0"
+        for val, cond in reversed(e.args):
+            out = _pystr(val, names) if cond is sp.true else f"({_pystr(val, names)} if {_pystr(cond, names)} else {out})"
+        return out
+    if e.is_Relational:
+        return f"({_pystr(e.lhs, names)} {e.rel_op} {_pystr(e.rhs, names)})"
     if e.is_Function:
         fn = _FUNCS.get(e.func.__name__)
         if fn is None:

@@ -28,6 +28,8 @@ GOLDEN = [
     ("car", dict(T=7, obstacle="stage"), 2, 4),
     ("acrobot_hessian_test", dict(), 5, 6),
     ("linear_general", dict(T=6), 2, 7),
+    ("piecewise", dict(T=9), 6, 8),
+    ("user_jacobian", dict(T=5, nonlinear=True), 3, 9),
 ]
 
 
@@ -42,7 +44,7 @@ def main():
         nlp = solver.nlp
         nw = 8 if model.get("shared_parameters") else 0
         z, lam, sigma, w = make_inputs(name, model, nlp.num_variables, nlp.num_constraint, nw, B, config)
-        out = oracle_eval_all(solver, model, z, lam, sigma, w)
+        out = oracle_eval_all(solver, model, z, lam, sigma, w, hessian=bool(model["evaluate_hessian"]))
         js = np.array(nlp.jacobian_structure(), dtype=np.int64).reshape(-1, 2)
         hs = np.array(nlp.hessian_lagrangian_structure(), dtype=np.int64).reshape(-1, 2)
         lo, hi = nlp.constraint_bounds

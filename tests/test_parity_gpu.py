@@ -21,6 +21,7 @@ CASES = [
     ("car", dict(T=51, obstacle="stage"), 3, 4),
     ("acrobot_hessian_test", dict(), 40, 6),
     ("linear_general", dict(), 3, 7),
+    ("piecewise", dict(), 64, 8),
 ]
 
 
@@ -58,6 +59,36 @@ def test_callbacks_match_oracle(name, kw, B, config):
     assert np.array_equal(J2, J) or np.allclose(J2, J, rtol=1e-13, atol=1e-15)
     assert_close("fused jacobian", J2, ref["J"])
     assert_close("fused hessian", H2, ref["H"])
+    pn.close()
+
+
+@pytest.mark.parametrize("nonlinear", [False, True])
+def test_user_jacobian_dynamics_matches_oracle(nonlinear):
+    """Second Dynamics constructor (/root/reference/src/dynamics.jl:59-101, test/solve.jl:140-225): the USER's
+    Jacobian expressions are what gets evaluated (dense column-major slots, no Hessian). With nonlinear=True the
+    supplied Jacobian is deliberately not the derivative of f, so "differentiated f instead" would fail here."""
+    kw = dict(nonlinear=nonlinear)
+    mo, mp = M.build_user_jacobian(O, **kw), M.build_user_jacobian(D, **kw)
+    B = 33
+    osolver, psolver = O.solver_from(mo), D.solver_from(mp, batch=B)
+    on, pn = osolver.nlp, psolver.nlp
+    assert pn.jacobian_structure() == on.jacobian_structure() and pn.num_jacobian == 100
+    assert pn.features_available() == ["Grad", "Jac"]  # src/moi.jl:122 without :Hess
+    z, lam, sigma, w = make_inputs("user_jacobian", mp, pn.num_variables, pn.num_constraint, 0, B, 9)
+    ref = oracle_eval_all(osolver, mo, z, lam, sigma, w, hessian=False)
+    g = np.full((B, pn.num_variables), np.nan)
+    c = np.full((B, pn.num_constraint), np.nan)
+    J = np.full((B, pn.num_jacobian), np.nan)
+    assert_close("objective", pn.eval_objective(z), ref["f"])
+    pn.eval_objective_gradient(g, z)
+    pn.eval_constraint(c, z)
+    pn.eval_constraint_jacobian(J, z)
+    assert_close("gradient", g, ref["g"])
+    assert_close("constraint", c, ref["c"])
+    assert_close("jacobian", J, ref["J"])
+    if nonlinear:  # the scaled entry really is the user's, not d f / d x
+        exact = -0.1 * np.cos(z[:, 0]) * z[:, 2]
+        assert np.allclose(J[:, 1], 3.0 * exact, rtol=1e-12) and not np.allclose(J[:, 1], exact, rtol=1e-3)
     pn.close()
 
 

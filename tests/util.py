@@ -29,6 +29,9 @@ def make_inputs(name: str, model: dict, nz: int, nc: int, nw: int, B: int, confi
     elif name == "car":
         X = np.concatenate([r.uniform(0, 1, (B, T, 2)), r.uniform(-math.pi, math.pi, (B, T, 1))], axis=2)
         U = r.uniform(-0.5, 0.5, (B, T, m))
+    elif name == "piecewise":  # both branches of every ifelse get exercised
+        X = r.uniform(-1.5, 1.5, (B, T, n))
+        U = r.uniform(-1.5, 1.5, (B, T, m))
     else:
         X = r.uniform(0, 1, (B, T, n))
         U = r.uniform(0, 1, (B, T, m))
