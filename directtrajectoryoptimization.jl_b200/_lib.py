@@ -119,6 +119,8 @@ def lib() -> C.CDLL:
         "dto_kkt_matrix": (C.c_int, [vp, i64, vp]),
         "dto_kkt_factor": (C.c_int, [vp, i64, vp, vp]),
         "dto_kkt_device_pointer": (vp, [vp, C.c_int, C.c_int]),
+        "dto_kkt_set_primal_reg": (C.c_int, [vp, vp]),
+        "dto_kkt_inertia": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -60,12 +60,23 @@ __device__ __forceinline__ void cp_async_wait()
 
 // band entries of row (blk*W + i): slot w holds the column c = w (mod W) of [row-W+1, row].
 // JbmH = (this problem's J) - nnz_H, so that a table entry s >= nnz_H addresses J[s - nnz_H].
+__device__ __forceinline__ double row_shift(const dto_kkt_args& a, size_t row, int64_t b)
+{
+    // diagonal shift of permuted row `row`: +primal_reg (per problem when a.preg is given), -dual_reg, 1.0 on padding
+    double reg = a.dreg[row];
+    if (a.preg != nullptr) {
+        const int32_t ip = a.iperm[row];
+        if (ip >= 0 && ip < a.N_z) reg = a.preg[b];
+    }
+    return reg;
+}
+
 template <int W>
 __device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* __restrict__ Hb, const double* __restrict__ JbmH,
-                                          int blk, int i, double (&X)[W])
+                                          int blk, int i, double (&X)[W], int64_t b = 0)
 {
     const int32_t* src = a.src + ((size_t)blk * W) * W + i;
-    const double reg = a.dreg[(size_t)blk * W + i];
+    const double reg = row_shift(a, (size_t)blk * W + i, b);
     int32_t sidx[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) sidx[w] = src[w * W];
@@ -345,7 +356,8 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     double rr;
     double rn1 = 0.0, regn1 = 1.0, rn2 = 0.0, regn2 = 1.0;   // rhs / diagonal shift of this lane's rows in blocks blk+1, blk+2
     int32_t nidx[W];
-    load_rows<W>(a, Hb, Jb, 0, i, R);
+    load_rows<W>(a, Hb, Jb, 0, i, R, b);
+    int neg = 0;   // negative pivots seen so far (every lane of the group sees every pivot)
     {
         const int32_t ip = a.iperm[i];
         rr = ip >= 0 ? hb[ip] : 0.0;
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
             }
             const int32_t ip = a.iperm[(size_t)blk * W + i];
             rn = ip >= 0 ? hb[ip] : 0.0;
-            regn = a.dreg[(size_t)blk * W + i];
+            regn = row_shift(a, (size_t)blk * W + i, b);
         }
         cp_async_commit();
     };
@@ -394,6 +406,7 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
             vs[(i - s - 1) & (W - 1)] = v;                       // lane s (v = 0) lands on the free slot W-1 ...
             if (i == s) vs[W - 1] = rr;                          // ... which carries y_j instead
             const double d = shfl_g<G>(R[p], s);
+            neg += d < 0.0 ? 1 : 0;
             const double dinv = 1.0 / d;
             const double l = v * dinv;
             const int qi = (i - s) & (W - 1);                   // row - j
@@ -436,6 +449,7 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     cp_async_wait<0>();
     __syncwarp();
     __threadfence_block();
+    if (a.nneg != nullptr && valid && i == 0) a.nneg[b] = neg;
     kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
 }
 
@@ -447,7 +461,7 @@ __global__ void kkt_assemble_kernel(const dto_kkt_args a, int64_t problem, doubl
     const double* Hb = a.H + problem * a.nnz_H;
     const double* Jb = a.J + problem * a.nnz_J - a.nnz_H;
     double X[W];
-    load_rows<W>(a, Hb, Jb, blk, i, X);
+    load_rows<W>(a, Hb, Jb, blk, i, X, problem);
 #pragma unroll
     for (int w = 0; w < W; ++w) out[((size_t)blk * W + w) * W + i] = X[w];
 }

@@ -38,6 +38,10 @@ typedef struct dto_kkt_args {
     double* L;           /* [B][factor_stride]: per problem [nblk*W][LW] columns of L (slot 0 = pivot d_j,
                             slot q = L(j+q, j)) followed by [nblk*W] D^-1 L^-1 h                 */
     double* sol;         /* [B][dim] K^-1 h, natural order                                     */
+    /* per-problem primal regularisation (inertia control of a solver driving the batch): when non-NULL the
+     * diagonal shift of the VARIABLE rows of problem b is preg[b] instead of the scalar primal_reg          */
+    const double* preg;  /* [B] or NULL                                                        */
+    int32_t* nneg;       /* [B] or NULL: number of negative pivots of D (inertia; N_c when K is quasi-definite) */
 } dto_kkt_args;
 
 /* The factor kernel is instantiated for a few bounds BW on the half bandwidth; a column of L is stored

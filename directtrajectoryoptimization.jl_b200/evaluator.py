@@ -285,6 +285,20 @@ class BatchedNLPData:
     def launch_count(self) -> int:
         return int(_lib.lib().dto_launch_count(self.handle))
 
+    @property
+    def num_shards(self) -> int:
+        return int(_lib.lib().dto_batch_num_shards(self.handle))
+
+    def shard_device(self, shard: int = 0) -> int:
+        return int(_lib.lib().dto_shard_device(self.handle, shard))
+
+    def shard_range(self, shard: int = 0):
+        L = _lib.lib()
+        return int(L.dto_shard_begin(self.handle, shard)), int(L.dto_shard_size(self.handle, shard))
+
+    def stream_pointer(self, shard: int = 0) -> int:
+        return int(_lib.lib().dto_get_stream(self.handle, shard) or 0)
+
     def device_pointer(self, array: int, shard: int = 0) -> int:
         p = _lib.lib().dto_device_pointer(self.handle, array, shard)
         if not p:
@@ -392,12 +406,41 @@ class Solver:
         actions = [z[us[t] - 1: us[t] - 1 + nu[t]].copy() for t in range(self.nlp.T - 1)]
         return states, actions
 
-    def solve(self, options: Optional[dict] = None, record_iterates: bool = False):
-        """solve!(solver) (src/solver.jl:45-47) for every problem of the batch: B per-problem NLP solvers
-        run in lock step and their callbacks rendezvous into batched GPU calls (driver.py).
-        The reference's caller is Ipopt, which is not available in this image; the per-problem solver is
-        SciPy's `trust-constr` (same five callbacks, same sparsity structures, same bounds). Returns the
-        per-problem solver results; `get_trajectory(problem)` then returns the final iterate."""
+    def solve(self, options: Optional[dict] = None, record_iterates: bool = False, method: str = "auto"):
+        """solve!(solver) (src/solver.jl:45-47) for every problem of the batch. The reference's caller is
+        Ipopt, which is not available in this image. Two drivers stand in for it:
+          * "sqp" (default where it applies: exact Hessians, equality constraints, free variables): the
+            lock-step batched Newton-KKT solver of sqp.py -- callbacks, KKT assembly, factorisation and
+            line-search evaluations all on the device, no per-problem host solver (BASELINE config 3);
+          * "broker": B per-problem host NLP solvers (SciPy trust-constr) running in lock step whose
+            callbacks rendezvous into batched GPU calls (driver.py): the protocol an Ipopt-
+            per-task driver would use.
+        `get_trajectory(problem)` afterwards returns the final iterate."""
+        if method == "auto":
+            lo, up = self.nlp.variable_bounds
+            clo, cup = self.nlp.constraint_bounds
+            ok = (self.nlp.hessian_lagrangian and not np.any(np.isfinite(lo) | np.isfinite(up)) and np.array_equal(clo, cup)
+                  and self.nlp.num_shards == 1)
+            method = "sqp" if ok else "broker"
+        if method == "sqp":
+            from . import sqp
+            o = sqp.SQPOptions()
+            ref_opts = self.options if isinstance(self.options, dict) else {}
+            if "max_iter" in ref_opts:
+                o.max_iter = int(ref_opts["max_iter"])       # Options.max_iter (src/options.jl:9)
+            for k_, v in (options or {}).items():
+                setattr(o, k_, v)
+            be = sqp.DeviceBackend(self.nlp, dual_reg=o.dual_reg)
+            try:
+                z0 = be.torch.as_tensor(self._initial, device=be.xp.device)
+                res = sqp.solve(be, z0, options=o, record=record_iterates)
+                Z = res.z.cpu().numpy()
+                self.sqp_launches = self.nlp.launch_count() - be.launches0
+            finally:
+                be.close()
+            self.nlp.set_x(Z)
+            self.results, self.iterates, self.broker = res, res.history, None
+            return res
         from .driver import solve_batch
         opts = dict(options or {})
         ref_opts = self.options if isinstance(self.options, dict) else {}

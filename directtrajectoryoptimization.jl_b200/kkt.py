@@ -78,8 +78,25 @@ class KKTSystem:
         _lib.check(_lib.lib().dto_kkt_solve(self._h, _p(solution) if solution is not None else None))
         return solution
 
-    def launch(self, with_callbacks: bool = True) -> None:
-        _lib.check(_lib.lib().dto_kkt_launch(self._h, int(bool(with_callbacks))))
+    def launch(self, with_callbacks=True) -> None:
+        """with_callbacks: True/1 callbacks + right-hand side + factor/solve; False/0 linear algebra only on the
+        g, c, J, H resident on the device; 2 callbacks only."""
+        _lib.check(_lib.lib().dto_kkt_launch(self._h, int(with_callbacks)))
+
+    def set_primal_reg(self, reg=None) -> None:
+        """Per-problem primal regularisation [B] (inertia control); None: back to the scalar of the constructor."""
+        if reg is None:
+            _lib.check(_lib.lib().dto_kkt_set_primal_reg(self._h, None))
+            return
+        from .evaluator import _f64
+        r = _f64(reg, (self.nlp.batch,), "reg")
+        _lib.check(_lib.lib().dto_kkt_set_primal_reg(self._h, _p(r)))
+
+    def inertia(self) -> np.ndarray:
+        """Negative pivots of D per problem for the last factorisation (== num_constraint when K is quasi-definite)."""
+        out = np.empty(self.nlp.batch, dtype=np.int32)
+        _lib.check(_lib.lib().dto_kkt_inertia(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def rhs(self) -> np.ndarray:
         out = np.empty((self.nlp.batch, self.dim))

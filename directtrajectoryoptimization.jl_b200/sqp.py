@@ -1,0 +1,361 @@
+"""Lock-step batched Newton-KKT (SQP) solver on top of the device-resident callbacks and KKT kernels.
+
+Reference anchor: `solve!(solver)` (/root/reference/src/solver.jl:45-47) hands the five MOI callbacks to
+Ipopt (src/data.jl:222-255). Ipopt (libipopt) is not in this image, and a CPU solver per problem fed through
+PCIe is exactly the bottleneck the KKT consumer of SURVEY 8(f) N3 removes -- so BASELINE config 3 ("acrobot
+T=101, batch 4096, full solves with device-resident callbacks") runs on this solver instead: every problem of
+the batch advances through the same iteration at the same time, all arrays stay in HBM, and every linear
+algebra / callback step is one of this package's CUDA kernels:
+
+    callbacks at (z, lambda, sigma = 1)            dto_kkt_launch(with_callbacks = 1): gradient, constraint,
+                                                   fused Jacobian + Hessian-of-Lagrangian kernels
+    K = [[H + delta_b I, J'], [J, -delta_c I]]     kkt_band_kernel: per-problem delta_b (inertia control), banded
+    K [dz; dlam] = -[g + J'lam; c]                 LDL' without pivoting, negative pivots counted per problem
+    trial points z + alpha dz                      objective_kernel + knot_kernel<C> (batched f, c)
+
+What is left to the host language are O(B N) vector updates and per-problem scalars (step acceptance,
+regularisation, convergence masks); they are written against an array namespace `xp` -- torch on the device
+for the product, numpy for the oracle-driven twin the parity test runs (tests/sqp_oracle.py) -- so both arms
+execute literally the same algorithm.
+
+Scope (stated plainly): equality-constrained problems with free variables (end points pinned by stage
+constraints as in examples/acrobot, examples/cartpole, examples/pendulum -- not by bounds, and no inequality
+rows). It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
+damping and Ipopt-style inertia correction of the primal regularisation; it is NOT Ipopt:
+iterate-for-iterate parity with the reference's Ipopt runs is unverifiable here and is not claimed.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+
+@dataclass
+class SQPOptions:
+    max_iter: int = 200
+    tol_constraint: float = 1.0e-8     # ||c||_inf
+    tol_dual: float = 1.0e-6           # ||g + J' lambda||_inf
+    dual_reg: float = 1.0e-9           # delta_c: keeps K quasi-definite when J loses rank
+    reg_first: float = 1.0e-4          # Ipopt's delta_w^0
+    reg_min: float = 1.0e-20
+    reg_max: float = 1.0e10
+    reg_inc_first: float = 100.0       # kappa_w^+ bar
+    reg_inc: float = 8.0               # kappa_w^+
+    reg_dec: float = 1.0 / 3.0         # kappa_w^-
+    max_refactor: int = 14
+    armijo: float = 1.0e-4
+    max_backtrack: int = 25
+    merit_margin: float = 1.1
+    merit_rho: float = 0.3
+    soc: bool = True
+    merit_memory: bool = False
+    merit_min: float = 1.0
+    lm_first: float = 1.0e-2           # Levenberg-Marquardt damping added to H: first value, growth when the search
+    lm_min: float = 1.0e-4             #   accepted less than lm_grow_below of the step, decay after full steps
+    lm_grow: float = 4.0
+    lm_shrink: float = 0.25
+    lm_grow_below: float = 0.3
+    lm_zero: float = 1.0e-10
+    exact_below: float = 1.0           # ||c||_inf under which the exact Hessian of the Lagrangian is used
+
+
+class SQPResult:
+    def __init__(self, z, lam, iterations, converged, constraint_violation, dual_residual, objective, history):
+        self.z, self.lam = z, lam
+        self.iterations = iterations            # per problem: iterations until it converged (or max_iter)
+        self.converged = converged
+        self.constraint_violation = constraint_violation
+        self.dual_residual = dual_residual
+        self.objective = objective
+        self.history = history                  # list of per-iteration dicts (only with record=True)
+
+
+def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool = False) -> SQPResult:
+    """`be` is a backend (see DeviceBackend below / tests/sqp_oracle.py):
+         be.xp                       array namespace (torch or numpy flavoured shim, see `_XP`)
+         be.B, be.N_z, be.N_c
+         be.free                     [N_z] 0/1 mask: 0 = variable pinned by equal bounds (its step is zero)
+         be.callbacks(z, lam, lamH, delta) -> f [B], g [B,N_z], c [B,N_c]  (leaves J, H(z, lamH) and a first solve with delta ready for `newton`)
+         be.newton(delta)            -> sol [B, N_z+N_c] = K^-1 [g + J'lam; c], nneg [B] negative pivots,
+                                        rz [B,N_z] = g + J'lam   with per-problem primal regularisation delta [B]
+         be.objective_constraint(z)  -> f [B], c [B,N_c]
+    All arrays are [B, ...] and stay wherever `xp` keeps them."""
+    o = options or SQPOptions()
+    xp = be.xp
+    B, N_z, N_c = be.B, be.N_z, be.N_c
+    z = xp.copy(z0)
+    lam = xp.zeros((B, N_c)) if lam0 is None else xp.copy(lam0)
+    free = be.free
+    delta_last = xp.zeros((B,))
+    nu = xp.ones((B,))
+    done = xp.zeros_bool((B,))
+    iters = xp.zeros((B,))
+    history = []
+    f = cv = dr = None
+    exact = xp.zeros((B,))
+    lm = xp.full((B,), o.lm_first)
+    for it in range(o.max_iter):
+        # Hessian of the Lagrangian with the multipliers of the problems that are close to feasible; the others
+        # use the objective's Hessian only (Gauss-Newton): far from the constraint manifold the multiplier
+        # estimates of a swing-up are huge and their curvature term makes H wildly indefinite
+        # ---- Newton-KKT step: Levenberg-Marquardt damping lm (grows when the line search had to cut the step,
+        # shrinks after full steps) + inertia control on top of it (Ipopt's IC algorithm, per problem)
+        delta = xp.copy(lm)
+        f, g, c = be.callbacks(z, lam, lam * exact[:, None], delta)
+        sol, nneg, rz = be.newton(delta)
+        cv = xp.max_abs_rows(c)
+        dr = xp.max_abs_rows(rz * free)
+        exact = xp.where(cv <= o.exact_below, xp.ones((B,)), xp.zeros((B,)))
+        newly = (~done) & (cv <= o.tol_constraint) & (dr <= o.tol_dual)
+        iters = xp.where(newly, xp.full((B,), float(it)), iters)
+        done = done | newly
+        if record:
+            history.append(dict(it=it, z=xp.to_numpy(z), lam=xp.to_numpy(lam), f=xp.to_numpy(f), cv=xp.to_numpy(cv),
+                                dr=xp.to_numpy(dr), done=xp.to_numpy(done)))
+        if xp.all(done):
+            break
+        bad = ((nneg != N_c) | ~xp.finite_rows(sol)) & ~done
+        tries = 0
+        first = xp.ones_bool((B,))
+        while xp.any(bad) and tries < o.max_refactor:
+            start = xp.where(delta_last == 0.0, xp.full((B,), o.reg_first), xp.maximum(xp.full((B,), o.reg_min), o.reg_dec * delta_last))
+            grow = xp.where(delta_last == 0.0, xp.full((B,), o.reg_inc_first), xp.full((B,), o.reg_inc))
+            nxt = xp.where(first, xp.maximum(start, 2.0 * delta), xp.minimum(xp.full((B,), o.reg_max), grow * delta))
+            delta = xp.where(bad, nxt, delta)
+            first = first & ~bad
+            sol2, nneg2, _ = be.newton(delta)
+            sol = xp.where_rows(bad, sol2, sol)
+            nneg = xp.where(bad, nneg2, nneg)
+            bad = ((nneg != N_c) | ~xp.finite_rows(sol)) & ~done
+            tries += 1
+        delta_last = xp.where(delta > lm, delta, delta_last)
+        dz = -sol[:, :N_z] * free
+        dlam = -sol[:, N_z:]
+        # ---- l1 merit line search: phi = f + nu ||c||_1. Penalty by the curvature rule (Nocedal & Wright 18.36):
+        # nu >= (g'dz + max(dz'(H + delta I)dz, 0)/2) / ((1 - rho) ||c||_1), where the KKT system gives
+        # dz'(H + delta I)dz = -g'dz + c'(lambda + dlam) without a product with H. (nu >= ||lambda+||_inf would
+        # also give descent, but the multipliers of a swing-up far from the solution are huge and such a nu
+        # makes the search follow the curved constraint manifold in tiny steps.)
+        c1 = xp.sum_abs_rows(c)
+        gd = xp.sum_rows(g * dz)
+        curv = xp.maximum(-gd + xp.sum_rows(c * (lam + dlam)), xp.zeros((B,)))
+        nu_need = (gd + 0.5 * curv) / ((1.0 - o.merit_rho) * xp.maximum(c1, xp.full((B,), 1.0e-300)))
+        if o.merit_memory:
+            nu = xp.where((c1 > 0.0) & (nu < nu_need), o.merit_margin * nu_need, nu)
+        else:  # the penalty of THIS step only: large multipliers of early iterations do not throttle later ones
+            nu = xp.maximum(xp.full((B,), o.merit_min), o.merit_margin * nu_need)
+        slope = gd - nu * c1
+        phi0 = f + nu * c1
+        alpha = xp.ones((B,))
+        soc_used = xp.zeros_bool((B,))
+        accepted = xp.copy_bool(done) | bad     # converged problems and failed factorisations do not move
+        for ls in range(o.max_backtrack):
+            zt = z + alpha[:, None] * dz
+            ft, ct = be.objective_constraint(zt)
+            phit = ft + nu * xp.sum_abs_rows(ct)
+            ok = (phit <= phi0 + o.armijo * alpha * slope) & ~accepted
+            z = xp.where_rows(ok, zt, z)
+            lam = xp.where_rows(ok, lam + alpha[:, None] * dlam, lam)
+            accepted = accepted | ok
+            if xp.all(accepted):
+                break
+            if ls == 0 and o.soc:
+                # second-order correction (Maratos effect: near the constraint manifold a long tangential step is
+                # rejected because c grows quadratically along it): re-solve the same K with the constraint
+                # right-hand side c(z) + c(z + dz) and try that step once before backtracking
+                need = ~accepted & (xp.sum_abs_rows(ct) >= c1)
+                if xp.any(need):
+                    sol_s = be.newton_soc(c + ct, delta)
+                    dzs = -sol_s[:, :N_z] * free
+                    zs = z + dzs
+                    fs, cs = be.objective_constraint(zs)
+                    oks = (fs + nu * xp.sum_abs_rows(cs) <= phi0 + o.armijo * slope) & need & xp.finite_rows(sol_s)
+                    z = xp.where_rows(oks, zs, z)
+                    lam = xp.where_rows(oks, lam - sol_s[:, N_z:], lam)
+                    accepted = accepted | oks
+                    soc_used = soc_used | oks
+                    if xp.all(accepted):
+                        break
+            alpha = xp.where(accepted, alpha, 0.5 * alpha)
+        # a problem whose search failed keeps its point; more regularisation next time shortens the step
+        stuck = ~accepted
+        moved = ~done & ~bad
+        lm = xp.where(moved & (alpha < o.lm_grow_below), xp.maximum(xp.full((B,), o.lm_min), o.lm_grow * xp.maximum(lm, delta)), lm)
+        lm = xp.where(moved & accepted & (alpha >= 1.0), o.lm_shrink * lm, lm)
+        lm = xp.where(lm < o.lm_zero, xp.zeros((B,)), lm)
+        if record:
+            history[-1].update(alpha=xp.to_numpy(alpha), delta=xp.to_numpy(delta), nu=xp.to_numpy(nu), stuck=xp.to_numpy(stuck),
+                               slope=xp.to_numpy(slope), soc=xp.to_numpy(soc_used))
+        delta_last = xp.where(stuck | bad, xp.maximum(xp.full((B,), o.reg_first), o.reg_inc * xp.maximum(delta_last, delta)), delta_last)
+    iters = xp.where(done, iters, xp.full((B,), float(o.max_iter)))
+    return SQPResult(z, lam, iters, done, cv, dr, f, history)
+
+
+# --------------------------------------------------------------------------------------- array namespaces
+class _XP:
+    """The handful of batched array operations the algorithm uses, for torch (device) and numpy."""
+
+    def __init__(self, mod, device=None):
+        self.m = mod
+        self.device = device
+        self.is_torch = mod.__name__ == "torch"
+
+    def _kw(self):
+        return dict(dtype=self.m.float64, device=self.device) if self.is_torch else dict(dtype=self.m.float64)
+
+    def zeros(self, shape):
+        return self.m.zeros(shape, **self._kw())
+
+    def ones(self, shape):
+        return self.m.ones(shape, **self._kw())
+
+    def full(self, shape, v):
+        return self.m.full(shape, float(v), **self._kw())
+
+    def zeros_bool(self, shape):
+        return self.m.zeros(shape, dtype=self.m.bool, device=self.device) if self.is_torch else self.m.zeros(shape, dtype=bool)
+
+    def ones_bool(self, shape):
+        return ~self.zeros_bool(shape)
+
+    def copy(self, a):
+        return a.clone() if self.is_torch else a.copy()
+
+    copy_bool = copy
+
+    def where(self, c, a, b):
+        return self.m.where(c, a, b)
+
+    def where_rows(self, c, a, b):
+        return self.m.where(c[:, None], a, b)
+
+    def maximum(self, a, b):
+        return self.m.maximum(a, b)
+
+    def minimum(self, a, b):
+        return self.m.minimum(a, b)
+
+    def max_abs_rows(self, a):
+        if a.shape[1] == 0:
+            return self.zeros((a.shape[0],))
+        return a.abs().amax(dim=1) if self.is_torch else self.m.abs(a).max(axis=1)
+
+    def sum_abs_rows(self, a):
+        return a.abs().sum(dim=1) if self.is_torch else self.m.abs(a).sum(axis=1)
+
+    def sum_rows(self, a):
+        return a.sum(dim=1) if self.is_torch else a.sum(axis=1)
+
+    def finite_rows(self, a):
+        return self.m.isfinite(a).all(dim=1) if self.is_torch else self.m.isfinite(a).all(axis=1)
+
+    def all(self, a):
+        return bool(a.all())
+
+    def any(self, a):
+        return bool(a.any())
+
+    def to_numpy(self, a):
+        return a.detach().cpu().numpy().copy() if self.is_torch else self.m.array(a, copy=True)
+
+
+# --------------------------------------------------------------------------------------- device backend
+class _CudaArray:
+    """zero-copy view of a device buffer of libdto.so for torch (CUDA array interface)"""
+
+    def __init__(self, ptr: int, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class DeviceBackend:
+    """The product arm: callbacks and KKT solves are this package's CUDA kernels on the batch's device arrays;
+    torch provides the views of those arrays and the O(B N) vector glue. One shard (one device) per backend:
+    multi-GPU runs use one backend per rank / per shard, problems are independent."""
+
+    def __init__(self, nlp, dual_reg: float = 1.0e-9):
+        import torch
+
+        from . import _lib
+        from .evaluator import A_C, A_F, A_G, A_LAMBDA, A_SIGMA, A_Z, K_CONSTRAINT, K_OBJECTIVE
+        from .kkt import KKTSystem
+        if nlp.num_shards != 1:
+            raise ValueError("DeviceBackend drives one shard; create one batch per device")
+        self.nlp = nlp
+        self.torch = torch
+        dev = torch.device("cuda", nlp.shard_device(0))
+        self.xp = _XP(torch, dev)
+        self.B, self.N_z, self.N_c = nlp.batch, nlp.num_variables, nlp.num_constraint
+        lo, up = nlp.variable_bounds
+        import numpy as np
+        clo, cup = nlp.constraint_bounds
+        if np.any(clo != cup):
+            raise NotImplementedError("sqp: inequality constraints are outside this solver's scope")
+        if np.any(np.isfinite(lo) | np.isfinite(up)):
+            raise NotImplementedError("sqp: bounds on variables are outside this solver's scope (pin end points with stage constraints)")
+        self.free = torch.ones(self.N_z, dtype=torch.float64, device=dev)
+        self.kkt = KKTSystem(nlp, 0.0, dual_reg)
+        self._K = (K_OBJECTIVE, K_CONSTRAINT)
+        view = lambda arr, shape: torch.as_tensor(_CudaArray(nlp.device_pointer(arr, 0), shape), device=dev)  # noqa: E731
+        B = self.B
+        self.d_z = view(A_Z, (B, self.N_z))
+        self.d_lam = view(A_LAMBDA, (B, self.N_c))
+        self.d_sigma = view(A_SIGMA, (B,))
+        self.d_f = view(A_F, (B,))
+        self.d_g = view(A_G, (B, self.N_z))
+        self.d_c = view(A_C, (B, self.N_c))
+        kview = lambda which, shape, ts="<f8": torch.as_tensor(_CudaArray(self.kkt.device_pointer(which, 0), shape, ts), device=dev)  # noqa: E731
+        self.d_rhs = kview(0, (B, self.kkt.dim))
+        self.d_sol = kview(1, (B, self.kkt.dim))
+        self.d_reg = kview(3, (B,))
+        self.d_nneg = kview(4, (B,), "<i4")
+        self.d_sigma.fill_(1.0)
+        self.stream = torch.cuda.ExternalStream(nlp.stream_pointer(0), device=dev)
+        self.launches0 = nlp.launch_count()
+
+    def close(self):
+        self.kkt.close()
+
+    def callbacks(self, z, lam, lam_hess, delta):
+        """f, g, c at z; J and H(z, lam_hess) stay on the device; first KKT solve with the damping `delta` and the
+        right-hand side of the TRUE multipliers `lam` (the Hessian may use others: Gauss-Newton for far-away problems)"""
+        t = self.torch
+        with t.cuda.stream(self.stream):
+            self.d_z.copy_(z)
+            self.d_lam.copy_(lam_hess)
+            self.d_reg.copy_(delta)
+            self.nlp.launch(self._K[0])                 # f
+            self.kkt.launch(2)                          # g, c, J, H(z, lam_hess)
+            self.d_lam.copy_(lam)
+            self.kkt.launch(0)                          # h = [g + J'lam; c], K = L D L', sol
+            self._fresh = True
+            return self.d_f.clone(), self.d_g.clone(), self.d_c.clone()
+
+    def _solution(self):
+        t = self.torch
+        return self.d_sol.clone(), self.d_nneg.to(t.float64), self.d_rhs[:, :self.N_z].clone()
+
+    def newton(self, delta):
+        with self.torch.cuda.stream(self.stream):
+            if not self._fresh:                         # re-factor with the new per-problem regularisation
+                self.d_reg.copy_(delta)
+                self.kkt.launch(0)
+            self._fresh = False
+            return self._solution()
+
+    def newton_soc(self, c_soc, delta):
+        """second-order correction: same K, constraint right-hand side c_soc (the device c is overwritten: the
+        iteration's own copy lives in the solver)"""
+        with self.torch.cuda.stream(self.stream):
+            self.d_c.copy_(c_soc)
+            self.d_reg.copy_(delta)
+            self.kkt.launch(0)
+            self._fresh = False
+            return self.d_sol.clone()
+
+    def objective_constraint(self, z):
+        t = self.torch
+        with t.cuda.stream(self.stream):
+            self.d_z.copy_(z)
+            self.nlp.launch(self._K[0])
+            self.nlp.launch(self._K[1])
+            return self.d_f.clone(), self.d_c.clone()

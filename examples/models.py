@@ -91,9 +91,12 @@ def build_pendulum(api, T=11, evaluate_hessian=True):
     oT = lambda x, u, w: 0.1 * dot(x[0:2], x[0:2])
     ct = api.Cost(ot, n, m, num_parameter=0, evaluate_hessian=evaluate_hessian)
     cT = api.Cost(oT, n, 0, num_parameter=0, evaluate_hessian=evaluate_hessian)
-    con1 = api.Constraint(lambda x, u, w: x - x1, n, m, evaluate_hessian=evaluate_hessian)
-    conT = api.Constraint(lambda x, u, w: x - xT, n, m, evaluate_hessian=evaluate_hessian)
+    c1 = lambda x, u, w: x - x1
+    cT_ = lambda x, u, w: x - xT
+    con1 = api.Constraint(c1, n, m, evaluate_hessian=evaluate_hessian)
+    conT = api.Constraint(cT_, n, m, evaluate_hessian=evaluate_hessian)
     return dict(
+        fns=dict(dyn=pendulum_midpoint, cost=[ot] * (T - 1) + [oT], con=[c1] + [None] * (T - 2) + [cT_], general=None),
         name="pendulum", T=T, n=n, m=m,
         dynamics=[dt] * (T - 1),
         objective=[ct] * (T - 1) + [cT],
@@ -161,6 +164,7 @@ def build_cartpole(api, T=101, evaluate_hessian=True, parameterized=True):
     con1 = api.Constraint(c1, n, m, num_parameter=nw, evaluate_hessian=evaluate_hessian)
     conT = api.Constraint(cT, n, 0, num_parameter=nw, evaluate_hessian=evaluate_hessian)
     return dict(
+        fns=dict(dyn=cartpole_rk3_implicit, cost=[ot] * (T - 1) + [oT], con=[c1] + [None] * (T - 2) + [cT], general=None),
         name="cartpole", T=T, n=n, m=m,
         dynamics=[dt] * (T - 1),
         objective=[ct] * (T - 1) + [cTc],
@@ -224,16 +228,21 @@ def build_acrobot(api, T=101, evaluate_hessian=True, stage_endpoint_constraints=
     oT = lambda x, u, w: 0.1 * dot(x[2:4], x[2:4])
     ct = api.Cost(ot, n, m, num_parameter=0, evaluate_hessian=evaluate_hessian)
     cT = api.Cost(oT, n, 0, num_parameter=0, evaluate_hessian=evaluate_hessian)
+    c1 = lambda x, u, w: x - x1
+    cT_ = lambda x, u, w: x - xT
+    con_fns = [None] * T
     if stage_endpoint_constraints:
-        cons = ([api.Constraint(lambda x, u, w: x - x1, n, m, evaluate_hessian=evaluate_hessian)]
+        con_fns = [c1] + [None] * (T - 2) + [cT_]
+        cons = ([api.Constraint(c1, n, m, evaluate_hessian=evaluate_hessian)]
                 + [api.Constraint() for _ in range(2, T)]
-                + [api.Constraint(lambda x, u, w: x - xT, n, 0, evaluate_hessian=evaluate_hessian)])
+                + [api.Constraint(cT_, n, 0, evaluate_hessian=evaluate_hessian)])
         bounds = [api.Bound(n, m)] * (T - 1) + [api.Bound(n, 0)]
     else:  # test/solve.jl: end points pinned through bounds
         cons = [api.Constraint() for _ in range(T)]
         bounds = ([api.Bound(n, m, state_lower=x1, state_upper=x1)] + [api.Bound(n, m)] * (T - 2)
                   + [api.Bound(n, 0, state_lower=xT, state_upper=xT)])
     return dict(
+        fns=dict(dyn=acrobot_midpoint, cost=[ot] * (T - 1) + [oT], con=con_fns, general=None),
         name="acrobot", T=T, n=n, m=m,
         dynamics=[dt] * (T - 1), objective=[ct] * (T - 1) + [cT], constraints=cons, bounds=bounds,
         general=None, evaluate_hessian=evaluate_hessian, x1=x1, xT=xT,
@@ -311,7 +320,9 @@ def build_car(api, T=51, evaluate_hessian=True, obstacle="general"):
               + [api.Bound(n, m, action_lower=al, action_upper=au)] * (T - 2)
               + [api.Bound(n, 0, state_lower=xT, state_upper=xT)])
     general = None
+    gen_fn, con_fns = None, [None] * T
     if obstacle == "stage":
+        con_fns = [car_obs] * T
         cont = api.Constraint(car_obs, n, m, num_parameter=0, indices_inequality=[1],
                               evaluate_hessian=evaluate_hessian)
         conT = api.Constraint(car_obs, n, 0, num_parameter=0, indices_inequality=[1],
@@ -328,9 +339,11 @@ def build_car(api, T=51, evaluate_hessian=True, obstacle="general"):
                 rows.append(car_obs(z[o:o + n], None, w)[0])
             return arr(*rows)
 
+        gen_fn = g
         general = api.GeneralConstraint(g, nz, 0, indices_inequality=list(range(1, T + 1)),
                                         evaluate_hessian=evaluate_hessian)
     return dict(
+        fns=dict(dyn=car_midpoint, cost=[ot] * (T - 1) + [oT], con=con_fns, general=gen_fn),
         name="car", T=T, n=n, m=m,
         dynamics=[dt] * (T - 1), objective=[ct] * (T - 1) + [cT], constraints=cons, bounds=bounds,
         general=general, evaluate_hessian=evaluate_hessian, x1=x1, xT=xT,

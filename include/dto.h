@@ -206,8 +206,16 @@ int dto_kkt_solve(dto_kkt* k, double* sol);
  * buffers are needed for the overlap to happen. */
 int dto_kkt_solve_host(dto_kkt* k, const double* z, const double* sigma, const double* lambda, double* sol, int nchunks);
 /* the same, enqueued on the shard streams without synchronising; with_callbacks = 0 reuses the
- * g, c, J, H already on the device */
+ * g, c, J, H already on the device; with_callbacks = 2 runs the callbacks only (the caller may then change
+ * lambda or c on the device before a dto_kkt_launch(k, 0): e.g. a Hessian evaluated with other multipliers
+ * than the right-hand side, or a second-order-correction right-hand side) */
 int dto_kkt_launch(dto_kkt* k, int with_callbacks);
+/* Inertia control for a solver that drives the batch (reference: Ipopt perturbs the Hessian handed over by
+ * MOI.eval_hessian_lagrangian, src/moi.jl:72, until the KKT matrix has N_c negative eigenvalues): reg[B] replaces
+ * the scalar primal_reg problem by problem (NULL: back to the scalar); dto_kkt_inertia returns the number of
+ * negative pivots of D per problem for the last factorisation (N_c when K is quasi-definite). */
+int dto_kkt_set_primal_reg(dto_kkt* k, const double* reg /* [B] or NULL */);
+int dto_kkt_inertia(dto_kkt* k, int32_t* nneg /* [B] */);
 /* which = 0: h [B][dim]; 1: sol [B][dim] (device -> host, after a solve) */
 int dto_kkt_get(dto_kkt* k, int which, double* out);
 /* inspection: dense row-major [dim][dim] assembled K of one problem (from the current device J, H,
@@ -215,7 +223,8 @@ int dto_kkt_get(dto_kkt* k, int which, double* out);
  * Lband[dim][row_width] with Lband[R][q] = L(R, R-q), D[dim]; P K P' = L D L' */
 int dto_kkt_matrix(dto_kkt* k, int64_t problem, double* dense);
 int dto_kkt_factor(dto_kkt* k, int64_t problem, double* Lband, double* D);
-/* which = 0 h, 1 sol, 2 factor storage */
+/* which = 0 h, 1 sol, 2 factor storage, 3 per-problem primal regularisation [shard size] (asking for it switches the
+ * kernels to per-problem mode: the caller writes it on the device), 4 negative-pivot counts [shard size] int32 */
 void* dto_kkt_device_pointer(dto_kkt* k, int which, int shard);
 
 #ifdef __cplusplus

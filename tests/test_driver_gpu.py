@@ -30,7 +30,7 @@ def test_pendulum_solve_matches_oracle_driven_solve():
         psolver.initialize_controls([np.array([0.01 * (b + 1)]) for _ in range(T - 1)], problem=b)
     z0 = psolver._initial.copy()
     opts = {"maxiter": 300}
-    res = psolver.solve(options=opts, record_iterates=True)
+    res = psolver.solve(options=opts, record_iterates=True, method="broker")
     n0 = psolver.nlp.launch_count()
     assert n0 > 0, "no CUDA kernel was launched by solve!"
     Zo, reso, _, its_o = driver.solve_batch(OracleBatch(osolver, B), z0, options=opts, record_iterates=True)

@@ -4,6 +4,7 @@ that pin the oracle; tolerances are the reference's (1e-8) unless a closed form 
 import math
 
 import numpy as np
+import pytest
 import sympy as sp
 
 from examples import models as M
@@ -173,6 +174,96 @@ def test_hessian_of_lagrangian_acrobot():
     h2 = np.zeros(len(key))
     nlp.eval_hessian_lagrangian(h2, z0[:np_], 2.0, z0[np_:])
     assert np.allclose(h2 - h1, 2.0 * (h0 - h1), rtol=1e-12, atol=1e-14)
+
+
+SHAPES = [("pendulum", dict(T=4)), ("cartpole", dict(T=4)), ("cartpole", dict(T=3, parameterized=False)), ("acrobot", dict(T=3)),
+          ("car", dict(T=4, obstacle="general")), ("car", dict(T=4, obstacle="stage"))]
+
+
+@pytest.mark.parametrize("name,kw", SHAPES, ids=[f"{n}-{'-'.join(str(v) for v in k.values())}" for n, k in SHAPES])
+def test_hessian_of_lagrangian_all_baseline_shapes(name, kw):
+    """The check of test/hessian_lagrangian.jl:131-205 -- assembled Hessian of the Lagrangian against an
+    INDEPENDENT dense symbolic Hessian of the hand-built Lagrangian, both triangles, sorted-key order -- for all
+    four BASELINE shapes (small T), including the car with its obstacle as a nonlinear GeneralConstraint (Q7: the
+    intended (z, w, lambda) semantics). The reference Hessian is plain `sympy.hessian` of
+        L = sigma * sum_t cost_t + sum_t lambda_dyn_t . d(x_{t+1}, x_t, u_t, w_t) + sum_t lambda_stage_t . c_t + lambda_gen . g(z, w)
+    built from the model FUNCTIONS, not from the element objects: it shares neither the structural-pattern rules
+    (oracle/symbolics.py) nor the index builders (oracle/elements.py) with what it checks."""
+    m_ = M.BUILDERS[name](O, **kw)
+    solver = O.solver_from(m_)
+    nlp = solver.nlp
+    T, n, m = m_["T"], m_["n"], m_["m"]
+    fns = m_["fns"]
+    nw = 8 if m_.get("shared_parameters") else 0
+    N_z, N_c = nlp.num_variables, nlp.num_constraint
+    zs = [sp.Symbol(f"q{i}") for i in range(N_z)]
+    ls = [sp.Symbol(f"l{i}") for i in range(N_c)]
+    ws = np.array([sp.Symbol(f"p{i}") for i in range(nw)], dtype=object)
+    sigma = sp.Symbol("sg")
+    z = np.array(zs, dtype=object)
+    X = [z[t * (n + m):t * (n + m) + n] for t in range(T)]
+    U = [z[t * (n + m) + n:(t + 1) * (n + m)] for t in range(T - 1)] + [np.zeros(0, dtype=object)]
+    L = 0
+    for t in range(T):
+        L = L + sigma * fns["cost"][t](X[t], U[t], ws)
+    row = 0
+    for t in range(T - 1):                       # dynamics rows first (src/data.jl:64-75)
+        d = M.cat(fns["dyn"](X[t + 1], X[t], U[t], ws))
+        L = L + M.dot(ls[row:row + len(d)], d)
+        row += len(d)
+    for t in range(T):                           # then stage rows
+        if fns["con"][t] is not None:
+            c = M.cat(fns["con"][t](X[t], U[t], ws))
+            L = L + M.dot(ls[row:row + len(c)], c)
+            row += len(c)
+    if fns["general"] is not None:               # then the general block
+        gv = M.cat(fns["general"](z, ws))
+        L = L + M.dot(ls[row:row + len(gv)], gv)
+        row += len(gv)
+    assert row == N_c
+    # reference Hessian: central second differences of L itself in 60-digit arithmetic (truncation ~1e-30): no
+    # symbolic differentiation at all, so it is independent of sympy's diff as well as of the oracle's rules
+    import mpmath
+    mpmath.mp.dps = 60
+    rng = np.random.default_rng(12)
+    z0, l0, w0 = rng.uniform(-1, 1, N_z), rng.normal(size=N_c), rng.normal(size=nw)
+    sg = 0.37
+    Lf = sp.lambdify(zs, L.subs({**dict(zip(ls, [sp.Float(v, 60) for v in l0])), **dict(zip(ws, [sp.Float(v, 60) for v in w0])),
+                                 sigma: sp.Float(sg, 60)}), modules="mpmath")
+    h = mpmath.mpf(10) ** -15
+    x0 = [mpmath.mpf(float(v)) for v in z0]
+
+    def at(shifts):
+        x = list(x0)
+        for i, sgn in shifts:
+            x[i] = x[i] + sgn * h
+        return Lf(*x)
+
+    f0 = at(())
+    fp = [at(((i, 1),)) for i in range(N_z)]
+    fm = [at(((i, -1),)) for i in range(N_z)]
+    dense = np.zeros((N_z, N_z))
+    band = 2 * (n + m)                            # knots couple only with their neighbour (and the general block per knot)
+    for i in range(N_z):
+        dense[i, i] = float((fp[i] - 2 * f0 + fm[i]) / h ** 2)
+        for j in range(i + 1, min(N_z, i + band)):
+            v = (at(((i, 1), (j, 1))) - at(((i, 1), (j, -1))) - at(((i, -1), (j, 1))) + at(((i, -1), (j, -1)))) / (4 * h ** 2)
+            dense[i, j] = dense[j, i] = float(v)
+    if nw:
+        solver.set_parameters([w0.copy() for _ in range(T)] + [np.zeros(0)])
+    key = nlp.hessian_lagrangian_structure()
+    hv = np.zeros(len(key))
+    nlp.eval_hessian_lagrangian(hv, z0, sg, l0)
+    assert key == sorted(set(key))                                    # sorted unique (row, col) keys
+    got = np.zeros((N_z, N_z))
+    for (r, c), v in zip(key, hv):
+        got[r - 1, c - 1] = v
+        assert (c, r) in set(key)                                     # both triangles handed to Ipopt (Q8)
+    assert np.allclose(got, got.T, rtol=0, atol=0)
+    # every non-zero of the exact Hessian has a slot, and the values agree
+    missing = [(i + 1, j + 1) for i in range(N_z) for j in range(N_z) if abs(dense[i, j]) > 1e-20 and (i + 1, j + 1) not in set(key)]
+    assert missing == []
+    assert np.max(np.abs(got - dense)) <= 1e-12 * max(1.0, np.max(np.abs(dense)))
 
 
 def test_structure_sizes_match_survey_tables():
