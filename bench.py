@@ -434,6 +434,17 @@ def run_ours(args):
                             "ncu_pipe_fp64_pct": f64["ncu_pipe_fp64_pct"], "source": f64["source"]}
         if kkt is not None:
             line["kkt"] = kkt
+        if world == 1 and not args.no_solve:
+            # secondary (BASELINE config 3): acrobot T=101 x 4096 FULL SOLVES on the device (lock-step Newton-KKT
+            # solver over the same callbacks + KKT kernels); Ipopt is absent, so this is this repository's solver
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import solve_config3
+                for n_ in nlps:
+                    n_.close()
+                line["solve"] = solve_config3.run(B=4096, T=101, max_iter=300)
+            except Exception as e:  # noqa: BLE001
+                line["solve"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:
             co, mo = build_c_baseline(T)
             try:
@@ -466,6 +477,7 @@ def main():
     ap.add_argument("--no-bind", action="store_true", dest="no_bind", help="do not bind the process to the GPU-local host cores")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
     ap.add_argument("--no-kkt", action="store_true", dest="no_kkt")
+    ap.add_argument("--no-solve", action="store_true", dest="no_solve")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200:

@@ -203,13 +203,14 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     double A[W], Bv[W];
     double ra, rb = 0.0, rc = 0.0, regc = 0.0;
     int32_t nidx[W];                                  // gather indices of the rows two blocks ahead
-    load_rows<W>(a, Hb, Jb, 0, i, A);
+    load_rows<W>(a, Hb, Jb, 0, i, A, b);
+    int neg = 0;   // negative pivots of D so far (every lane of the group sees every pivot): the inertia of K
     {
         const int32_t ip = a.iperm[i];
         ra = ip >= 0 ? hb[ip] : 0.0;
     }
     if (nblk > 1) {
-        load_rows<W>(a, Hb, Jb, 1, i, Bv);
+        load_rows<W>(a, Hb, Jb, 1, i, Bv, b);
         const int32_t ip = a.iperm[W + i];
         rb = ip >= 0 ? hb[ip] : 0.0;
     } else {
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
             cp_async_commit();
             const int32_t ip = a.iperm[(size_t)(blk + 2) * W + i];
             rc = ip >= 0 ? hb[ip] : 0.0;
-            regc = a.dreg[(size_t)(blk + 2) * W + i];
+            regc = row_shift(a, (size_t)(blk + 2) * W + i, b);
             load_idx(blk + 3);
         }
         double* LA = Lg + (size_t)blk * W * LW + i;  // + s*LW + (row - j) with immediates
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
             if (inA) vs[i - s - 1] = vA;
             if (hasB && inB) vs[i + G - s - 1] = vB;
             const double d = shfl_g<G>(A[p], s);
+            neg += d < 0.0 ? 1 : 0;
             const double dinv = 1.0 / d;
             const double lA = vA * dinv;
             const double lB = vB * dinv;
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     }
     __syncwarp();
     __threadfence_block();
+    if (a.nneg != nullptr && valid && i == 0) a.nneg[b] = neg;
 
     kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
 }

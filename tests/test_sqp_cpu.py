@@ -1,0 +1,96 @@
+"""The batched Newton-KKT algorithm (dto_b200/sqp.py) driven by the CPU oracle (tests/sqp_oracle.py): the
+host-side logic -- inertia control, Levenberg-Marquardt damping, merit line search with second-order
+correction, per-problem masks -- checked without a GPU. The device arm runs the same function
+(tests/test_sqp_gpu.py compares the two iterate by iterate)."""
+import numpy as np
+
+import dto_b200 as D
+from dto_b200 import kkt as PK
+from dto_b200 import sqp
+from examples import models as M
+from oracle import api as O
+
+from sqp_oracle import OracleBackend, band_ldl_solve
+
+
+def _guess(model, B, seed):
+    T, n, m = model["T"], model["n"], model["m"]
+    rng = np.random.default_rng(seed)
+    z = np.zeros((B, T * n + (T - 1) * m))
+    for t in range(T):
+        o = t * (n + m)
+        z[:, o:o + n] = model["x1"] + (model["xT"] - model["x1"]) * t / (T - 1)
+        if t < T - 1:
+            z[:, o + n:o + n + m] = rng.normal(size=(B, m))
+    return z
+
+
+def test_oracle_driven_solver_converges_and_meets_reference_acceptance():
+    """pendulum swing-up (examples/pendulum/pendulum.jl), 3 problems in lock step: converged KKT point, end points
+    within the reference's 1e-3 (test/solve.jl:134-137), problems that converge early stop moving."""
+    mo, mp = M.build_pendulum(O), M.build_pendulum(D)
+    osolver = O.solver_from(mo)
+    perm, bw = PK.analyze(D.solver_from(mp, batch=1).nlp)     # host-only symbolic phase of the product
+    B = 3
+    be = OracleBackend(osolver, B, perm=perm - 1, bw=bw, linear="band")
+    res = sqp.solve(be, _guess(mo, B, 1), options=sqp.SQPOptions(max_iter=40), record=True)
+    assert res.converged.all() and res.constraint_violation.max() < 1e-8 and res.dual_residual.max() < 1e-6
+    n = mo["n"]
+    assert np.all(np.linalg.norm(res.z[:, :n] - mo["x1"], axis=1) < 1e-3)
+    assert np.all(np.linalg.norm(res.z[:, -n:] - mo["xT"], axis=1) < 1e-3)
+    # a converged problem is frozen: its z does not change in later iterations
+    for b in range(B):
+        k = int(res.iterations[b])
+        for h in res.history[k + 1:]:
+            assert np.array_equal(h["z"][b], res.history[k]["z"][b])
+
+
+def test_inertia_control_regularises_an_indefinite_hessian():
+    """A Hessian with negative curvature in the null space of J gives the wrong inertia; the loop must raise the
+    per-problem regularisation until D has exactly N_c negative pivots (Ipopt's IC rule)."""
+    class Toy:
+        xp = sqp._XP(np)
+        B, N_z, N_c = 2, 3, 1
+        free = np.ones(3)
+
+        def __init__(self):
+            self.deltas = []
+
+        def callbacks(self, z, lam, lam_h, delta):
+            self.z = z
+            f = 0.5 * (-z[:, 0] ** 2 + z[:, 1] ** 2 + z[:, 2] ** 2) + 0.25 * z[:, 0] ** 4
+            g = np.stack([-z[:, 0] + z[:, 0] ** 3, z[:, 1], z[:, 2]], 1)
+            c = (z[:, 1] + z[:, 2] - 1.0)[:, None]
+            self.g, self.c, self.lam = g, c, lam
+            return f, g, c
+
+        def _K(self, b, d):
+            H = np.diag([-1.0 + 3 * self.z[b, 0] ** 2, 1.0, 1.0]) + d * np.eye(3)
+            J = np.array([[0.0, 1.0, 1.0]])
+            return np.block([[H, J.T], [J, -1e-9 * np.eye(1)]]), J
+
+        def newton(self, delta):
+            self.deltas.append(delta.copy())
+            sol, nneg, rz = np.zeros((2, 4)), np.zeros(2), np.zeros((2, 3))
+            for b in range(2):
+                K, J = self._K(b, delta[b])
+                rz[b] = self.g[b] + J.T @ self.lam[b]
+                sol[b], nneg[b] = band_ldl_solve(K, np.concatenate([rz[b], self.c[b]]), np.arange(4), 3)
+            return sol, nneg, rz
+
+        def newton_soc(self, c_soc, delta):
+            saved, self.c = self.c, c_soc
+            try:
+                return self.newton(delta)[0]
+            finally:
+                self.c = saved
+
+        def objective_constraint(self, z):
+            return 0.5 * (-z[:, 0] ** 2 + z[:, 1] ** 2 + z[:, 2] ** 2) + 0.25 * z[:, 0] ** 4, (z[:, 1] + z[:, 2] - 1.0)[:, None]
+
+    be = Toy()
+    res = sqp.solve(be, np.array([[0.1, 0.0, 0.0], [1.5, 0.3, 0.3]]), options=sqp.SQPOptions(max_iter=60, lm_first=0.0))
+    assert res.converged.all()
+    assert np.allclose(np.abs(res.z[:, 0]), 1.0, atol=1e-6) and np.allclose(res.z[:, 1:], 0.5, atol=1e-6)
+    # problem 0 started where d2f/dx0^2 < 0: its regularisation was raised above 1 - 3 x0^2 at least once, problem 1's was not
+    assert max(d[0] for d in be.deltas) > 0.9 and max(d[1] for d in be.deltas[:3]) == 0.0

@@ -73,5 +73,8 @@ def run(B=4096, T=101, max_iter=300, name="acrobot", options=None):
 
 if __name__ == "__main__":
     a = sys.argv[1:]
-    out = run(int(a[0]) if a else 4096, int(a[1]) if len(a) > 1 else 101, int(a[2]) if len(a) > 2 else 300, a[3] if len(a) > 3 else "acrobot")
+    opts = json.loads(os.environ.get("DTO_SQP_OPTIONS", "{}"))   # e.g. '{"max_backtrack": 12}'
+    out = run(int(a[0]) if a else 4096, int(a[1]) if len(a) > 1 else 101, int(a[2]) if len(a) > 2 else 300, a[3] if len(a) > 3 else "acrobot",
+              options=opts)
+    out["options"] = opts
     print(json.dumps(out))
