@@ -26,10 +26,16 @@
 // the slow path, which computes the same records in place.
 #pragma once
 
-#define DTO_WS_COMPUTE 8
-#ifndef DTO_WS_HELPERS
-#define DTO_WS_HELPERS 4          /* 4: helper h serves compute warps h, h+4 (FP64-heavy models); 8: one helper per compute warp */
+#ifndef DTO_WS_COMPUTE
+#define DTO_WS_COMPUTE 8          /* compute warps per CTA: 8 (2 per SM sub-partition) or 12 (3 per sub-partition) */
 #endif
+#ifndef DTO_WS_HELPERS
+#define DTO_WS_HELPERS 8          /* helper h serves compute warps h, h + HELPERS, ...: COMPUTE must be a multiple */
+#endif
+/* registers per thread the launch allocates: 64 K registers per SM over the CTA's threads ROUNDED UP TO 128 (ptxas
+ * sizes the pool per group of four warps: 18 warps get 65536/640 = 96, not 112), multiple of 8 */
+#define DTO_WS_WARPS (DTO_WS_COMPUTE + DTO_WS_HELPERS)
+#define DTO_WS_BASE_REGS ((65536 / (128 * ((DTO_WS_WARPS + 3) / 4))) > 255 ? 248 : ((65536 / (128 * ((DTO_WS_WARPS + 3) / 4))) & ~7))
 #define DTO_WS_DESC_DOUBLES 192   /* 3 x int4 per item, 32 items */
 #define DTO_WS_PIECE_DOUBLES 64   /* 1 x int4 per piece, 32 pieces */
 #define DTO_WS_HDR_DOUBLES 2      /* 1 x int4: b0, ... */
@@ -321,9 +327,9 @@ __host__ __device__ constexpr bool ws_split_general()
 
 // setmaxnreg can only hand out what the launch allocated (12 warps x 168 registers): a split that asks
 // for more makes the compute warps spin in setmaxnreg.inc forever (measured: a hung launch)
-static_assert(DTO_WS_HELPERS == 4 || DTO_WS_HELPERS == 8, "4 or 8 helper warps");
-static_assert(DTO_WS_HELPERS * DTO_WS_HREG + DTO_WS_COMPUTE * DTO_WS_CREG <= (DTO_WS_HELPERS + DTO_WS_COMPUTE) * (DTO_WS_HELPERS == 4 ? 168 : 128),
-              "DTO_WS_HREG / DTO_WS_CREG exceed the registers of the launch (168 per thread at 384 threads, 128 at 512)");
+static_assert(DTO_WS_HELPERS <= DTO_WS_COMPUTE && DTO_WS_WARPS <= 32, "at most one helper per compute warp, at most 32 warps");
+static_assert(DTO_WS_HELPERS * DTO_WS_HREG + DTO_WS_COMPUTE * DTO_WS_CREG <= DTO_WS_WARPS * DTO_WS_BASE_REGS,
+              "DTO_WS_HREG / DTO_WS_CREG exceed the registers of the launch (64 K per SM over all warps of the CTA)");
 static_assert(DTO_WS_HREG % 8 == 0 && DTO_WS_CREG % 8 == 0 && DTO_WS_HREG >= 24 && DTO_WS_CREG <= 256, "setmaxnreg takes multiples of 8 in [24, 256]");
 
 template <class M, int MODE>
@@ -341,15 +347,26 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     const int T = a.T;
     const int total = (int)(a.B * T);
     const int tiles = (total + OWN - 1) / OWN;
+#if DTO_WS_PDL
+    // programmatic dependent launch: the next kernel of the stream may start its CTAs as soon as SMs free up
+    // (its own prologue then overlaps this grid's tail); it waits in griddepcontrol.wait before touching data
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
 
-    // the knot table lives in shared memory (the launch plan guarantees it fits)
-    const int kt_doubles = (T + 1) * 8;
-    {
-        const int4* src = reinterpret_cast<const int4*>(a.knot);
-        int4* dst = reinterpret_cast<int4*>(dto_smem);
-        for (int i = threadIdx.x; i < (T + 1) * 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    // the knot table lives in shared memory (the launch plan guarantees it fits). Only the slow path (ragged last
+    // tile, launches without a plan table) reads it, so nobody waits for it here: one bulk copy, completion on
+    // its own mbarrier (the 8 bytes after the table), waited for where the table is first used
+    const int kt_doubles = (T + 1) * 8 + 2;
+    const uint32_t kt_bar = smem_u32(dto_smem + (T + 1) * 8);
+    if (threadIdx.x == 0) {
+        mbar_init(kt_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(kt_bar, (uint32_t)(T + 1) * 64u);
+        bulk_load(smem_u32(dto_smem), a.knot, (uint32_t)(T + 1) * 64u, kt_bar);
+        mbar_arrive(kt_bar);
     }
     const dto_knot_entry* tab = reinterpret_cast<const dto_knot_entry*>(dto_smem);
+    bool kt_ready = false;
 
     int base[6], ioff[5], in_sz, stage_sz, out0, out_sz;
     const int NOUT = a.ws_nout;  // output staging buffers per compute warp (1 or 2)
@@ -366,14 +383,19 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
     const int4* __restrict__ plan = reinterpret_cast<const int4*>(a.ws_plan);
     const int G4 = ws_gen_int4<MODE>(a);  // int4 of general-constraint records per plan block / stage
 
+    // (DTO_WS_PDL) everything up to here touched only shared memory and launch-constant tables; problem data (z,
+    // lambda, sigma, w, outputs) may still be in use by the previous kernel of the stream until it has completed:
+    // each role executes griddepcontrol.wait right before its first access to problem data
     if (warp < DTO_WS_HELPERS) {
         // =============================== helper warp ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DTO_WS_HREG));
+        bool dep_ok = DTO_WS_PDL == 0;
         for (int kk = 0;; ++kk) {
             bool any = false;
 #pragma unroll 1
-            for (int ci = 0; ci < DTO_WS_COMPUTE / DTO_WS_HELPERS; ++ci) {
-                const int c = warp + ci * DTO_WS_HELPERS;
+            for (int ci = 0; ci < (DTO_WS_COMPUTE + DTO_WS_HELPERS - 1) / DTO_WS_HELPERS; ++ci) {
+                const int c = warp + ci * DTO_WS_HELPERS;   // helper h serves compute warps h, h + HELPERS, ...
+                if (c >= DTO_WS_COMPUTE) break;
                 const int tile0 = blockIdx.x * DTO_WS_COMPUTE + c;
                 const int tile = tile0 + kk * stride;                                // tile to produce
                 const bool have_drain = kk >= 2 && tile0 + (kk - 2) * stride < tiles;  // tile kk-2 to drain
@@ -430,6 +452,10 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                         }
                     } else {
                         // ---- ragged last tile (or no plan table): compute the records here ----
+                        if (!kt_ready) {
+                            mbar_wait(kt_bar, 0);   // the knot table has landed in shared memory
+                            kt_ready = true;
+                        }
                         const tile_t q = tile_geom_at<HALO>(a, g0, n);
                         b0 = q.b0;
                         int4 piece, d0, d1, d2;
@@ -439,6 +465,10 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
                         sdesc[64 + lane] = d2;
                         sdesc[96 + lane] = piece;
                         if (G4) reinterpret_cast<int*>(sdesc + 128 + 32 * DTO_WS_GEN_K)[lane] = -1;  // general entries: table path
+                    }
+                    if (!dep_ok) {   // the plan records of the first tile were fetched while the previous kernel drained
+                        asm volatile("griddepcontrol.wait;" ::: "memory");
+                        dep_ok = true;
                     }
                     if (copy.y > 0) {
                         mbar_expect_tx(full, (uint32_t)copy.y);
@@ -456,10 +486,16 @@ __global__ void __launch_bounds__((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, 1) kno
             }
             if (!any && kk >= 2) break;  // (a lone tile is produced in round 0 and drained in round 2)
         }
-        bulk_wait_all();
+        // the stores only have to have READ their shared-memory source before the CTA exits; their global writes
+        // complete with the grid (what a TMA-store epilogue waits for: cp.async.bulk.wait_group.read 0)
+        bulk_wait_read();
+        if (!kt_ready && warp == 0) mbar_wait(kt_bar, 0);  // never leave a bulk copy into this CTA's shared memory in flight
     } else {
         // =============================== compute warp ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DTO_WS_CREG));
+#if DTO_WS_PDL
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // (parameters not staged in shared memory are read from HBM)
+#endif
         const int c = warp - DTO_WS_HELPERS;
         double* __restrict__ smc = dto_smem + kt_doubles + (size_t)c * per_warp;
         const uint32_t bar0 = smem_u32(smc);
@@ -582,7 +618,7 @@ inline int64_t plan_ws(dto_launch_args& b)
     if (!b.w_flat && b.N_w > 65535) return 0;
     int out_sz = 0;
     const int64_t one = (int64_t)ws_layout<MODE>(b, nullptr, nullptr, nullptr, nullptr, nullptr, &out_sz);
-    const int64_t kt = (int64_t)(b.T + 1) * 64;
+    const int64_t kt = (int64_t)(b.T + 1) * 64 + 16;   // + the table's mbarrier
     for (int nout = 2; nout >= 1; --nout) {
         const int64_t per_warp = one + (nout - 1) * (int64_t)out_sz;
         if (per_warp > 65535) continue;  // 16-bit region offsets

@@ -63,6 +63,9 @@
 #ifndef DTO_WS_CREG
 #define DTO_WS_CREG 232    /* registers per compute-warp thread after setmaxnreg.inc (HREG + 2*CREG <= 512) */
 #endif
+#ifndef DTO_WS_PDL
+#define DTO_WS_PDL 0       /* 1: launch the ws kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail) */
+#endif
 #ifndef DTO_WS_PLAN
 #define DTO_WS_PLAN 1      /* precomputed tile-plan table for the ws kernel (0: helpers compute every tile's records) */
 #endif
@@ -772,8 +775,10 @@ __global__ void __launch_bounds__(DTO_PWARPS * 32, DTO_PCTAS) knot_kernel_p(cons
 #include "dto_kernel_ws.cuh"
 
 // ---------------------------------------------------------------------------------------
-// objective value: one warp per problem, lanes stride over knots, xor-shuffle tree
-// (/root/reference/src/costs.jl:49-56)
+// objective value: one warp per problem. The per-knot costs of 32 consecutive knots are evaluated in
+// parallel (lane = knot), then added to the running sum ONE BY ONE in knot order -- the reference's serial
+// `J += cost_t` (/root/reference/src/costs.jl:49-56), so the rounding of the sum is the reference's too
+// (a shuffle tree would be ~T/32 times shorter but sums in another order).
 // ---------------------------------------------------------------------------------------
 template <class M>
 __global__ void __launch_bounds__(DTO_WARPS * 32) objective_kernel(const __grid_constant__ dto_launch_args a)
@@ -783,13 +788,17 @@ __global__ void __launch_bounds__(DTO_WARPS * 32) objective_kernel(const __grid_
     if (b >= a.B) return;
     const double* __restrict__ zb = a.z + (size_t)b * a.N_z;
     double acc = 0.0;
-    for (int t = lane; t < a.T; t += 32) {
-        const dto_knot_entry ke = load_knot(a.knot, t);
-        const double* x = zb + ke.zofs;
-        acc += M::cost_val(ke.kcost, x, x + ke.nx, a.w + (size_t)b * a.N_w + ke.wofs);
+    for (int t0 = 0; t0 < a.T; t0 += 32) {
+        const int t = t0 + lane;
+        double v = 0.0;
+        if (t < a.T) {
+            const dto_knot_entry ke = load_knot(a.knot, t);
+            const double* x = zb + ke.zofs;
+            v = M::cost_val(ke.kcost, x, x + ke.nx, a.w + (size_t)b * a.N_w + ke.wofs);
+        }
+        const int n = min(32, a.T - t0);  // warp-uniform
+        for (int k = 0; k < n; ++k) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, k));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) a.f[b] = acc;
 }
 
@@ -878,8 +887,22 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st, bool* used_ws)
             long long ctas = (warps + DTO_WS_COMPUTE - 1) / DTO_WS_COMPUTE;
             if (ctas > sms[dev]) ctas = sms[dev];
             b.ws_plan = ws_get_plan<M, MODE>(b, st);
+#if DTO_WS_PDL
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)ctas);
+            cfg.blockDim = dim3((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32);
+            cfg.dynamicSmemBytes = (size_t)wsmem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, knot_kernel_ws<M, MODE>, b);
+#else
             knot_kernel_ws<M, MODE><<<(unsigned)ctas, (DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, (size_t)wsmem, st>>>(b);
             cudaError_t e = cudaGetLastError();
+#endif
             if (e != cudaSuccess)
                 fprintf(stderr, "[dto] knot_kernel_ws<mode %d> launch failed: %s (grid %lld, smem %lld)\n", MODE, cudaGetErrorString(e), ctas,
                         (long long)wsmem);

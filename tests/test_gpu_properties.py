@@ -98,6 +98,37 @@ def test_full_size_vs_c_oracle_and_properties(name, kw, B, config):
     pn.close()
 
 
+def test_in_process_shards_over_all_visible_devices_are_bit_identical():
+    """The in-process multi-device path of libdto.so (one host thread, one stream per shard, contiguous shards,
+    host gather = each shard's D2H into its slice): the batch is spread over EVERY visible device --
+    and over at least three shards, so the path is exercised on a one-GPU box too (a device may be listed more
+    than once) -- and all five callbacks + the fused pass + the KKT consumer must reproduce the one-shard bits."""
+    from dto_b200 import kkt as PK
+    ndev = _lib.lib().dto_device_count()
+    devices = [d % ndev for d in range(max(3, ndev))]
+    name, kw, B, config = "cartpole", dict(T=11), 1000, 2     # 1000 problems: ragged shards (334, 334, 332)
+    mp = M.BUILDERS[name](D, **kw)
+    one = D.solver_from(mp, batch=B, devices=[0]).nlp
+    many = D.solver_from(mp, batch=B, devices=devices).nlp
+    assert many.num_shards == len(devices) and sorted({many.shard_device(i) for i in range(many.num_shards)}) == sorted(set(devices))
+    assert sum(many.shard_range(i)[1] for i in range(many.num_shards)) == B
+    z, lam, sigma, w = make_inputs(name, mp, one.num_variables, one.num_constraint, one.num_parameter, B, config)
+    a, b = _eval_all(one, z, lam, sigma, w), _eval_all(many, z, lam, sigma, w)
+    for k in ("f", "g", "c", "J", "H"):
+        assert np.array_equal(a[k], b[k]), k
+    Ja, Ha, Jb, Hb = (np.empty_like(a[k]) for k in ("J", "H", "J", "H"))
+    one.eval_jacobian_hessian(Ja, Ha, z, sigma, lam)
+    many.eval_jacobian_hessian(Jb, Hb, z, sigma, lam)
+    assert np.array_equal(Ja, Jb) and np.array_equal(Ha, Hb)
+    k1, k2 = PK.KKTSystem(one), PK.KKTSystem(many)
+    s1, s2 = np.empty((B, k1.dim)), np.empty((B, k2.dim))
+    k1.solve(s1, variables=z, scaling=sigma, duals=lam)
+    k2.solve(s2, variables=z, scaling=sigma, duals=lam)
+    assert np.array_equal(s1, s2)
+    assert np.array_equal(k1.inertia(), k2.inertia()) and np.all(k1.inertia() == one.num_constraint)
+    k1.close(); k2.close(); one.close(); many.close()
+
+
 def test_sigma_linearity_and_dual_linearity():
     """H(sigma, lambda) = sigma * H_cost + H_constraints(lambda), linear in each."""
     mp = M.build_acrobot(D, T=21)
