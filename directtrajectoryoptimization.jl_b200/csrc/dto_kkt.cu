@@ -71,6 +71,27 @@ __device__ __forceinline__ double row_shift(const dto_kkt_args& a, size_t row, i
     return reg;
 }
 
+// right-hand-side entry of original row ip (natural order): read from the rhs array written by kkt_rhs_kernel, or
+// (a.fuse_rhs) computed here with the same operations in the same order -- the reference's loop
+// (examples/pendulum/pendulum.jl:155-173): cy = sum over constraint rows ascending of C[j,i]*y[j]; h[i] = grad[i] + cy
+__device__ __forceinline__ double rhs_entry(const dto_kkt_args& a, int64_t b, int32_t ip, const double* __restrict__ hb, bool valid)
+{
+    if (ip < 0) return 0.0;
+    if (!a.fuse_rhs) return hb[ip];
+    double h;
+    if (ip < a.N_z) {
+        const double* __restrict__ Jb = a.J + b * a.nnz_J;
+        const double* __restrict__ yb = a.y + b * a.N_c;
+        double cy = 0.0;
+        for (int k = a.colptr[ip]; k < a.colptr[ip + 1]; ++k) cy = __dadd_rn(cy, __dmul_rn(Jb[a.colslot[k]], yb[a.colrow[k]]));
+        h = __dadd_rn(a.g[b * a.N_z + ip], cy);
+    } else {
+        h = a.c[b * a.N_c + (ip - a.N_z)];
+    }
+    if (valid) a.rhs[b * a.dim + ip] = h;
+    return h;
+}
+
 template <int W>
 __device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* __restrict__ Hb, const double* __restrict__ JbmH,
                                           int blk, int i, double (&X)[W], int64_t b = 0)
@@ -205,14 +226,10 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     int32_t nidx[W];                                  // gather indices of the rows two blocks ahead
     load_rows<W>(a, Hb, Jb, 0, i, A, b);
     int neg = 0;   // negative pivots of D so far (every lane of the group sees every pivot): the inertia of K
-    {
-        const int32_t ip = a.iperm[i];
-        ra = ip >= 0 ? hb[ip] : 0.0;
-    }
+    ra = rhs_entry(a, b, a.iperm[i], hb, valid);
     if (nblk > 1) {
         load_rows<W>(a, Hb, Jb, 1, i, Bv, b);
-        const int32_t ip = a.iperm[W + i];
-        rb = ip >= 0 ? hb[ip] : 0.0;
+        rb = rhs_entry(a, b, a.iperm[W + i], hb, valid);
     } else {
 #pragma unroll
         for (int w = 0; w < W; ++w) Bv[w] = 0.0;
@@ -243,8 +260,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
                 cp_async8_zfill(stage + w * W + i, sx >= 0 ? (const void*)(bp + sx) : (const void*)Hb, sx >= 0 ? 8 : 0);
             }
             cp_async_commit();
-            const int32_t ip = a.iperm[(size_t)(blk + 2) * W + i];
-            rc = ip >= 0 ? hb[ip] : 0.0;
+            rc = rhs_entry(a, b, a.iperm[(size_t)(blk + 2) * W + i], hb, valid);
             regc = row_shift(a, (size_t)(blk + 2) * W + i, b);
             load_idx(blk + 3);
         }
@@ -361,10 +377,7 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     int32_t nidx[W];
     load_rows<W>(a, Hb, Jb, 0, i, R, b);
     int neg = 0;   // negative pivots seen so far (every lane of the group sees every pivot)
-    {
-        const int32_t ip = a.iperm[i];
-        rr = ip >= 0 ? hb[ip] : 0.0;
-    }
+    rr = rhs_entry(a, b, a.iperm[i], hb, valid);
     auto load_idx = [&](int blk) {
         if (blk < nblk) {
             const int32_t* src = a.src + ((size_t)blk * W) * W + i;
@@ -382,8 +395,7 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
                 const double* bp = (sx < a.nnz_H) ? Hb : Jb;
                 cp_async8_zfill(st + w * W + i, sx >= 0 ? (const void*)(bp + sx) : (const void*)Hb, sx >= 0 ? 8 : 0);
             }
-            const int32_t ip = a.iperm[(size_t)blk * W + i];
-            rn = ip >= 0 ? hb[ip] : 0.0;
+            rn = rhs_entry(a, b, a.iperm[(size_t)blk * W + i], hb, valid);
             regn = row_shift(a, (size_t)blk * W + i, b);
         }
         cp_async_commit();

@@ -27,8 +27,18 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a tool (nsys / ncu --nvtx) is attached
+
 #include "../../include/dto.h"
 #include "dto_model_abi.h"
+
+// NVTX range over one host-API phase (tracing): shows up as "dto:<what>" in a timeline
+struct DtoRange {
+    explicit DtoRange(const char* name) { nvtxRangePushA(name); }
+    ~DtoRange() { nvtxRangePop(); }
+    DtoRange(const DtoRange&) = delete;
+    DtoRange& operator=(const DtoRange&) = delete;
+};
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -314,8 +324,21 @@ extern "C" int dto_shape_create(dto_model* m, const dto_shape_desc* d, dto_shape
         DTO_REQUIRE(cost[t]->nx + cost[t]->nu == s->nx[t] + s->nu[t],
                     "dto_shape_create: objective[%d] has %d+%d variables, knot has %d+%d (gradient slice would not fit, "
                     "src/costs.jl:61)", t, cost[t]->nx, cost[t]->nu, s->nx[t], s->nu[t]);
-        if (stage[t])
+        if (stage[t]) {
             DTO_REQUIRE(stage[t]->nx == s->nx[t], "dto_shape_create: constraints[%d].num_state=%d != %d", t, stage[t]->nx, s->nx[t]);
+            // A Constraint may be declared with more actions than its knot has (examples/pendulum builds the terminal
+            // one with num_action = m) as long as it does not USE them: a Jacobian / Hessian entry beyond the knot's
+            // [x; u] would read the next problem's z (the reference raises a BoundsError there)
+            const int32_t nv = s->nx[t] + s->nu[t];
+            for (int32_t e = 0; e < stage[t]->nnz_jac; ++e)
+                DTO_REQUIRE(stage[t]->jac_col[e] >= 1 && stage[t]->jac_col[e] <= nv,
+                            "dto_shape_create: constraints[%d] uses variable %d of [x; u] but knot %d has only %d+%d (an action "
+                            "the knot does not have?)", t, stage[t]->jac_col[e], t, s->nx[t], s->nu[t]);
+            for (int32_t e = 0; stage[t]->has_hess && e < stage[t]->nnz_hess; ++e)
+                DTO_REQUIRE(stage[t]->hess_row[e] >= 1 && stage[t]->hess_row[e] <= nv && stage[t]->hess_col[e] >= 1 && stage[t]->hess_col[e] <= nv,
+                            "dto_shape_create: constraints[%d] has a Hessian entry (%d,%d) outside the knot's %d variables", t,
+                            stage[t]->hess_row[e], stage[t]->hess_col[e], nv);
+        }
         if (!cost[t]->has_hess) s->hessian_available = false;
     }
 
@@ -985,6 +1008,8 @@ extern "C" int dto_set_duals(dto_batch* b, const double* sigma, const double* la
 
 static int launch_all(dto_batch* b, int kernel_id)
 {
+    static const char* const names[] = {"dto:objective", "dto:gradient", "dto:constraint", "dto:jacobian", "dto:hessian", "dto:jacobian+hessian"};
+    DtoRange range(kernel_id >= 0 && kernel_id < 6 ? names[kernel_id] : "dto:launch");
     const dto_shape* s = b->shape;
     if (kernel_id < 0 || kernel_id >= DTO_K_COUNT) return fail(DTO_ERR_BAD_ARG, "dto_launch: kernel id %d", kernel_id);
     if (!b->have_x) return fail(DTO_ERR_STATE, "evaluation requested before dto_set_x");
@@ -1021,6 +1046,7 @@ static int eval_to_host(dto_batch* b, int kernel_id, int array, double* host)
 {
     if (!b) return fail(DTO_ERR_BAD_ARG, "null batch");
     if (!host && array_width(b->shape, array) > 0) return fail(DTO_ERR_BAD_ARG, "null output pointer");
+    DtoRange range("dto:eval_to_host");
     int r;
     if ((r = launch_all(b, kernel_id))) return r;
     if ((r = d2h(b, array, host))) return r;
@@ -1046,6 +1072,7 @@ extern "C" int dto_eval_jacobian_hessian_host(dto_batch* b, const double* z, con
                                               double* H, int nchunks)
 {
     if (!b || !z || !sigma || !lambda) return fail(DTO_ERR_BAD_ARG, "dto_eval_jacobian_hessian_host: null argument");
+    DtoRange range("dto:eval_jacobian_hessian_host (chunked H2D | kernel | D2H pipeline)");
     const dto_shape* s = b->shape;
     if (!s->hessian_available)
         return fail(DTO_ERR_NO_HESSIAN, "Hessian requested but a Cost was built without evaluate_hessian (reference throws at src/costs.jl:68)");

@@ -242,6 +242,10 @@ class BatchedNLPData:
             self.set_x(variables)
         if duals is not None:
             self.set_duals(1.0 if scaling is None else scaling, duals)
+        elif scaling is not None:
+            # MOI's signature always carries sigma together with lambda (src/moi.jl:72): a lone sigma would silently
+            # keep the multipliers of some earlier call
+            raise ValueError("eval_hessian_lagrangian: scaling given without duals; pass both (MOI.eval_hessian_lagrangian(H, z, sigma, lambda))")
         _lib.check(_lib.lib().dto_eval_hessian_lagrangian(self.handle, _p(H)))
 
     def eval_jacobian_hessian(self, jacobian, hessian, variables=None, scaling=None, duals=None, chunks: int = 0):
@@ -260,6 +264,8 @@ class BatchedNLPData:
             self.set_x(variables)
         if duals is not None:
             self.set_duals(1.0 if scaling is None else scaling, duals)
+        elif scaling is not None:
+            raise ValueError("eval_jacobian_hessian: scaling given without duals; pass both")
         _lib.check(_lib.lib().dto_eval_jacobian_hessian(self.handle, _p(J), _p(H)))
 
     # ---- device-resident interface (no host copies)

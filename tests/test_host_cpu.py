@@ -212,3 +212,31 @@ def test_json_spec_round_trip_builds_identical_model(tmp_path):
     doc["dynamics"][0]["jacobian_sparsity"][0][0] = 2
     with pytest.raises(ValueError):
         spec_io.load_spec(doc)
+
+
+def test_stage_constraint_using_a_missing_action_is_rejected():
+    """a Constraint at the terminal knot (no action there) whose function USES u would put Jacobian
+    columns beyond that problem's z; the reference raises a BoundsError, the shape assembly must refuse too. Merely
+    declaring num_action > 0 without using u (examples/pendulum's terminal constraint) stays legal."""
+    n, m, T = 2, 1, 4
+    dt = D.Dynamics(M.pendulum_midpoint, n, n, m)
+    ct, cT = D.Cost(lambda x, u, w: M.dot(x, x) + M.dot(u, u), n, m), D.Cost(lambda x, u, w: M.dot(x, x), n, 0)
+    ok_T = D.Constraint(lambda x, u, w: x - np.array([1.0, 0.0]), n, m)          # declares an action, does not use it
+    bad_T = D.Constraint(lambda x, u, w: x - np.array([1.0, 0.0]) * u[0], n, m)  # uses the action the terminal knot lacks
+    bounds = [D.Bound(n, m)] * (T - 1) + [D.Bound(n, 0)]
+    s = D.Solver([dt] * (T - 1), [ct] * (T - 1) + [cT], [D.Constraint()] * (T - 1) + [ok_T], bounds, batch=1)
+    assert s.nlp.num_constraint == (T - 1) * n + n
+    with pytest.raises(_lib.DtoError) as e:
+        D.Solver([dt] * (T - 1), [ct] * (T - 1) + [cT], [D.Constraint()] * (T - 1) + [bad_T], bounds, batch=1).nlp.num_constraint
+    assert "uses variable 3" in str(e.value)
+
+
+def test_lone_scaling_is_an_error():
+    """eval_hessian_lagrangian(H, z, scaling=2.0) without duals must not silently keep an old sigma."""
+    s = D.solver_from(M.build_pendulum(D), batch=1)
+    H = np.empty((1, s.nlp.num_hessian))
+    with pytest.raises(ValueError):
+        s.nlp.eval_hessian_lagrangian(H, None, scaling=2.0)
+    J = np.empty((1, s.nlp.num_jacobian))
+    with pytest.raises(ValueError):
+        s.nlp.eval_jacobian_hessian(J, H, None, scaling=2.0)
