@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
         "dto_kkt_device_pointer": (vp, [vp, C.c_int, C.c_int]),
         "dto_kkt_set_primal_reg": (C.c_int, [vp, vp]),
         "dto_kkt_inertia": (C.c_int, [vp, vp]),
+        "dto_kkt_launch_subset": (C.c_int, [vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     const int grp = lane / G, i = lane % G;
     const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * SM::NG + grp;
     const bool valid = b0 < a.B;
-    const int64_t b = valid ? b0 : a.B - 1;          // idle groups shadow the last problem, stores masked
+    const int64_t bs = valid ? b0 : a.B - 1;         // idle groups shadow the last slot, stores masked
+    const int64_t b = a.pidx ? (int64_t)a.pidx[bs] : bs;   // subset launch: slot -> problem
     const double* Hb = a.H + b * a.nnz_H;
     const double* Jb = a.J + b * a.nnz_J - a.nnz_H;  // see load_rows
     const double* hb = a.rhs + b * a.dim;
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     const int grp = lane / G, i = lane % G;
     const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * SM::NG + grp;
     const bool valid = b0 < a.B;
-    const int64_t b = valid ? b0 : a.B - 1;
+    const int64_t bs = valid ? b0 : a.B - 1;
+    const int64_t b = a.pidx ? (int64_t)a.pidx[bs] : bs;
     const double* Hb = a.H + b * a.nnz_H;
     const double* Jb = a.J + b * a.nnz_J - a.nnz_H;  // see load_rows
     const double* hb = a.rhs + b * a.dim;
@@ -485,10 +487,12 @@ __global__ void kkt_assemble_kernel(const dto_kkt_args a, int64_t problem, doubl
 // for each variable i: cy = sum over constraint rows j ascending of C[j,i]*y[j]; h[i] = grad[i] + cy.
 __global__ void kkt_rhs_kernel(const dto_kkt_args a)
 {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= a.B * a.dim) return;
-    const int64_t b = gid / a.dim;
-    const int i = (int)(gid - b * a.dim);
+    const int64_t gid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid0 >= a.B * a.dim) return;
+    const int64_t slot = gid0 / a.dim;
+    const int i = (int)(gid0 - slot * a.dim);
+    const int64_t b = a.pidx ? (int64_t)a.pidx[slot] : slot;
+    const int64_t gid = b * a.dim + i;
     double h;
     if (i < a.N_z) {
         const double* Jb = a.J + b * a.nnz_J;

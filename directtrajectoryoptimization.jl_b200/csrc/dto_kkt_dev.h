@@ -44,6 +44,9 @@ typedef struct dto_kkt_args {
      * diagonal shift of the VARIABLE rows of problem b is preg[b] instead of the scalar primal_reg          */
     const double* preg;  /* [B] or NULL                                                        */
     int32_t* nneg;       /* [B] or NULL: number of negative pivots of D (inertia; N_c when K is quasi-definite) */
+    /* subset launch (a solver re-factorising only the problems whose inertia was wrong): when non-NULL, slot s of
+     * the launch works on problem pidx[s] and B is the number of slots; every array above stays indexed by problem */
+    const int32_t* pidx; /* [B] or NULL                                                        */
 } dto_kkt_args;
 
 /* The factor kernel is instantiated for a few bounds BW on the half bandwidth; a column of L is stored

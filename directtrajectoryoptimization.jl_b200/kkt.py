@@ -83,6 +83,10 @@ class KKTSystem:
         g, c, J, H resident on the device; 2 callbacks only."""
         _lib.check(_lib.lib().dto_kkt_launch(self._h, int(with_callbacks)))
 
+    def launch_subset(self, idx_device_ptr: int, count: int) -> None:
+        """Linear algebra only (as launch(0)) for `count` problems whose int32 numbers sit at a DEVICE address."""
+        _lib.check(_lib.lib().dto_kkt_launch_subset(self._h, C.c_void_p(int(idx_device_ptr)), int(count)))
+
     def set_primal_reg(self, reg=None) -> None:
         """Per-problem primal regularisation [B] (inertia control); None: back to the scalar of the constructor."""
         if reg is None:

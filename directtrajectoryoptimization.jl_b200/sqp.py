@@ -76,8 +76,10 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
          be.B, be.N_z, be.N_c
          be.free                     [N_z] 0/1 mask: 0 = variable pinned by equal bounds (its step is zero)
          be.callbacks(z, lam, lamH, delta) -> f [B], g [B,N_z], c [B,N_c]  (leaves J, H(z, lamH) and a first solve with delta ready for `newton`)
-         be.newton(delta)            -> sol [B, N_z+N_c] = K^-1 [g + J'lam; c], nneg [B] negative pivots,
-                                        rz [B,N_z] = g + J'lam   with per-problem primal regularisation delta [B]
+         be.newton(delta, mask=None) -> sol [B, N_z+N_c] = K^-1 [g + J'lam; c], nneg [B] negative pivots,
+                                        rz [B,N_z] = g + J'lam   with per-problem primal regularisation delta [B];
+                                        with a mask only those rows have to be recomputed (the others are ignored)
+         be.newton_soc(c_soc, delta, mask) -> sol with the constraint right-hand side c_soc (masked rows)
          be.objective_constraint(z)  -> f [B], c [B,N_c]
     All arrays are [B, ...] and stay wherever `xp` keeps them."""
     o = options or SQPOptions()
@@ -123,7 +125,7 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             nxt = xp.where(first, xp.maximum(start, 2.0 * delta), xp.minimum(xp.full((B,), o.reg_max), grow * delta))
             delta = xp.where(bad, nxt, delta)
             first = first & ~bad
-            sol2, nneg2, _ = be.newton(delta)
+            sol2, nneg2, _ = be.newton(delta, bad)     # only the problems in `bad` need the new factorisation
             sol = xp.where_rows(bad, sol2, sol)
             nneg = xp.where(bad, nneg2, nneg)
             bad = ((nneg != N_c) | ~xp.finite_rows(sol)) & ~done
@@ -150,6 +152,13 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
         soc_used = xp.zeros_bool((B,))
         accepted = xp.copy_bool(done) | bad     # converged problems and failed factorisations do not move
         for ls in range(o.max_backtrack):
+            if ls >= 1 and getattr(be, "backtrack", None) is not None:
+                # the remaining rounds in one call (device: a replayed CUDA graph of exactly the operations below,
+                # no host round trip per round; rounds after every problem was accepted change nothing)
+                r = be.backtrack(z, lam, dz, dlam, nu, phi0, slope, alpha, accepted, o.armijo, o.max_backtrack - ls)
+                if r is not None:
+                    z, lam, alpha, accepted = r
+                    break
             zt = z + alpha[:, None] * dz
             ft, ct = be.objective_constraint(zt)
             phit = ft + nu * xp.sum_abs_rows(ct)
@@ -165,7 +174,7 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
                 # right-hand side c(z) + c(z + dz) and try that step once before backtracking
                 need = ~accepted & (xp.sum_abs_rows(ct) >= c1)
                 if xp.any(need):
-                    sol_s = be.newton_soc(c + ct, delta)
+                    sol_s = be.newton_soc(c + ct, delta, need)
                     dzs = -sol_s[:, :N_z] * free
                     zs = z + dzs
                     fs, cs = be.objective_constraint(zs)
@@ -314,6 +323,7 @@ class DeviceBackend:
         self.stream = torch.cuda.current_stream(dev)
         nlp.set_stream(self.stream.cuda_stream, 0)
         self.launches0 = nlp.launch_count()
+        self._graph = None          # (CUDAGraph, static buffers, armijo) of one backtracking round; False = capture unavailable
 
     def close(self):
         self.kkt.close()
@@ -337,21 +347,34 @@ class DeviceBackend:
         t = self.torch
         return self.d_sol.clone(), self.d_nneg.to(t.float64), self.d_rhs[:, :self.N_z].clone()
 
-    def newton(self, delta):
+    def _relaunch(self, mask):
+        """linear algebra again: for every problem, or (lock step would otherwise make one bad problem re-factor the
+        whole batch) only for the problems of `mask` -- dto_kkt_launch_subset; the others keep their solution"""
+        if mask is None:
+            self.kkt.launch(0)
+            return
+        self._idx = mask.nonzero().flatten().to(self.torch.int32)      # (kept alive until the next launch)
+        n = int(self._idx.numel())
+        if n * 2 >= self.B:
+            self.kkt.launch(0)
+        elif n > 0:
+            self.kkt.launch_subset(self._idx.data_ptr(), n)
+
+    def newton(self, delta, mask=None):
         with self.torch.cuda.stream(self.stream):
             if not self._fresh:                         # re-factor with the new per-problem regularisation
                 self.d_reg.copy_(delta)
-                self.kkt.launch(0)
+                self._relaunch(mask)
             self._fresh = False
             return self._solution()
 
-    def newton_soc(self, c_soc, delta):
+    def newton_soc(self, c_soc, delta, mask=None):
         """second-order correction: same K, constraint right-hand side c_soc (the device c is overwritten: the
         iteration's own copy lives in the solver)"""
         with self.torch.cuda.stream(self.stream):
             self.d_c.copy_(c_soc)
             self.d_reg.copy_(delta)
-            self.kkt.launch(0)
+            self._relaunch(mask)
             self._fresh = False
             return self.d_sol.clone()
 
@@ -362,3 +385,61 @@ class DeviceBackend:
             self.nlp.launch(self._K[0])
             self.nlp.launch(self._K[1])
             return self.d_f.clone(), self.d_c.clone()
+
+    # ---- backtracking rounds as one replayed CUDA graph -------------------------------------------------------
+    def _round(self, S, armijo):
+        """One backtracking round on the static buffers S: the very statements of the loop in `solve`."""
+        t = self.torch
+        t.add(S["z"], S["alpha"][:, None] * S["dz"], out=self.d_z)       # zt = z + alpha dz, straight into the device z
+        self.nlp.launch(self._K[0])
+        self.nlp.launch(self._K[1])
+        phit = self.d_f + S["nu"] * self.d_c.abs().sum(dim=1)
+        ok = (phit <= S["phi0"] + armijo * S["alpha"] * S["slope"]) & ~S["accepted"]
+        S["z"].copy_(t.where(ok[:, None], self.d_z, S["z"]))
+        S["lam"].copy_(t.where(ok[:, None], S["lam"] + S["alpha"][:, None] * S["dlam"], S["lam"]))
+        S["accepted"].logical_or_(ok)
+        S["alpha"].copy_(t.where(S["accepted"], S["alpha"], 0.5 * S["alpha"]))
+
+    def _capture(self, armijo):
+        t = self.torch
+        dev = self.xp.device
+        f64 = dict(dtype=t.float64, device=dev)
+        S = {"z": t.zeros((self.B, self.N_z), **f64), "dz": t.zeros((self.B, self.N_z), **f64), "lam": t.zeros((self.B, self.N_c), **f64),
+             "dlam": t.zeros((self.B, self.N_c), **f64), "nu": t.ones((self.B,), **f64), "phi0": t.zeros((self.B,), **f64),
+             "slope": t.zeros((self.B,), **f64), "alpha": t.ones((self.B,), **f64), "accepted": t.ones((self.B,), dtype=t.bool, device=dev)}
+        side = t.cuda.Stream(device=dev)
+        side.wait_stream(self.stream)
+        self.nlp.set_stream(side.cuda_stream, 0)
+        try:
+            with t.cuda.stream(side):
+                for _ in range(2):                       # warm-up outside the capture (lazy allocations, plan tables)
+                    self._round(S, armijo)
+            side.synchronize()
+            g = t.cuda.CUDAGraph()
+            with t.cuda.graph(g, stream=side):
+                self._round(S, armijo)
+        finally:
+            self.nlp.set_stream(self.stream.cuda_stream, 0)
+        self.stream.wait_stream(side)
+        return g, S
+
+    def backtrack(self, z, lam, dz, dlam, nu, phi0, slope, alpha, accepted, armijo, rounds):
+        if self._graph is False:
+            return None
+        try:
+            if self._graph is None or self._graph[2] != armijo:
+                g, S = self._capture(armijo)
+                self._graph = (g, S, armijo)
+        except Exception as e:  # noqa: BLE001 - e.g. a driver that cannot capture: the eager loop of `solve` runs instead
+            import warnings
+            warnings.warn(f"sqp: CUDA-graph capture of the backtracking round failed ({e}); using the eager loop")
+            self._graph = False
+            self.backtrack = None
+            return None
+        g, S, _ = self._graph
+        for k, v in (("z", z), ("lam", lam), ("dz", dz), ("dlam", dlam), ("nu", nu), ("phi0", phi0), ("slope", slope), ("alpha", alpha),
+                     ("accepted", accepted)):
+            S[k].copy_(v)
+        for _ in range(rounds):
+            g.replay()
+        return S["z"].clone(), S["lam"].clone(), S["alpha"].clone(), S["accepted"].clone()

@@ -215,6 +215,10 @@ int dto_kkt_launch(dto_kkt* k, int with_callbacks);
  * the scalar primal_reg problem by problem (NULL: back to the scalar); dto_kkt_inertia returns the number of
  * negative pivots of D per problem for the last factorisation (N_c when K is quasi-definite). */
 int dto_kkt_set_primal_reg(dto_kkt* k, const double* reg /* [B] or NULL */);
+/* dto_kkt_launch(k, 0) for a subset of the problems of a one-shard batch (the ones whose inertia was wrong, or that
+ * need a second-order correction): idx is a DEVICE pointer to `count` int32 problem numbers; all other problems keep
+ * their right-hand side, factor, solution and pivot count. */
+int dto_kkt_launch_subset(dto_kkt* k, const int32_t* idx_device, int64_t count);
 int dto_kkt_inertia(dto_kkt* k, int32_t* nneg /* [B] */);
 /* which = 0: h [B][dim]; 1: sol [B][dim] (device -> host, after a solve) */
 int dto_kkt_get(dto_kkt* k, int which, double* out);

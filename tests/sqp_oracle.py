@@ -93,7 +93,7 @@ class OracleBackend:
         h = np.concatenate([self.cur["g"][b] + Jd.T @ self.lam[b], self.cur["c"][b]])
         return K, h
 
-    def newton_soc(self, c_soc, delta):
+    def newton_soc(self, c_soc, delta, mask=None):
         saved = self.cur["c"]
         self.cur["c"] = np.asarray(c_soc)
         try:
@@ -101,7 +101,7 @@ class OracleBackend:
         finally:
             self.cur["c"] = saved
 
-    def newton(self, delta):
+    def newton(self, delta, mask=None):
         n, m = self.N_z, self.N_c
         sol = np.zeros((self.B, n + m))
         nneg = np.zeros(self.B)

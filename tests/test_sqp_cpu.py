@@ -69,7 +69,7 @@ def test_inertia_control_regularises_an_indefinite_hessian():
             J = np.array([[0.0, 1.0, 1.0]])
             return np.block([[H, J.T], [J, -1e-9 * np.eye(1)]]), J
 
-        def newton(self, delta):
+        def newton(self, delta, mask=None):
             self.deltas.append(delta.copy())
             sol, nneg, rz = np.zeros((2, 4)), np.zeros(2), np.zeros((2, 3))
             for b in range(2):
@@ -78,7 +78,7 @@ def test_inertia_control_regularises_an_indefinite_hessian():
                 sol[b], nneg[b] = band_ldl_solve(K, np.concatenate([rz[b], self.c[b]]), np.arange(4), 3)
             return sol, nneg, rz
 
-        def newton_soc(self, c_soc, delta):
+        def newton_soc(self, c_soc, delta, mask=None):
             saved, self.c = self.c, c_soc
             try:
                 return self.newton(delta)[0]
