@@ -147,6 +147,9 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
         }
         cp_async_commit();
     };
+    // inertia: lane i owns column j = blk*W + i, slot 0 of the stored column is the pivot d_j; one load per lane
+    // and block here instead of a compare + add per elimination step in the factor loop (padding rows: d = 1)
+    int neg = 0;
     auto read_cols = [&](int blk, double (&C)[W], double& acc) {
         const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
 #pragma unroll
@@ -155,6 +158,7 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
             C[w] = (q >= 1 && q <= BW) ? sl[i * LW + q] : 0.0;   // (LW-1) odd => conflict-free over the lanes
         }
         acc = sl[W * LW + i];
+        neg += sl[i * LW] < 0.0 ? 1 : 0;
     };
     double xa, xp = 0.0;
     issue_cols(nblk - 1);
@@ -192,6 +196,11 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
         xa = xp;
     }
     cp_async_wait<0>();
+    if (a.nneg != nullptr) {   // number of negative pivots of the whole factor: sum over the group's lanes
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) neg += __shfl_xor_sync(0xffffffffu, neg, o, G);
+        if (valid && i == 0) a.nneg[b] = neg;
+    }
 }
 
 // One problem per group of W lanes (two problems per warp for W = 16). Row block = W rows.
@@ -226,7 +235,6 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     double ra, rb = 0.0, rc = 0.0, regc = 0.0;
     int32_t nidx[W];                                  // gather indices of the rows two blocks ahead
     load_rows<W>(a, Hb, Jb, 0, i, A, b);
-    int neg = 0;   // negative pivots of D so far (every lane of the group sees every pivot): the inertia of K
     ra = rhs_entry(a, b, a.iperm[i], hb, valid);
     if (nblk > 1) {
         load_rows<W>(a, Hb, Jb, 1, i, Bv, b);
@@ -279,7 +287,6 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
             if (inA) vs[i - s - 1] = vA;
             if (hasB && inB) vs[i + G - s - 1] = vB;
             const double d = shfl_g<G>(A[p], s);
-            neg += d < 0.0 ? 1 : 0;
             const double dinv = 1.0 / d;
             const double lA = vA * dinv;
             const double lB = vB * dinv;
@@ -324,7 +331,6 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     }
     __syncwarp();
     __threadfence_block();
-    if (a.nneg != nullptr && valid && i == 0) a.nneg[b] = neg;
 
     kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
 }
@@ -378,7 +384,6 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     double rn1 = 0.0, regn1 = 1.0, rn2 = 0.0, regn2 = 1.0;   // rhs / diagonal shift of this lane's rows in blocks blk+1, blk+2
     int32_t nidx[W];
     load_rows<W>(a, Hb, Jb, 0, i, R, b);
-    int neg = 0;   // negative pivots seen so far (every lane of the group sees every pivot)
     rr = rhs_entry(a, b, a.iperm[i], hb, valid);
     auto load_idx = [&](int blk) {
         if (blk < nblk) {
@@ -423,7 +428,6 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
             vs[(i - s - 1) & (W - 1)] = v;                       // lane s (v = 0) lands on the free slot W-1 ...
             if (i == s) vs[W - 1] = rr;                          // ... which carries y_j instead
             const double d = shfl_g<G>(R[p], s);
-            neg += d < 0.0 ? 1 : 0;
             const double dinv = 1.0 / d;
             const double l = v * dinv;
             const int qi = (i - s) & (W - 1);                   // row - j
@@ -466,7 +470,6 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     cp_async_wait<0>();
     __syncwarp();
     __threadfence_block();
-    if (a.nneg != nullptr && valid && i == 0) a.nneg[b] = neg;
     kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
 }
 
