@@ -48,7 +48,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 2, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_compute": 8, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 1, "ws_split_gen": 0, "ws_hint": 0, "ws_pdl": 1}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 2, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_compute": 8, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 1, "ws_split_gen": 0, "ws_hint": 0, "ws_pdl": 1, "live_cap": 56}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -387,7 +387,7 @@ def _emit_element_dag(el: ElementSpec, k: int, out: List[str], stats: dict, cpoo
             # fast path: one basic block; slow path (library sin/cos, IEEE division) only when an argument
             # left the domain of the branch-free functions
             chunks.append("    unsigned dto_bad = 0u;")
-            chunks.extend(emit(g, outputs, load, cpool=cpool, order=_tuning().get("emit", 0), bf=True))
+            chunks.extend(emit(g, outputs, load, cpool=cpool, order=_tuning().get("emit", 0), bf=True, live_cap=_tuning().get("live_cap", 56)))
             chunks.append("    if (__builtin_expect(dto_bad != 0u, 0)) {")
             chunks.extend(emit(g, outputs, load, indent="        ", prefix="s", cpool=cpool, order=_tuning().get("emit", 0)))
             chunks.append("    }")

@@ -740,7 +740,7 @@ def _needs_pool(v: float) -> bool:
 
 def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], str], indent: str = "    ",
          prefix: str = "t", cpool: Optional[Dict[float, int]] = None, cname: str = "dto_k", order: int = 0,
-         bf: bool = False) -> List[str]:
+         bf: bool = False, live_cap: int = 56) -> List[str]:
     """Straight-line C for the nodes reachable from `outputs` [(lhs, node)], DFS post-order in
     output order (keeps live ranges short); sin/cos of one argument become one sincos().
     bf=True: sin/cos/reciprocal use the branch-free device functions dto_sincos_bf / dto_rcp_bf, which
@@ -830,7 +830,7 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
             name[n] = nm
             lines.append(f"{indent}const double {nm} = {op}({ref(a[0])});")
 
-    if order == 2:
+    if order in (2, 3):
         # register-pressure-aware list scheduling: among the ready nodes pick the one that retires the
         # most live values (last uses) -- ptxas largely keeps source order for long FP64 blocks, so
         # the emitted order decides how many registers the ~1000-instruction knot program needs
@@ -871,16 +871,31 @@ def emit(g: Graph, outputs: List[Tuple[str, int]], load: Dict[Tuple[str, int], s
                     stored.add(lhs)
 
         flush_outputs()
+        # order 3: critical-path-first list scheduling under a cap on live values -- two in-order warps per
+        # sub-partition cannot hide the FP64 latency by themselves, so independent chains are interleaved in the
+        # SOURCE order (ptxas keeps long FP64 blocks largely in order); above the cap the pressure rule takes over
+        height: Dict[int, int] = {}
+        if order == 3:
+            lat = {"rcp": 6, "sin": 12, "cos": 12, "powi": 2}
+            for n in reversed(nodes):
+                height[n] = lat.get(g.op[n], 1) + max([height[c_] for c_ in consumers[n]], default=0)
+        live = 0
         while ready:
             best, best_key = None, None
+            over = order == 3 and live >= live_cap
             for n in ready:
                 frees = sum(1 for a in set(ops_of[n]) if uses[a] == 1)
                 creates = 0 if (not consumers[n]) else 1
-                # prefer: most net frees, then consumers of the value defined last (chains), then source order
-                key = (frees - creates, 1 if last_pick in ops_of[n] else 0, -order_idx[n])
+                if order == 3 and not over:
+                    # longest remaining path first; among equals the one that frees most, not the chain just extended
+                    key = (height[n], frees - creates, 0 if last_pick in ops_of[n] else 1, -order_idx[n])
+                else:
+                    # prefer: most net frees, then consumers of the value defined last (chains), then source order
+                    key = (frees - creates, 1 if last_pick in ops_of[n] else 0, -order_idx[n])
                 if best_key is None or key > best_key:
                     best, best_key = n, key
             n = best
+            live += (1 if consumers[n] else 0) - sum(1 for a in set(ops_of[n]) if uses[a] == 1)
             ready.remove(n)
             define(n)
             if g.op[n] in ("sin", "cos") and g.args[n][0] in paired:  # sincos defines both
