@@ -437,12 +437,15 @@ class Solver:
             for k_, v in (options or {}).items():
                 setattr(o, k_, v)
             be = sqp.DeviceBackend(self.nlp, dual_reg=o.dual_reg)
+            res = None
             try:
                 z0 = be.torch.as_tensor(self._initial, device=be.xp.device)
                 res = sqp.solve(be, z0, options=o, record=record_iterates)
                 Z = res.z.cpu().numpy()
-                self.sqp_launches = self.nlp.launch_count() - be.launches0
+                self.sqp_launches = res.backend.total_launches()
             finally:
+                if res is not None and res.backend is not be:
+                    res.backend.close()
                 be.close()
             self.nlp.set_x(Z)
             self.results, self.iterates, self.broker = res, res.history, None

@@ -56,11 +56,16 @@ class SQPOptions:
     lm_shrink: float = 0.25
     lm_grow_below: float = 0.3
     lm_zero: float = 1.0e-10
+    repack: bool = False               # drop converged problems from the batch once they are half of it (they ride along in
+    repack_min: int = 4096             #   lock step otherwise); never below repack_min problems. Off by default: at B = 4096 an
+                                       #   iteration is bound by its ~60 launches and the latency of one banded factorisation, not
+                                       #   by the batch size, so a smaller batch is no faster (measured 1.80 vs 1.53 s)
     exact_below: float = 1.0           # ||c||_inf under which the exact Hessian of the Lagrangian is used
 
 
 class SQPResult:
-    def __init__(self, z, lam, iterations, converged, constraint_violation, dual_residual, objective, history):
+    def __init__(self, z, lam, iterations, converged, constraint_violation, dual_residual, objective, history, backend=None):
+        self.backend = backend                  # the backend in use at the end (a smaller one after re-packing): close it
         self.z, self.lam = z, lam
         self.iterations = iterations            # per problem: iterations until it converged (or max_iter)
         self.converged = converged
@@ -96,7 +101,20 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
     f = cv = dr = None
     exact = xp.zeros((B,))
     lm = xp.full((B,), o.lm_first)
+    # results in the caller's problem order; `ids` = original problem number of every row of the working batch
+    B0 = B
+    ids = xp.arange(B0)
+    out = dict(z=xp.copy(z), lam=xp.copy(lam), iters=xp.full((B0,), float(o.max_iter)), done=xp.zeros_bool((B0,)),
+               cv=xp.zeros((B0,)), dr=xp.zeros((B0,)), f=xp.zeros((B0,)))
+
+    def flush(rows):
+        """current values of the working rows `rows` (boolean mask) -> result arrays"""
+        sel = ids[rows]
+        for key, val in (("z", z), ("lam", lam), ("iters", iters), ("done", done), ("cv", cv), ("dr", dr), ("f", f)):
+            out[key][sel] = val[rows]
+
     for it in range(o.max_iter):
+        B = be.B
         # Hessian of the Lagrangian with the multipliers of the problems that are close to feasible; the others
         # use the objective's Hessian only (Gauss-Newton): far from the constraint manifold the multiplier
         # estimates of a swing-up are huge and their curvature term makes H wildly indefinite
@@ -114,8 +132,22 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
         if record:
             history.append(dict(it=it, z=xp.to_numpy(z), lam=xp.to_numpy(lam), f=xp.to_numpy(f), cv=xp.to_numpy(cv),
                                 dr=xp.to_numpy(dr), done=xp.to_numpy(done)))
-        if xp.all(done):
+        n_done = xp.count(done)
+        if n_done == B:
             break
+        if o.repack and not record and 2 * n_done >= B and B - n_done >= o.repack_min and getattr(be, "shrink", None) is not None:
+            # converged problems leave the batch: their rows go to the result arrays, the rest is re-packed into a
+            # smaller batch (problems are independent, every kernel and every row-wise update gives the same bits
+            # for a problem wherever it sits in the batch)
+            flush(done)
+            keep = ~done
+            be = be.shrink(keep)
+            z, lam, f, g, c, sol, nneg, rz, cv, dr = (v[keep] for v in (z, lam, f, g, c, sol, nneg, rz, cv, dr))
+            delta, delta_last, nu, iters, exact, lm, ids = (v[keep] for v in (delta, delta_last, nu, iters, exact, lm, ids))
+            B = be.B
+            done = xp.zeros_bool((B,))
+            be.callbacks(z, lam, lam * exact[:, None], delta)   # same state as before on the smaller batch (J, H, factor):
+            be.newton(delta)                                    # deterministic, so g, c, sol ... above stay valid
         bad = ((nneg != N_c) | ~xp.finite_rows(sol)) & ~done
         tries = 0
         first = xp.ones_bool((B,))
@@ -196,8 +228,9 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             history[-1].update(alpha=xp.to_numpy(alpha), delta=xp.to_numpy(delta), nu=xp.to_numpy(nu), stuck=xp.to_numpy(stuck),
                                slope=xp.to_numpy(slope), soc=xp.to_numpy(soc_used))
         delta_last = xp.where(stuck | bad, xp.maximum(xp.full((B,), o.reg_first), o.reg_inc * xp.maximum(delta_last, delta)), delta_last)
-    iters = xp.where(done, iters, xp.full((B,), float(o.max_iter)))
-    return SQPResult(z, lam, iters, done, cv, dr, f, history)
+    iters = xp.where(done, iters, xp.full((be.B,), float(o.max_iter)))
+    flush(xp.ones_bool((be.B,)))
+    return SQPResult(out["z"], out["lam"], out["iters"], out["done"], out["cv"], out["dr"], out["f"], history, backend=be)
 
 
 # --------------------------------------------------------------------------------------- array namespaces
@@ -258,6 +291,12 @@ class _XP:
     def finite_rows(self, a):
         return self.m.isfinite(a).all(dim=1) if self.is_torch else self.m.isfinite(a).all(axis=1)
 
+    def arange(self, n):
+        return self.m.arange(n, device=self.device) if self.is_torch else self.m.arange(n)
+
+    def count(self, a):
+        return int(a.sum())
+
     def all(self, a):
         return bool(a.all())
 
@@ -302,6 +341,9 @@ class DeviceBackend:
         if np.any(np.isfinite(lo) | np.isfinite(up)):
             raise NotImplementedError("sqp: bounds on variables are outside this solver's scope (pin end points with stage constraints)")
         self.free = torch.ones(self.N_z, dtype=torch.float64, device=dev)
+        self._dual_reg = dual_reg
+        self._owned_nlp = None      # a batch created by shrink() (closed with this backend)
+        self._launches_before = 0
         self.kkt = KKTSystem(nlp, 0.0, dual_reg)
         self._K = (K_OBJECTIVE, K_CONSTRAINT)
         view = lambda arr, shape: torch.as_tensor(_CudaArray(nlp.device_pointer(arr, 0), shape), device=dev)  # noqa: E731
@@ -327,6 +369,33 @@ class DeviceBackend:
 
     def close(self):
         self.kkt.close()
+        if self._owned_nlp is not None:
+            self._owned_nlp.close()
+            self._owned_nlp = None
+
+    def total_launches(self) -> int:
+        return self._launches_before + self.nlp.launch_count() - self.launches0
+
+    def shrink(self, keep):
+        """A backend over the problems of the boolean mask `keep` only: a new, smaller batch of the same shape (static
+        tables and model library are shared), per-problem parameters copied device to device."""
+        from .evaluator import A_W
+        t = self.torch
+        idx = keep.nonzero().flatten()
+        n = int(idx.numel())
+        nlp2 = self.nlp.new_batch(batch=n)
+        dev = self.xp.device
+        if self.nlp.num_parameter:
+            nw = self.nlp.num_parameter
+            src = t.as_tensor(_CudaArray(self.nlp.device_pointer(A_W, 0), (self.B, nw)), device=dev)
+            dst = t.as_tensor(_CudaArray(nlp2.device_pointer(A_W, 0), (n, nw)), device=dev)
+            dst.copy_(src[idx])
+            t.cuda.current_stream(dev).synchronize()
+        be2 = DeviceBackend(nlp2, dual_reg=self._dual_reg)
+        be2._owned_nlp = nlp2
+        be2._launches_before = self.total_launches()
+        self.close()
+        return be2
 
     def callbacks(self, z, lam, lam_hess, delta):
         """f, g, c at z; J and H(z, lam_hess) stay on the device; first KKT solve with the damping `delta` and the

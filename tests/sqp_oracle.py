@@ -56,6 +56,12 @@ class OracleBackend:
         hc = np.array([c for _, c in self.hs]) - 1
         self._idx = (jr, jc, hr, hc)
 
+    def shrink(self, keep):
+        import copy
+        other = copy.copy(self)
+        other.B = int(np.count_nonzero(keep))
+        return other
+
     def _eval(self, z, lam, what):
         B = z.shape[0]
         if self.co is not None:

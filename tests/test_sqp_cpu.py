@@ -94,3 +94,26 @@ def test_inertia_control_regularises_an_indefinite_hessian():
     assert np.allclose(np.abs(res.z[:, 0]), 1.0, atol=1e-6) and np.allclose(res.z[:, 1:], 0.5, atol=1e-6)
     # problem 0 started where d2f/dx0^2 < 0: its regularisation was raised above 1 - 3 x0^2 at least once, problem 1's was not
     assert max(d[0] for d in be.deltas) > 0.9 and max(d[1] for d in be.deltas[:3]) == 0.0
+
+
+def test_repacking_the_batch_changes_no_result():
+    """Converged problems leave the working batch once they are half of it; every remaining problem must walk through
+    exactly the same iterates as without re-packing (bit for bit: problems are independent, updates are row-wise)."""
+    mo, mp = M.build_pendulum(O), M.build_pendulum(D)
+    osolver = O.solver_from(mo)
+    perm, bw = PK.analyze(D.solver_from(mp, batch=1).nlp)
+    B = 6
+    first = sqp.solve(OracleBackend(osolver, 2, perm=perm - 1, bw=bw, linear="band"), _guess(mo, 2, 1), options=sqp.SQPOptions(max_iter=40))
+    z0 = _guess(mo, B, 3)
+    z0[[0, 2, 5]] = first.z[0]                       # three problems start at a solution ...
+    lam0 = np.zeros((B, osolver.nlp.num_constraint))
+    lam0[[0, 2, 5]] = first.lam[0]                   # ... with its multipliers: they converge in the first iteration
+    res = {}
+    for repack in (False, True):
+        be = OracleBackend(osolver, B, perm=perm - 1, bw=bw, linear="band")
+        res[repack] = sqp.solve(be, z0, lam0, options=sqp.SQPOptions(max_iter=40, repack=repack, repack_min=1))
+    assert res[True].backend.B < B and res[False].backend.B == B       # the batch really shrank
+    assert res[True].converged.all() and np.array_equal(res[True].iterations, res[False].iterations)
+    assert res[True].iterations[0] == 0 and res[True].iterations[1] > 0
+    for k in ("z", "lam", "objective", "constraint_violation"):
+        assert np.array_equal(getattr(res[True], k), getattr(res[False], k)), k

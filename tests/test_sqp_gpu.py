@@ -79,3 +79,37 @@ def test_solver_api_runs_sqp_on_device():
     xs, us = s.get_trajectory(3)
     assert np.linalg.norm(xs[0] - mp["x1"]) < 1e-6 and np.linalg.norm(xs[-1] - mp["xT"]) < 1e-6 and len(us) == mp["T"] - 1
     s.nlp.close()
+
+
+def test_repacking_on_the_device_changes_no_result():
+    """Same property as tests/test_sqp_cpu.py on the device arm: a smaller batch of the same shape is created for the
+    unconverged problems (parameters copied device to device, CUDA graph re-captured); final iterates are bit-identical
+    to the run that keeps every problem in the batch. Half of the problems start at a solution so that they converge
+    in the first iteration and the batch really shrinks."""
+    import torch
+    mp = M.BUILDERS["pendulum"](D)
+    B = 12
+    pn0 = D.solver_from(mp, batch=2).nlp
+    be0 = sqp.DeviceBackend(pn0)
+    first = sqp.solve(be0, torch.as_tensor(_guess(mp, 2, 9), device=be0.xp.device), options=sqp.SQPOptions(max_iter=200))
+    assert bool(first.converged[0])
+    zs, ls = first.z[0].cpu().numpy(), first.lam[0].cpu().numpy()
+    be0.close(); pn0.close()
+    z0 = _guess(mp, B, 10)
+    lam0 = np.zeros((B, len(ls)))
+    z0[::2], lam0[::2] = zs, ls
+    out = {}
+    for repack in (False, True):
+        pn = D.solver_from(mp, batch=B).nlp
+        be = sqp.DeviceBackend(pn)
+        res = sqp.solve(be, torch.as_tensor(z0, device=be.xp.device), torch.as_tensor(lam0, device=be.xp.device),
+                        options=sqp.SQPOptions(max_iter=120, repack=repack, repack_min=2))
+        out[repack] = (res.z.cpu().numpy(), res.iterations.cpu().numpy(), res.converged.cpu().numpy(), res.backend.B, res.backend.total_launches())
+        if res.backend is not be:
+            res.backend.close()
+        be.close()
+        pn.close()
+    assert out[True][3] < B == out[False][3]
+    assert np.array_equal(out[True][2], out[False][2]) and np.array_equal(out[True][1], out[False][1])
+    assert np.array_equal(out[True][0], out[False][0])
+    assert out[True][4] > 0 and out[True][1][0] == 0

@@ -48,7 +48,7 @@ def run(B=4096, T=101, max_iter=300, name="acrobot", options=None):
     res = sqp.solve(be, zt, options=o)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    launches = nlp.launch_count() - l0
+    launches = res.backend.total_launches()
     Z = res.z.cpu().numpy()
     n = model["n"]
     e1 = np.linalg.norm(Z[:, :n] - model["x1"], axis=1)
@@ -59,6 +59,8 @@ def run(B=4096, T=101, max_iter=300, name="acrobot", options=None):
     conv = res.converged.cpu().numpy()
     ok = (cv < 1e-6) & (e1 < 1e-3) & (eT < 1e-3)
     f = res.objective.cpu().numpy()
+    if res.backend is not be:
+        res.backend.close()
     be.close()
     return {"workload": f"{name} swing-up T={T}, B={B}, full solves (lock-step Newton-KKT SQP, device-resident callbacks + KKT)",
             "B": B, "T": T, "max_iter": max_iter, "seconds": dt, "solves_per_s": B / dt, "knot_iterations_per_s": float(it.sum()) * T / dt,
