@@ -122,6 +122,7 @@ def lib() -> C.CDLL:
         "dto_kkt_set_primal_reg": (C.c_int, [vp, vp]),
         "dto_kkt_inertia": (C.c_int, [vp, vp]),
         "dto_kkt_launch_subset": (C.c_int, [vp, vp, i64]),
+        "dto_kkt_set_fixed": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

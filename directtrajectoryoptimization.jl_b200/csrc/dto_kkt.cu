@@ -64,6 +64,7 @@ __device__ __forceinline__ double row_shift(const dto_kkt_args& a, size_t row, i
 {
     // diagonal shift of permuted row `row`: +primal_reg (per problem when a.preg is given), -dual_reg, 1.0 on padding
     double reg = a.dreg[row];
+    if (a.rowfixed != nullptr && a.rowfixed[row]) return 1.0;   // pinned variable: identity row
     if (a.preg != nullptr) {
         const int32_t ip = a.iperm[row];
         if (ip >= 0 && ip < a.N_z) reg = a.preg[b];
@@ -85,6 +86,7 @@ __device__ __forceinline__ double rhs_entry(const dto_kkt_args& a, int64_t b, in
         double cy = 0.0;
         for (int k = a.colptr[ip]; k < a.colptr[ip + 1]; ++k) cy = __dadd_rn(cy, __dmul_rn(Jb[a.colslot[k]], yb[a.colrow[k]]));
         h = __dadd_rn(a.g[b * a.N_z + ip], cy);
+        if (a.fixed != nullptr && a.fixed[ip]) h = 0.0;
     } else {
         h = a.c[b * a.N_c + (ip - a.N_z)];
     }
@@ -504,6 +506,7 @@ __global__ void kkt_rhs_kernel(const dto_kkt_args a)
         for (int k = a.colptr[i]; k < a.colptr[i + 1]; ++k)
             cy = __dadd_rn(cy, __dmul_rn(Jb[a.colslot[k]], yb[a.colrow[k]]));
         h = __dadd_rn(a.g[b * a.N_z + i], cy);
+        if (a.fixed != nullptr && a.fixed[i]) h = 0.0;   // pinned variable: no step
     } else {
         h = a.c[b * a.N_c + (i - a.N_z)];
     }

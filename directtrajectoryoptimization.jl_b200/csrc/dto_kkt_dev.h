@@ -47,6 +47,11 @@ typedef struct dto_kkt_args {
     /* subset launch (a solver re-factorising only the problems whose inertia was wrong): when non-NULL, slot s of
      * the launch works on problem pidx[s] and B is the number of slots; every array above stays indexed by problem */
     const int32_t* pidx; /* [B] or NULL                                                        */
+    /* variables pinned by equal lower/upper bounds (Bound(state_lower = x1, state_upper = x1), test/solve.jl): their
+     * rows and columns of K are replaced by the identity (the gather table carries structural zeros there) and their
+     * right-hand-side entries by 0, so their step is exactly 0 and the others get the reduced Newton step */
+    const uint8_t* fixed;    /* [N_z] or NULL: 1 = pinned variable                             */
+    const uint8_t* rowfixed; /* [nblk*W] or NULL: 1 = permuted row belongs to a pinned variable (diagonal shift 1.0)  */
 } dto_kkt_args;
 
 /* The factor kernel is instantiated for a few bounds BW on the half bandwidth; a column of L is stored

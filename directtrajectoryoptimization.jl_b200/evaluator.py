@@ -425,8 +425,9 @@ class Solver:
         if method == "auto":
             lo, up = self.nlp.variable_bounds
             clo, cup = self.nlp.constraint_bounds
-            ok = (self.nlp.hessian_lagrangian and not np.any(np.isfinite(lo) | np.isfinite(up)) and np.array_equal(clo, cup)
-                  and self.nlp.num_shards == 1)
+            pinned = np.isfinite(lo) & (lo == up)
+            ok = (self.nlp.hessian_lagrangian and not np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)
+                  and np.array_equal(clo, cup) and self.nlp.num_shards == 1)
             method = "sqp" if ok else "broker"
         if method == "sqp":
             from . import sqp

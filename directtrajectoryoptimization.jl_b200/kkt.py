@@ -87,6 +87,16 @@ class KKTSystem:
         """Linear algebra only (as launch(0)) for `count` problems whose int32 numbers sit at a DEVICE address."""
         _lib.check(_lib.lib().dto_kkt_launch_subset(self._h, C.c_void_p(int(idx_device_ptr)), int(count)))
 
+    def set_fixed(self, fixed=None) -> None:
+        """Pinned variables (equal lower/upper bounds): boolean mask [num_variables]; their step is exactly zero."""
+        if fixed is None:
+            _lib.check(_lib.lib().dto_kkt_set_fixed(self._h, None))
+            return
+        m = np.ascontiguousarray(np.asarray(fixed).astype(np.uint8))
+        if m.shape != (self.nlp.num_variables,):
+            raise ValueError(f"fixed: expected shape ({self.nlp.num_variables},)")
+        _lib.check(_lib.lib().dto_kkt_set_fixed(self._h, m.ctypes.data_as(C.c_void_p)))
+
     def set_primal_reg(self, reg=None) -> None:
         """Per-problem primal regularisation [B] (inertia control); None: back to the scalar of the constructor."""
         if reg is None:

@@ -18,9 +18,9 @@ regularisation, convergence masks); they are written against an array namespace 
 for the product, numpy for the oracle-driven twin the parity test runs (tests/sqp_oracle.py) -- so both arms
 execute literally the same algorithm.
 
-Scope (stated plainly): equality-constrained problems with free variables (end points pinned by stage
-constraints as in examples/acrobot, examples/cartpole, examples/pendulum -- not by bounds, and no inequality
-rows). It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
+Scope (stated plainly): equality-constrained problems whose variables are free or PINNED by equal lower and upper
+bounds (end points fixed by stage constraints as in examples/acrobot, or by Bound(state_lower = x1, state_upper = x1)
+as in test/solve.jl); inequality bounds and inequality rows are rejected, not approximated. It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
 damping and Ipopt-style inertia correction of the primal regularisation; it is NOT Ipopt:
 iterate-for-iterate parity with the reference's Ipopt runs is unverifiable here and is not claimed.
 """
@@ -91,6 +91,8 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
     xp = be.xp
     B, N_z, N_c = be.B, be.N_z, be.N_c
     z = xp.copy(z0)
+    if getattr(be, "pin", None) is not None:
+        z = be.pin(z)
     lam = xp.zeros((B, N_c)) if lam0 is None else xp.copy(lam0)
     free = be.free
     delta_last = xp.zeros((B,))
@@ -338,13 +340,18 @@ class DeviceBackend:
         clo, cup = nlp.constraint_bounds
         if np.any(clo != cup):
             raise NotImplementedError("sqp: inequality constraints are outside this solver's scope")
-        if np.any(np.isfinite(lo) | np.isfinite(up)):
-            raise NotImplementedError("sqp: bounds on variables are outside this solver's scope (pin end points with stage constraints)")
-        self.free = torch.ones(self.N_z, dtype=torch.float64, device=dev)
+        fixed = np.isfinite(lo) & (lo == up)            # Bound(state_lower = x1, state_upper = x1): pinned variables
+        if np.any((np.isfinite(lo) | np.isfinite(up)) & ~fixed):
+            raise NotImplementedError("sqp: inequality bounds on variables are outside this solver's scope")
+        self.free = torch.as_tensor((~fixed).astype(np.float64), device=dev)
+        self.pinned_value = torch.as_tensor(np.where(fixed, lo, 0.0), device=dev)
+        self._fixed = fixed
         self._dual_reg = dual_reg
         self._owned_nlp = None      # a batch created by shrink() (closed with this backend)
         self._launches_before = 0
         self.kkt = KKTSystem(nlp, 0.0, dual_reg)
+        if fixed.any():
+            self.kkt.set_fixed(fixed)                   # identity rows/columns in K, zero right-hand side: their step is 0
         self._K = (K_OBJECTIVE, K_CONSTRAINT)
         view = lambda arr, shape: torch.as_tensor(_CudaArray(nlp.device_pointer(arr, 0), shape), device=dev)  # noqa: E731
         B = self.B
@@ -415,6 +422,10 @@ class DeviceBackend:
     def _solution(self):
         t = self.torch
         return self.d_sol.clone(), self.d_nneg.to(t.float64), self.d_rhs[:, :self.N_z].clone()
+
+    def pin(self, z):
+        """pinned variables take their bound value (Ipopt: fixed variables are removed from the problem)"""
+        return z * self.free + self.pinned_value
 
     def _relaunch(self, mask):
         """linear algebra again: for every problem, or (lock step would otherwise make one bad problem re-factor the

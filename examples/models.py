@@ -365,11 +365,16 @@ def test_euler_implicit(y, x, u, w):
     return y - (x + h * test_pendulum(y, u, w))
 
 
-def build_linear_general(api, T=11):
+def build_linear_general(api, T=11, reference_exact=False):
     """test/solve.jl:227-296 flavour: double integrator, linear GeneralConstraint pinning
-    the end points over the whole z; every Hessian enabled (general/dynamics ones are empty)."""
+    the end points over the whole z; every Hessian enabled (general/dynamics ones are empty).
+    reference_exact=True is the test verbatim: A = [1 1; 0 1], B = [0; 1], x1 pinned by a Bound, only xT by the
+    GeneralConstraint."""
     n, m = 2, 1
     h = 0.1
+
+    if reference_exact:
+        h = 1.0
 
     def dyn(y, x, u, w):
         A = np.array([[1.0, h], [0.0, 1.0]], dtype=object)
@@ -384,12 +389,17 @@ def build_linear_general(api, T=11):
     x1 = np.array([0.0, 0.0])
     xT = np.array([1.0, 0.0])
     nz = T * n + (T - 1) * m
-    gc = api.GeneralConstraint(lambda z, w: cat(z[0:n] - x1, z[nz - n:nz] - xT), nz, 0, evaluate_hessian=True)
+    if reference_exact:
+        gc = api.GeneralConstraint(lambda z, w: z[nz - n:nz] - xT, nz, 0, evaluate_hessian=True)
+        bounds = [api.Bound(n, m, state_lower=x1, state_upper=x1)] + [api.Bound(n, m)] * (T - 2) + [api.Bound(n, 0)]
+    else:
+        gc = api.GeneralConstraint(lambda z, w: cat(z[0:n] - x1, z[nz - n:nz] - xT), nz, 0, evaluate_hessian=True)
+        bounds = [api.Bound(n, m)] * (T - 1) + [api.Bound(n, 0)]
     return dict(
         name="linear_general", T=T, n=n, m=m,
         dynamics=[dt] * (T - 1), objective=[ct] * (T - 1) + [cT],
         constraints=[api.Constraint() for _ in range(T)],
-        bounds=[api.Bound(n, m)] * (T - 1) + [api.Bound(n, 0)],
+        bounds=bounds,
         general=gc, evaluate_hessian=True, x1=x1, xT=xT,
     )
 

@@ -215,6 +215,10 @@ int dto_kkt_launch(dto_kkt* k, int with_callbacks);
  * the scalar primal_reg problem by problem (NULL: back to the scalar); dto_kkt_inertia returns the number of
  * negative pivots of D per problem for the last factorisation (N_c when K is quasi-definite). */
 int dto_kkt_set_primal_reg(dto_kkt* k, const double* reg /* [B] or NULL */);
+/* Variables pinned by equal lower and upper bounds (Bound(state_lower = x1, state_upper = x1), /root/reference/test/solve.jl:
+ * Ipopt's fixed-variable treatment): fixed[N_z], 1 = pinned, NULL = none. Their rows and columns of K become the identity
+ * and their right-hand-side entries 0, so the solution holds a zero step for them and the reduced Newton step for the rest. */
+int dto_kkt_set_fixed(dto_kkt* k, const uint8_t* fixed /* [num_variables] or NULL */);
 /* dto_kkt_launch(k, 0) for a subset of the problems of a one-shard batch (the ones whose inertia was wrong, or that
  * need a second-order correction): idx is a DEVICE pointer to `count` int32 problem numbers; all other problems keep
  * their right-hand side, factor, solution and pivot count. */

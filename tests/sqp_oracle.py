@@ -44,7 +44,10 @@ class OracleBackend:
         self.B, self.N_z, self.N_c = B, self.o.num_variables, self.o.num_constraint
         self.xp = _XP(np)
         lo, up = self.o.variable_bounds
-        self.free = (np.asarray(lo) != np.asarray(up)).astype(np.float64)
+        lo, up = np.asarray(lo, float), np.asarray(up, float)
+        self.fixed = np.isfinite(lo) & (lo == up)
+        self.free = (~self.fixed).astype(np.float64)
+        self.pinned_value = np.where(self.fixed, lo, 0.0)
         self.dual_reg = dual_reg
         self.co = c_twin
         self.perm = perm
@@ -55,6 +58,9 @@ class OracleBackend:
         hr = np.array([r for r, _ in self.hs]) - 1
         hc = np.array([c for _, c in self.hs]) - 1
         self._idx = (jr, jc, hr, hc)
+
+    def pin(self, z):
+        return z * self.free + self.pinned_value
 
     def shrink(self, keep):
         import copy
@@ -97,6 +103,12 @@ class OracleBackend:
         Jd = np.zeros((m, n))
         Jd[jr, jc] = self.cur["J"][b]
         h = np.concatenate([self.cur["g"][b] + Jd.T @ self.lam[b], self.cur["c"][b]])
+        if self.fixed.any():          # pinned variables: identity rows / columns, zero right-hand side
+            fx = np.nonzero(self.fixed)[0]
+            K[fx, :] = 0.0
+            K[:, fx] = 0.0
+            K[fx, fx] = 1.0
+            h[fx] = 0.0
         return K, h
 
     def newton_soc(self, c_soc, delta, mask=None):

@@ -355,3 +355,38 @@ def kkt_matrix_without_reg(kkt, pn, b, reg_b):
     K = kkt.matrix(b).copy()
     K[np.arange(pn.num_variables), np.arange(pn.num_variables)] -= reg_b
     return K
+
+
+def test_pinned_variables_get_identity_rows():
+    """dto_kkt_set_fixed: variables pinned by equal bounds -- K's rows and columns of those variables are the identity,
+    their right-hand-side entries zero; the solve returns exactly 0 for them and the reduced system's solution for the
+    rest (dense reference); un-pinning restores the full system."""
+    name, kw, B = "acrobot", dict(T=9), 5
+    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, 3)
+    kkt = PK.KKTSystem(pn, primal_reg=1.0e-3, dual_reg=1.0e-3)
+    N_z = pn.num_variables
+    full = np.empty((B, kkt.dim))
+    kkt.solve(full, variables=z, scaling=sigma, duals=lam)
+    K0, h0 = kkt.matrix(2), kkt.rhs()[2]
+    fixed = np.zeros(N_z, dtype=bool)
+    fixed[[0, 1, 2, 3, N_z - 4, N_z - 2]] = True
+    kkt.set_fixed(fixed)
+    sol = np.empty((B, kkt.dim))
+    kkt.solve(sol, variables=z, scaling=sigma, duals=lam)
+    K1, h1 = kkt.matrix(2), kkt.rhs()[2]
+    fx = np.nonzero(fixed)[0]
+    Kref, href = K0.copy(), h0.copy()
+    Kref[fx, :] = 0.0
+    Kref[:, fx] = 0.0
+    Kref[fx, fx] = 1.0
+    href[fx] = 0.0
+    assert np.array_equal(K1, Kref) and np.array_equal(h1, href)
+    assert np.all(sol[:, fx] == 0.0)
+    ref = np.linalg.solve(Kref, href)
+    assert np.max(np.abs(sol[2] - ref)) <= 1e-9 * max(1.0, np.max(np.abs(ref)))
+    kkt.set_fixed(None)
+    again = np.empty_like(full)
+    kkt.solve(again, variables=z, scaling=sigma, duals=lam)
+    assert np.array_equal(again, full)
+    kkt.close()
+    pn.close()

@@ -113,3 +113,45 @@ def test_repacking_on_the_device_changes_no_result():
     assert np.array_equal(out[True][2], out[False][2]) and np.array_equal(out[True][1], out[False][1])
     assert np.array_equal(out[True][0], out[False][0])
     assert out[True][4] > 0 and out[True][1][0] == 0
+
+
+def test_reference_solve_tests_with_bound_pinned_end_points():
+    """/root/reference/test/solve.jl verbatim problem set-ups: end points pinned by Bound(state_lower = x1,
+    state_upper = x1) -- Ipopt removes such variables; here their rows/columns of K are the identity
+    (dto_kkt_set_fixed) so their step is exactly zero. (i) :227-296 "general constraint": double integrator, x1 by
+    bound, xT by a GeneralConstraint -- device iterates equal the oracle-driven twin's and meet the test's acceptance;
+    (ii) :1-138 acrobot T=101 with both end points by bounds: >= 90 % of 64 seeded problems meet the acceptance."""
+    import torch
+    kw = dict(reference_exact=True)
+    mo, mp = M.build_linear_general(O, **kw), M.build_linear_general(D, **kw)
+    B = 4
+    osolver, pn = O.solver_from(mo), D.solver_from(mp, batch=B).nlp
+    z0 = _guess(mp, B, 21)
+    perm, bw = PK.analyze(pn)
+    opts = sqp.SQPOptions(max_iter=20, dual_reg=1.0e-6)
+    ref = sqp.solve(OracleBackend(osolver, B, dual_reg=opts.dual_reg, perm=perm - 1, bw=bw, linear="band"), z0, options=opts, record=True)
+    be = sqp.DeviceBackend(pn, dual_reg=opts.dual_reg)
+    got = sqp.solve(be, torch.as_tensor(z0, device=be.xp.device), options=opts, record=True)
+    be.close()
+    assert bool(got.converged.all()) and ref.converged.all() and len(got.history) == len(ref.history)
+    Z = got.z.cpu().numpy()
+    assert np.allclose(Z, ref.z, rtol=1e-8, atol=1e-10)
+    n = mp["n"]
+    assert np.array_equal(Z[:, :n], np.tile(mp["x1"], (B, 1)))                       # pinned: exactly the bound
+    assert np.all(np.linalg.norm(Z[:, -n:] - mp["xT"], axis=1) < 1e-3)               # test/solve.jl:294-295
+    pn.close()
+    # (ii) acrobot, end points by bounds
+    ma = M.build_acrobot(D, T=101, stage_endpoint_constraints=False)
+    B = 64
+    s = D.solver_from(ma, batch=B)
+    s.initialize_states(D.linear_interpolation(ma["x1"], ma["xT"], 101))
+    rng = np.random.default_rng(4)
+    for b in range(B):
+        s.initialize_controls([rng.normal(size=1) for _ in range(100)], problem=b)
+    res = s.solve(options=dict(max_iter=300))
+    ok = 0
+    for b in range(B):
+        xs, _ = s.get_trajectory(b)
+        ok += int(np.linalg.norm(xs[0] - ma["x1"]) < 1e-3 and np.linalg.norm(xs[-1] - ma["xT"]) < 1e-3 and float(res.constraint_violation[b]) < 1e-6)
+    assert ok >= 0.9 * B, ok
+    s.nlp.close()
