@@ -48,7 +48,7 @@ def _tuning() -> Dict[str, int]:
     """Compile-time kernel tuning (part of the content hash): warps per CTA and the minimum
     resident CTAs per SM handed to __launch_bounds__ (caps registers per thread).
     Override with DTO_TUNE="warps=4,min_ctas=3"."""
-    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 2, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_compute": 8, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 1, "ws_split_gen": 0, "ws_hint": 0, "ws_pdl": 1, "live_cap": 56}
+    t = {"warps": 2, "min_ctas": 6, "gather_unroll": 4, "emit": 2, "l2_prefetch": 1, "persist": 1, "pwarps": 12, "pctas": 1, "ws": 1, "ws_hreg": 40, "ws_creg": 0, "ws_helpers": 0, "ws_compute": 8, "ws_min_ops": 0, "ws_plan": 1, "ws_all": 0, "bf": 1, "ws_split_gen": 0, "ws_hint": 0, "ws_pdl": 1, "pdl_plain": 1, "live_cap": 56}
     for kv in os.environ.get("DTO_TUNE", "").split(","):
         if "=" in kv:
             k, v = kv.split("=")
@@ -861,7 +861,7 @@ def _build_model_locked(spec: ModelSpec, hsh: str, base: str, so: str, cu: str, 
            f"-DDTO_GATHER_UNROLL={tune['gather_unroll']}", f"-DDTO_L2_PREFETCH={tune['l2_prefetch']}",
            f"-DDTO_PERSIST={tune['persist']}", f"-DDTO_PWARPS={tune['pwarps']}", f"-DDTO_PCTAS={tune['pctas']}",
            f"-DDTO_WS={tune['ws']}", f"-DDTO_WS_HREG={tune['ws_hreg']}", f"-DDTO_WS_CREG={tune['ws_creg']}",
-           f"-DDTO_WS_MIN_OPS={tune['ws_min_ops']}", f"-DDTO_WS_PLAN={tune['ws_plan']}", f"-DDTO_WS_HELPERS={tune['ws_helpers']}", f"-DDTO_WS_COMPUTE={tune['ws_compute']}", f"-DDTO_WS_ALL_MODES={tune['ws_all']}", f"-DDTO_WS_SPLIT_GEN={tune['ws_split_gen']}", f"-DDTO_WS_HINT_NS={tune['ws_hint']}", f"-DDTO_WS_PDL={tune['ws_pdl']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
+           f"-DDTO_WS_MIN_OPS={tune['ws_min_ops']}", f"-DDTO_WS_PLAN={tune['ws_plan']}", f"-DDTO_WS_HELPERS={tune['ws_helpers']}", f"-DDTO_WS_COMPUTE={tune['ws_compute']}", f"-DDTO_WS_ALL_MODES={tune['ws_all']}", f"-DDTO_WS_SPLIT_GEN={tune['ws_split_gen']}", f"-DDTO_WS_HINT_NS={tune['ws_hint']}", f"-DDTO_WS_PDL={tune['ws_pdl']}", f"-DDTO_PDL_PLAIN={tune['pdl_plain']}", "-O3", "-std=c++17", "-lineinfo", "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v",
            "-I", CSRC_DIR, "-o", so + ".tmp", cu]
     t1 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)

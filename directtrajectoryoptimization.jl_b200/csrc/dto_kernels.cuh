@@ -66,6 +66,11 @@
 #ifndef DTO_WS_PDL
 #define DTO_WS_PDL 0       /* 1: launch the ws kernel with programmatic stream serialization (prologue overlaps the previous kernel's tail) */
 #endif
+#ifndef DTO_PDL_PLAIN
+#define DTO_PDL_PLAIN 1    /* 1: the plain knot kernel is launched with programmatic stream serialization too (it waits for the
+                              previous kernel before touching data, so only launch latency overlaps: cartpole B=4096 gradient
+                              10.3 -> 9.6 us, constraint 18.7 -> 17.1, Jacobian 24.3 -> 21.7) */
+#endif
 #ifndef DTO_WS_PLAN
 #define DTO_WS_PLAN 1      /* precomputed tile-plan table for the ws kernel (0: helpers compute every tile's records) */
 #endif
@@ -155,6 +160,10 @@ __global__ void __launch_bounds__(DTO_WARPS * 32, DTO_MIN_CTAS) knot_kernel(cons
     constexpr bool DO_J = (MODE & DTO_MODE_J) != 0, DO_H = (MODE & DTO_MODE_H) != 0;
     constexpr bool HALO = DO_H && (M::HESS_HALO != 0);
     constexpr int OWN = HALO ? 31 : 32;
+#if DTO_PDL_PLAIN
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -856,6 +865,32 @@ inline int plan_persistent(dto_launch_args& b, int64_t* smem_out, int min_ops_ok
     return 0;
 }
 
+// launch with programmatic stream serialization: the kernel may be scheduled while the previous kernel of the stream
+// drains; it must execute griddepcontrol.wait before touching anything that kernel may still read or write
+template <class K>
+inline cudaError_t launch_pdl(K kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t st, const dto_launch_args& args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // not while the stream is being captured into a CUDA graph: programmatic edges made the replay of the solver's
+    // line-search graph 2x slower (3.5 vs 1.5 s for config 3); a captured launch is an ordinary kernel node
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+        cudaGetLastError();
+        cap = cudaStreamCaptureStatusNone;
+    }
+    if (cap != cudaStreamCaptureStatusNone) cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 template <class M, int MODE>
 inline int launch_knot(const dto_launch_args& a, cudaStream_t st, bool* used_ws)
 {
@@ -888,17 +923,7 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st, bool* used_ws)
             if (ctas > sms[dev]) ctas = sms[dev];
             b.ws_plan = ws_get_plan<M, MODE>(b, st);
 #if DTO_WS_PDL
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)ctas);
-            cfg.blockDim = dim3((DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32);
-            cfg.dynamicSmemBytes = (size_t)wsmem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, knot_kernel_ws<M, MODE>, b);
+            cudaError_t e = launch_pdl(knot_kernel_ws<M, MODE>, (unsigned)ctas, (DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, (size_t)wsmem, st, b);
 #else
             knot_kernel_ws<M, MODE><<<(unsigned)ctas, (DTO_WS_COMPUTE + DTO_WS_HELPERS) * 32, (size_t)wsmem, st>>>(b);
             cudaError_t e = cudaGetLastError();
@@ -968,8 +993,12 @@ inline int launch_knot(const dto_launch_args& a, cudaStream_t st, bool* used_ws)
         }
     }
 #endif
+#if DTO_PDL_PLAIN
+    cudaError_t e = launch_pdl(knot_kernel<M, MODE>, (unsigned)ctas, DTO_WARPS * 32, (size_t)smem, st, b);
+#else
     knot_kernel<M, MODE><<<(unsigned)ctas, DTO_WARPS * 32, (size_t)smem, st>>>(b);
     cudaError_t e = cudaGetLastError();
+#endif
     if (e != cudaSuccess)
         fprintf(stderr, "[dto] knot_kernel<mode %d> launch failed: %s (grid %lld, block %d, smem %lld)\n", MODE, cudaGetErrorString(e),
                 ctas, DTO_WARPS * 32, (long long)smem);
@@ -1007,6 +1036,7 @@ inline int launch(int kernel_id, const dto_launch_args* pa, void* stream)
     if (a.B == 0) return 0;
     switch (kernel_id) {
     case DTO_K_OBJECTIVE:
+        // (no programmatic launch here: measured slower for this kernel of many tiny CTAs, 10.3 -> 12.7 us)
         objective_kernel<M><<<(unsigned)((a.B + DTO_WARPS - 1) / DTO_WARPS), DTO_WARPS * 32, 0, st>>>(a);
         e = (int)cudaGetLastError();
         return e ? -e : 1;
