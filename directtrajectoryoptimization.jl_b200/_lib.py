@@ -30,6 +30,14 @@ class ShapeDesc(C.Structure):
     ]
 
 
+class SqpOptions(C.Structure):
+    """dto_sqp_options (include/dto.h): SQPOptions of sqp.py for the native solver"""
+    _fields_ = [("max_iter", C.c_int32), ("max_refactor", C.c_int32), ("max_backtrack", C.c_int32), ("soc", C.c_int32)] + [
+        (n, C.c_double) for n in ("tol_constraint", "tol_dual", "dual_reg", "reg_first", "reg_min", "reg_max", "reg_inc_first", "reg_inc",
+                                  "reg_dec", "armijo", "merit_margin", "merit_rho", "merit_min", "lm_first", "lm_min", "lm_grow", "lm_shrink",
+                                  "lm_grow_below", "lm_zero", "lam_max", "exact_below")]
+
+
 _lib = None
 
 
@@ -123,6 +131,9 @@ def lib() -> C.CDLL:
         "dto_kkt_inertia": (C.c_int, [vp, vp]),
         "dto_kkt_launch_subset": (C.c_int, [vp, vp, i64]),
         "dto_kkt_set_fixed": (C.c_int, [vp, vp]),
+        "dto_kkt_resolve": (C.c_int, [vp, vp, i64]),
+        "dto_sqp_default_options": (None, [C.POINTER(SqpOptions)]),
+        "dto_sqp_solve": (C.c_int, [vp, C.POINTER(SqpOptions)] + [vp] * 12),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

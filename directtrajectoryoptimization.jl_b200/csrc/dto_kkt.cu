@@ -475,6 +475,76 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_band_kernel_s(cons
     kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Solve again with the factor of the last factorisation: K unchanged, new right-hand side (a second-order
+// correction re-solves with c(z) + c(z + dz), Nocedal & Wright 18.3). The forward substitution reads the stored
+// columns of L block by block through the same 3-slot cp.async ring the backward solve uses and applies the
+// very operations the factor kernel fuses into its elimination steps (fma(-l, y_j, r); y_j / d_j as y_j * (1/d_j)),
+// so the solution is bit-identical to factorising again -- at a fraction of the latency: no trailing update,
+// no gather of J and H.
+template <int W, int BW>
+__global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_resolve_kernel(const dto_kkt_args a)
+{
+    constexpr int G = W;
+    using SM = KktSmem<W, BW>;
+    constexpr int LW = SM::LW;
+    extern __shared__ __align__(16) unsigned char kkt_smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int grp = lane / G, i = lane % G;
+    const int64_t b0 = ((int64_t)blockIdx.x * 4 + wib) * SM::NG + grp;
+    const bool valid = b0 < a.B;
+    const int64_t bs = valid ? b0 : a.B - 1;
+    const int64_t b = a.pidx ? (int64_t)a.pidx[bs] : bs;
+    const double* hb = a.rhs + b * a.dim;
+    const int nblk = a.nblk;
+    double* Lg = a.L + (size_t)b * a.factor_stride;
+    double* Yg = Lg + (size_t)nblk * W * LW;
+    unsigned char* gsm = kkt_smem + (size_t)(wib * SM::NG + grp) * SM::PER_GROUP;
+    auto issue = [&](int blk) {
+        if (blk < nblk) {
+            unsigned char* dst = gsm + (blk % SM::RING) * SM::SLOT;
+            const unsigned char* srcL = reinterpret_cast<const unsigned char*>(Lg + (size_t)blk * W * LW);
+#pragma unroll
+            for (int k = 0; k < LW / 2; ++k) cp_async16(dst + (k * W + i) * 16, srcL + (k * W + i) * 16);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    issue(2);
+    double ra = rhs_entry(a, b, a.iperm[i], hb, valid);
+    double rb = nblk > 1 ? rhs_entry(a, b, a.iperm[W + i], hb, valid) : 0.0;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const double rc = blk + 2 < nblk ? rhs_entry(a, b, a.iperm[(size_t)(blk + 2) * W + i], hb, valid) : 0.0;
+        cp_async_wait<2>();
+        __syncwarp();
+        const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            const bool inA = i > s && i <= s + BW;
+            const bool hasB = (s + BW >= G);
+            const bool inB = hasB && (i <= s + BW - G);
+            const double lA = inA ? sl[s * LW + (i - s)] : 0.0;
+            const double lB = inB ? sl[s * LW + (i + G - s)] : 0.0;
+            const double dinv = 1.0 / sl[s * LW];
+            const double yj = shfl_g<G>(ra, s);
+            ra = fma(-lA, yj, ra);
+            if (hasB) rb = fma(-lB, yj, rb);
+            if (i == s) ra = yj * dinv;
+        }
+        if (valid) Yg[(size_t)blk * W + i] = ra;
+        ra = rb;
+        rb = rc;
+        __syncwarp();            // every lane is done with slot blk % RING
+        issue(blk + 3);
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    __threadfence_block();
+    kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
+}
+
 template <int W>
 __global__ void kkt_assemble_kernel(const dto_kkt_args a, int64_t problem, double* __restrict__ out)
 {
@@ -574,6 +644,33 @@ extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
         if (bound == 20) e = two ? launch_band_t<32, 20>(a, st) : launch_band_s<32, 20, 8>(a, st);
         else e = launch_band_t<32, 31>(a, st);
     }
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+template <int W, int BW>
+static cudaError_t launch_resolve_t(const dto_kkt_args* a, cudaStream_t st)
+{
+    const int64_t per_block = 4 * (32 / W);
+    if (KktSmem<W, BW>::BYTES > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kkt_resolve_kernel<W, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
+        if (e != cudaSuccess) return e;
+    }
+    kkt_resolve_kernel<W, BW><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
+    return cudaGetLastError();
+}
+
+// forward + backward solve with the stored factor (every factor kernel variant writes the same layout)
+extern "C" int dto_kkt_launch_resolve(const dto_kkt_args* a, void* stream)
+{
+    if (a->B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaErrorInvalidValue;
+    const int bound = dto_kkt_bw_bound(a->W, a->bw);
+    if (a->W == 16)
+        e = bound == 6 ? launch_resolve_t<16, 6>(a, st) : bound == 9 ? launch_resolve_t<16, 9>(a, st) : bound == 12 ? launch_resolve_t<16, 12>(a, st)
+                                                                                                                  : launch_resolve_t<16, 15>(a, st);
+    else if (a->W == 32)
+        e = bound == 20 ? launch_resolve_t<32, 20>(a, st) : launch_resolve_t<32, 31>(a, st);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 

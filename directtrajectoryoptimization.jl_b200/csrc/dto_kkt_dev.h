@@ -66,6 +66,7 @@ static inline int dto_kkt_col_width(int W, int bw) { return (dto_kkt_bw_bound(W,
 /* each returns the number of kernels enqueued (>= 0) or -(cudaError_t) */
 int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream);
 int dto_kkt_launch_band(const dto_kkt_args* a, void* stream);
+int dto_kkt_launch_resolve(const dto_kkt_args* a, void* stream);   /* solve again with the stored factor */
 int dto_kkt_launch_assemble(const dto_kkt_args* a, int64_t problem, double* out, void* stream);
 
 #ifdef __cplusplus

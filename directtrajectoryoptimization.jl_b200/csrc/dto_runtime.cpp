@@ -1191,3 +1191,8 @@ extern "C" int64_t dto_launch_count(const dto_batch* b) { return b ? b->launches
 // device-side KKT consumer
 // ------------------------------------------------------------------------------------------
 #include "dto_kkt_host.inc"
+
+// ------------------------------------------------------------------------------------------
+// batched Newton-KKT solver: the caller of the callback path
+// ------------------------------------------------------------------------------------------
+#include "dto_sqp_host.inc"

@@ -1,0 +1,65 @@
+/* dto_sqp_dev.h -- launch interface between the host runtime (dto_runtime.cpp, g++) and the per-problem bookkeeping
+ * kernels of the native lock-step Newton-KKT solver (dto_sqp.cu, nvcc). Plain C. The heavy work of an iteration is
+ * done by the callback kernels (model library) and the KKT kernels (dto_kkt.cu); the kernels here are the O(B N)
+ * glue between them: row reductions, step / merit bookkeeping, masks, trial points. */
+#ifndef DTO_SQP_DEV_H
+#define DTO_SQP_DEV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dto_sqp_params {   /* SQPOptions of sqp.py, same meaning */
+    double tol_constraint, tol_dual;
+    double reg_first, reg_min, reg_max, reg_inc_first, reg_inc, reg_dec;
+    double armijo, merit_margin, merit_rho, merit_min;
+    double lm_first, lm_min, lm_grow, lm_shrink, lm_grow_below, lm_zero;
+    double exact_below, lam_max;
+    int32_t soc;
+} dto_sqp_params;
+
+enum { DTO_SQP_N_DONE = 0, DTO_SQP_N_BAD = 1, DTO_SQP_N_IDX = 2, DTO_SQP_N_NEED = 3, DTO_SQP_N_OPEN = 4, DTO_SQP_N_SOC_OK = 5,
+       DTO_SQP_N_COUNTERS = 8 };
+
+typedef struct dto_sqp_args {
+    int64_t B;
+    int32_t N_z, N_c, dim, it;
+    dto_sqp_params p;
+    /* arrays of the batch and of its KKT handle (device) */
+    double* bz;           /* [B][N_z]  the z the callback kernels read                          */
+    double* blam;         /* [B][N_c]  the lambda the Hessian / right-hand-side kernels read   */
+    const double* bf;     /* [B]       objective                                               */
+    const double* bg;     /* [B][N_z]  gradient                                                */
+    double* bc;           /* [B][N_c]  constraint values (overwritten by trial evaluations)    */
+    const double* rhs;    /* [B][dim]  [g + J'lam ; c]                                         */
+    const double* sol;    /* [B][dim]  K^-1 rhs                                                */
+    double* preg;         /* [B]       per-problem primal regularisation read by the factor kernel */
+    const int32_t* nneg;  /* [B]       negative pivots of the last factorisation              */
+    /* solver state (device) */
+    double *z, *lam, *dz, *dlam, *ckeep;
+    double *delta, *delta_last, *nu, *lm, *exact, *alpha, *phi0, *slope, *c1, *fcur, *cv, *dr;
+    int32_t* iters;
+    uint8_t *done, *bad, *accepted, *first, *need;
+    const double* free;   /* [N_z] 1 = free variable, 0 = pinned by equal bounds               */
+    int32_t* counters;    /* [DTO_SQP_N_COUNTERS]                                              */
+    int32_t* idx;         /* [B] problem list of a subset launch                               */
+} dto_sqp_args;
+
+/* each returns 0 or -(cudaError_t) */
+int dto_sqp_k_begin(const dto_sqp_args* a, void* stream);        /* bz = z, blam = lam * exact, preg = delta = lm            */
+int dto_sqp_k_set_lam(const dto_sqp_args* a, void* stream);      /* blam = lam                                              */
+int dto_sqp_k_after_first(const dto_sqp_args* a, void* stream);  /* cv, dr, exact, done, bad, ckeep, counters              */
+int dto_sqp_k_reg_next(const dto_sqp_args* a, void* stream);     /* next regularisation of the bad problems + their index list */
+int dto_sqp_k_recheck(const dto_sqp_args* a, int32_t count, void* stream);  /* bad again? for the idx list                    */
+int dto_sqp_k_direction(const dto_sqp_args* a, void* stream);    /* dz, dlam, merit quantities, first trial point          */
+int dto_sqp_k_ls_round(const dto_sqp_args* a, int32_t round, void* stream);
+int dto_sqp_k_soc_trial(const dto_sqp_args* a, int32_t count, void* stream);
+int dto_sqp_k_soc_accept(const dto_sqp_args* a, int32_t count, void* stream);
+int dto_sqp_k_end(const dto_sqp_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

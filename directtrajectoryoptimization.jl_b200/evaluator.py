@@ -429,7 +429,7 @@ class Solver:
             ok = (self.nlp.hessian_lagrangian and not np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)
                   and np.array_equal(clo, cup) and self.nlp.num_shards == 1)
             method = "sqp" if ok else "broker"
-        if method == "sqp":
+        if method in ("sqp", "native"):
             from . import sqp
             o = sqp.SQPOptions()
             ref_opts = self.options if isinstance(self.options, dict) else {}
@@ -437,6 +437,14 @@ class Solver:
                 o.max_iter = int(ref_opts["max_iter"])       # Options.max_iter (src/options.jl:9)
             for k_, v in (options or {}).items():
                 setattr(o, k_, v)
+        if method == "native":
+            if record_iterates:
+                raise ValueError("solve: record_iterates needs method='sqp' (the native solver keeps no history)")
+            res = sqp.solve_native(self.nlp, self._initial, options=o)
+            self.sqp_launches = res.stats["launches"]
+            self.results, self.iterates, self.broker = res, [], None
+            return res
+        if method == "sqp":
             be = sqp.DeviceBackend(self.nlp, dual_reg=o.dual_reg)
             res = None
             try:

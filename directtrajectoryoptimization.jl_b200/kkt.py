@@ -87,6 +87,11 @@ class KKTSystem:
         """Linear algebra only (as launch(0)) for `count` problems whose int32 numbers sit at a DEVICE address."""
         _lib.check(_lib.lib().dto_kkt_launch_subset(self._h, C.c_void_p(int(idx_device_ptr)), int(count)))
 
+    def resolve(self, idx_device_ptr: int = 0, count: int = 0) -> None:
+        """New right-hand side, solve with the factor already on the device (no factorisation): all problems, or `count`
+        problems listed at a DEVICE address. Bit-identical to launch(0) while K is unchanged."""
+        _lib.check(_lib.lib().dto_kkt_resolve(self._h, C.c_void_p(int(idx_device_ptr)) if idx_device_ptr else None, int(count)))
+
     def set_fixed(self, fixed=None) -> None:
         """Pinned variables (equal lower/upper bounds): boolean mask [num_variables]; their step is exactly zero."""
         if fixed is None:

@@ -456,11 +456,19 @@ class DeviceBackend:
 
     def newton_soc(self, c_soc, delta, mask=None):
         """second-order correction: same K, constraint right-hand side c_soc (the device c is overwritten: the
-        iteration's own copy lives in the solver)"""
+        iteration's own copy lives in the solver). K is already factorised: dto_kkt_resolve runs the forward and
+        backward solves only (bit-identical to factorising again)"""
         with self.torch.cuda.stream(self.stream):
             self.d_c.copy_(c_soc)
-            self.d_reg.copy_(delta)
-            self._relaunch(mask)
+            if mask is None:
+                self.kkt.resolve()
+            else:
+                self._idx = mask.nonzero().flatten().to(self.torch.int32)
+                n = int(self._idx.numel())
+                if n * 2 >= self.B:
+                    self.kkt.resolve()
+                elif n > 0:
+                    self.kkt.resolve(self._idx.data_ptr(), n)
             self._fresh = False
             return self.d_sol.clone()
 
@@ -529,3 +537,44 @@ class DeviceBackend:
         for _ in range(rounds):
             g.replay()
         return S["z"].clone(), S["lam"].clone(), S["alpha"].clone(), S["accepted"].clone()
+
+
+# --------------------------------------------------------------------------------------- native arm
+def solve_native(nlp, z0, lam0=None, options: Optional[SQPOptions] = None) -> SQPResult:
+    """The same algorithm as `solve`, run by libdto.so itself (dto_sqp_solve, csrc/dto_sqp_host.inc + dto_sqp.cu): the
+    vector glue that `solve` leaves to torch is a handful of warp-per-problem kernels, and the host reads back eight
+    counters per decision instead of launching ~100 small torch operations per iteration. This is what a Julia caller
+    reaches through `ccall` (julia/DTOB200.jl `solve!`); no torch is involved. numpy in, numpy out."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _lib
+    o = options or SQPOptions()
+    if o.merit_memory:
+        raise NotImplementedError("solve_native: merit_memory is an experiment of the python arm only")
+    L = _lib.lib()
+    co = _lib.SqpOptions()
+    L.dto_sqp_default_options(C.byref(co))
+    for name, _ in _lib.SqpOptions._fields_:
+        setattr(co, name, type(getattr(co, name))(getattr(o, name)))
+    B, N_z, N_c = nlp.batch, nlp.num_variables, nlp.num_constraint
+    z0 = np.ascontiguousarray(z0, dtype=np.float64)
+    if z0.shape != (B, N_z):
+        raise ValueError(f"z0 has shape {z0.shape}, expected {(B, N_z)}")
+    if lam0 is not None:
+        lam0 = np.ascontiguousarray(lam0, dtype=np.float64)
+        if lam0.shape != (B, N_c):
+            raise ValueError(f"lam0 has shape {lam0.shape}, expected {(B, N_c)}")
+    lo, up = (np.ascontiguousarray(v, dtype=np.float64) for v in nlp.variable_bounds)
+    z, lam = np.empty((B, N_z)), np.empty((B, N_c))
+    iters, done = np.empty(B, np.int32), np.empty(B, np.uint8)
+    cv, dr, f = np.empty(B), np.empty(B), np.empty(B)
+    stats = np.zeros(8, np.int64)
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    _lib.check(L.dto_sqp_solve(nlp.handle, C.byref(co), ptr(z0), ptr(lam0), ptr(lo), ptr(up), ptr(z), ptr(lam), ptr(iters), ptr(done),
+                               ptr(cv), ptr(dr), ptr(f), ptr(stats)))
+    res = SQPResult(z, lam, iters.astype(np.float64), done.astype(bool), cv, dr, f, [])
+    res.stats = dict(iterations=int(stats[0]), launches=int(stats[1]), factorisations=int(stats[2]), syncs=int(stats[3]),
+                     refactorisations=int(stats[4]), corrections=int(stats[5]), search_rounds=int(stats[6]))
+    return res

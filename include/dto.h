@@ -223,6 +223,11 @@ int dto_kkt_set_fixed(dto_kkt* k, const uint8_t* fixed /* [num_variables] or NUL
  * need a second-order correction): idx is a DEVICE pointer to `count` int32 problem numbers; all other problems keep
  * their right-hand side, factor, solution and pivot count. */
 int dto_kkt_launch_subset(dto_kkt* k, const int32_t* idx_device, int64_t count);
+/* the same without factorising again: new right-hand side (the caller changed c, g or lambda on the device), forward and
+ * backward solve with the factor of the last factorisation -- bit-identical to dto_kkt_launch(k, 0) as long as z, the
+ * Hessian's multipliers and the regularisation are unchanged, at a fraction of its latency (second-order corrections).
+ * idx_device NULL: every problem of the batch (any number of shards). */
+int dto_kkt_resolve(dto_kkt* k, const int32_t* idx_device, int64_t count);
 int dto_kkt_inertia(dto_kkt* k, int32_t* nneg /* [B] */);
 /* which = 0: h [B][dim]; 1: sol [B][dim] (device -> host, after a solve) */
 int dto_kkt_get(dto_kkt* k, int which, double* out);
@@ -234,6 +239,38 @@ int dto_kkt_factor(dto_kkt* k, int64_t problem, double* Lband, double* D);
 /* which = 0 h, 1 sol, 2 factor storage, 3 per-problem primal regularisation [shard size] (asking for it switches the
  * kernels to per-problem mode: the caller writes it on the device), 4 negative-pivot counts [shard size] int32 */
 void* dto_kkt_device_pointer(dto_kkt* k, int which, int shard);
+
+/* ---- batched solver: the caller of the callback path ----
+ * Replaces solve!(solver) (/root/reference/src/solver.jl:45-47: MOI.optimize! hands the five callbacks to Ipopt) for a
+ * whole batch at once: a lock-step line-search Newton-KKT (SQP) method whose every step is a kernel of this library --
+ * the callbacks above, the KKT consumer, and O(B N) bookkeeping kernels (csrc/dto_sqp.cu); only eight counters per
+ * synchronisation cross PCIe during the iterations. It is NOT Ipopt (no inequality handling, l1 merit line search
+ * instead of a filter); scope: equality constraints, variables free or pinned by equal bounds. The algorithm is stated
+ * in directtrajectoryoptimization.jl_b200/sqp.py (`solve`); the fields below are that file's SQPOptions. */
+typedef struct dto_sqp_options {
+    int32_t max_iter;        /* Options.max_iter (src/options.jl:9) */
+    int32_t max_refactor;    /* inertia-correction attempts per iteration */
+    int32_t max_backtrack;   /* line-search rounds per iteration */
+    int32_t soc;             /* 1: second-order correction after a rejected full step */
+    double tol_constraint;   /* converged: ||c||_inf <= tol_constraint and ||g + J'lambda||_inf <= tol_dual */
+    double tol_dual;
+    double dual_reg;         /* delta_c of K = [[H + delta I, J'], [J, -delta_c I]] */
+    double reg_first, reg_min, reg_max, reg_inc_first, reg_inc, reg_dec;   /* Ipopt's inertia-correction constants */
+    double armijo, merit_margin, merit_rho, merit_min;                     /* l1 merit line search */
+    double lm_first, lm_min, lm_grow, lm_shrink, lm_grow_below, lm_zero;   /* Levenberg-Marquardt damping of H */
+    double lam_max;          /* multiplier estimates beyond this are reset to 0 (0 = off) */
+    double exact_below;      /* ||c||_inf under which the Hessian of the Lagrangian is used (else the objective's: Gauss-Newton) */
+} dto_sqp_options;
+void dto_sqp_default_options(dto_sqp_options* o);
+/* Solves every problem of a one-shard batch from z0 [B][N_z] (lambda0 [B][N_c] or NULL = 0). lower / upper [N_z] or
+ * NULL: primal_bounds (src/data.jl:123-133); a variable with lower == upper is pinned to that value, any other finite
+ * bound -> DTO_ERR_UNSUPPORTED, as are inequality constraint rows. Outputs (each may be NULL): z [B][N_z],
+ * lambda [B][N_c], iterations [B] (max_iter where not converged), converged [B], constraint_violation [B] = ||c||_inf,
+ * dual_residual [B], objective [B]; stats[8] = {iterations run, kernel launches, factorisation launches, host
+ * synchronisations, inertia-correction factorisations, second-order-correction solves, line-search rounds, 0}. The final iterate stays resident as the batch's z (dto_get_last_x). */
+int dto_sqp_solve(dto_batch* b, const dto_sqp_options* options, const double* z0, const double* lambda0, const double* lower,
+                  const double* upper, double* z, double* lambda, int32_t* iterations, uint8_t* converged,
+                  double* constraint_violation, double* dual_residual, double* objective, int64_t* stats);
 
 #ifdef __cplusplus
 }

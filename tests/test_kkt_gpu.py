@@ -393,3 +393,51 @@ def test_pinned_variables_get_identity_rows():
     assert np.array_equal(again, full)
     kkt.close()
     pn.close()
+
+
+@pytest.mark.parametrize("name,kw", [("cartpole", dict(T=11)), ("acrobot", dict(T=9)), ("car", dict(T=12, obstacle="general"))])
+def test_resolve_with_stored_factor_is_bit_identical_to_refactorising(name, kw):
+    """dto_kkt_resolve: K stays, the right-hand side changes (a second-order correction overwrites c on the device).
+    Forward and backward solves with the stored factor must give the very bits of factorising again -- for the whole
+    batch and for a problem list (the others keep their solution) -- and the dense solve of the assembled matrix."""
+    import torch
+    from dto_b200 import sqp
+    from dto_b200.evaluator import A_C
+    B = 19
+    mo, osolver, pn, z, lam, sigma, w = _setup(name, kw, B, 2)
+    kkt = PK.KKTSystem(pn, primal_reg=1.0e-2, dual_reg=1.0e-6)
+    dev = torch.device("cuda", pn.shard_device(0))
+    sol0 = np.empty((B, kkt.dim))
+    kkt.solve(sol0, variables=z, scaling=sigma, duals=lam)
+    nneg0 = kkt.inertia()
+    N_c = pn.num_constraint
+    d_c = torch.as_tensor(sqp._CudaArray(pn.device_pointer(A_C, 0), (B, N_c)), device=dev)
+    stream = torch.cuda.ExternalStream(pn.stream_pointer(0), device=dev)
+    rng = np.random.default_rng(8)
+    c_new = torch.as_tensor(rng.normal(size=(B, N_c)), device=dev)
+    with torch.cuda.stream(stream):
+        c_old = d_c.clone()
+        d_c.copy_(c_new)
+    kkt.resolve()
+    pn.sync()
+    got = kkt.solution()
+    kkt.launch(False)                       # factorise again with the new right-hand side
+    pn.sync()
+    ref = kkt.solution()
+    assert np.array_equal(got, ref) and not np.array_equal(got, sol0)
+    K, h = kkt.matrix(3), kkt.rhs()[3]
+    dense = np.linalg.solve(K, h)
+    assert np.max(np.abs(got[3] - dense)) <= 1e-6 * max(1.0, np.max(np.abs(dense)))
+    # problem list: back to the old c for three problems only
+    pick = np.array([1, 8, 17], dtype=np.int32)
+    idx = torch.as_tensor(pick, device=dev)
+    with torch.cuda.stream(stream):
+        d_c[idx.long()] = c_old[idx.long()]
+    kkt.resolve(idx.data_ptr(), len(pick))
+    pn.sync()
+    part = kkt.solution()
+    keep = np.setdiff1d(np.arange(B), pick)
+    assert np.array_equal(part[keep], ref[keep]) and np.array_equal(part[pick], sol0[pick])
+    assert np.array_equal(kkt.inertia(), nneg0)      # the pivot counts are re-read from the stored factor, not changed
+    kkt.close()
+    pn.close()

@@ -155,3 +155,82 @@ def test_reference_solve_tests_with_bound_pinned_end_points():
         ok += int(np.linalg.norm(xs[0] - ma["x1"]) < 1e-3 and np.linalg.norm(xs[-1] - ma["xT"]) < 1e-3 and float(res.constraint_violation[b]) < 1e-6)
     assert ok >= 0.9 * B, ok
     s.nlp.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# native arm: dto_sqp_solve (csrc/dto_sqp_host.inc + dto_sqp.cu) -- the same algorithm inside libdto.so, no torch
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kw,B,iters", [("pendulum", dict(), 4, 12), ("acrobot", dict(T=9), 3, 25)])
+def test_native_solver_walks_through_the_oracle_driven_iterates(name, kw, B, iters):
+    """dto_sqp_solve stopped after k iterations must stand where the oracle-driven twin stood after k iterations, for
+    every k (the native arm keeps no history, so it is simply run with max_iter = k); final multipliers, residuals and
+    iteration counts must match too."""
+    mo, mp = M.BUILDERS[name](O, **kw), M.BUILDERS[name](D, **kw)
+    osolver, pn = O.solver_from(mo), D.solver_from(mp, batch=B).nlp
+    z0 = _guess(mp, B, 5)
+    perm, bw = PK.analyze(pn)
+    opts = sqp.SQPOptions(max_iter=iters, dual_reg=1.0e-6)
+    ref = sqp.solve(OracleBackend(osolver, B, dual_reg=opts.dual_reg, perm=perm - 1, bw=bw, linear="band"), z0, options=opts, record=True)
+    for k in range(1, len(ref.history)):
+        got = sqp.solve_native(pn, z0, options=sqp.SQPOptions(max_iter=k, dual_reg=opts.dual_reg))
+        hr = ref.history[k]
+        scale = np.maximum(1.0, np.abs(hr["z"]))
+        assert np.max(np.abs(got.z - hr["z"]) / scale) < 1e-7, (name, k)
+        assert np.allclose(got.lam, hr["lam"], rtol=1e-5, atol=1e-7), (name, k)
+    got = sqp.solve_native(pn, z0, options=opts)
+    assert np.array_equal(got.converged, ref.converged) and np.array_equal(got.iterations, ref.iterations)
+    assert got.stats["iterations"] == len(ref.history) and got.stats["launches"] > 0
+    both = got.converged & ref.converged
+    assert np.allclose(got.objective[both], ref.objective[both], rtol=1e-8)
+    assert np.allclose(got.constraint_violation, ref.constraint_violation, atol=1e-9)
+    # the final iterate is the batch's resident z (get_trajectory, src/solver.jl:41-43)
+    assert np.array_equal(pn.last_x(B - 1), got.z[B - 1])
+    pn.close()
+
+
+def test_native_solver_pinned_end_points_and_scope():
+    """test/solve.jl:227-296 set-up (x1 pinned by equal bounds, xT by a GeneralConstraint) through dto_sqp_solve: same
+    result as the oracle-driven twin, pinned variables exactly at the bound; an inequality bound is refused with
+    DTO_ERR_UNSUPPORTED rather than approximated."""
+    from dto_b200 import _lib
+    kw = dict(reference_exact=True)
+    mo, mp = M.build_linear_general(O, **kw), M.build_linear_general(D, **kw)
+    B = 4
+    osolver, pn = O.solver_from(mo), D.solver_from(mp, batch=B).nlp
+    z0 = _guess(mp, B, 21)
+    perm, bw = PK.analyze(pn)
+    opts = sqp.SQPOptions(max_iter=20, dual_reg=1.0e-6)
+    ref = sqp.solve(OracleBackend(osolver, B, dual_reg=opts.dual_reg, perm=perm - 1, bw=bw, linear="band"), z0, options=opts, record=True)
+    got = sqp.solve_native(pn, z0, options=opts)
+    assert got.converged.all() and ref.converged.all() and got.stats["iterations"] == len(ref.history)
+    assert np.allclose(got.z, ref.z, rtol=1e-8, atol=1e-10)
+    n = mp["n"]
+    assert np.array_equal(got.z[:, :n], np.tile(mp["x1"], (B, 1)))
+    assert np.all(np.linalg.norm(got.z[:, -n:] - mp["xT"], axis=1) < 1e-3)
+    pn.close()
+    pb = D.solver_from(M.build_cartpole(D, T=11), batch=2).nlp        # |u| <= u_bnd: inequality bounds on the controls
+    with pytest.raises(_lib.DtoError) as e:
+        sqp.solve_native(pb, np.zeros((2, pb.num_variables)))
+    assert e.value.status == -7 and "inequality bound" in str(e.value)
+    pb.close()
+
+
+def test_native_solver_full_solves_and_solver_api():
+    """Solver.solve(method='native') on the reference's acrobot test (end points pinned by bounds, T = 101): the
+    acceptance of test/solve.jl:134-137 for >= 90 % of 64 seeded problems, and the same success set as the torch arm
+    on a smaller batch."""
+    ma = M.build_acrobot(D, T=101, stage_endpoint_constraints=False)
+    B = 64
+    s = D.solver_from(ma, batch=B)
+    s.initialize_states(D.linear_interpolation(ma["x1"], ma["xT"], 101))
+    rng = np.random.default_rng(4)
+    for b in range(B):
+        s.initialize_controls([rng.normal(size=1) for _ in range(100)], problem=b)
+    res = s.solve(options=dict(max_iter=300), method="native")
+    ok = 0
+    for b in range(B):
+        xs, _ = s.get_trajectory(b)
+        ok += int(np.linalg.norm(xs[0] - ma["x1"]) < 1e-3 and np.linalg.norm(xs[-1] - ma["xT"]) < 1e-3 and float(res.constraint_violation[b]) < 1e-6)
+    assert ok >= 0.9 * B, ok
+    assert s.sqp_launches > 100 and res.stats["syncs"] < res.stats["launches"]
+    s.nlp.close()
