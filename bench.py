@@ -442,7 +442,11 @@ def run_ours(args):
                 import solve_config3
                 for n_ in nlps:
                     n_.close()
-                line["solve"] = solve_config3.run(B=4096, T=101, max_iter=300)
+                # the shipped solver is the native arm (dto_sqp_solve; host z0 in, host results out inside its timed
+                # region); the torch-glued arm of the same algorithm (sqp.py) is reported beside it
+                line["solve"] = solve_config3.run(B=4096, T=101, max_iter=300, method="native")
+                t_arm = solve_config3.run(B=4096, T=101, max_iter=300, method="sqp")
+                line["solve"]["torch_glue_arm"] = {k: t_arm[k] for k in ("seconds", "solves_per_s", "accepted_frac", "gpu_launches")}
             except Exception as e:  # noqa: BLE001
                 line["solve"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:

@@ -8,7 +8,8 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB = os.path.join(PKG_DIR, "libdto.so")
+# DTO_LIB: use this prebuilt runtime instead (A/B experiments with kernel variants, tools/ab_kkt.sh); never built here
+LIB = os.environ.get("DTO_LIB") or os.path.join(PKG_DIR, "libdto.so")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 
@@ -23,6 +24,8 @@ def _stale() -> bool:
 
 
 def build_runtime(force: bool = False, verbose: bool = False) -> str:
+    if os.environ.get("DTO_LIB"):
+        return LIB
     if not force and not _stale():
         return LIB
     objs = []

@@ -33,6 +33,13 @@
 
 #include "dto_kkt_dev.h"
 
+#ifndef DTO_KKT_PREFETCH
+#define DTO_KKT_PREFETCH 1
+#endif
+#ifndef DTO_KKT_FUSE
+#define DTO_KKT_FUSE 1
+#endif
+
 namespace {
 
 template <int G>
@@ -209,7 +216,9 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
 // BW = compile-time bound on the half bandwidth (<= W - 1).
 // MINB = resident CTAs per SM asked of the compiler: 4 (<= 128 registers, no spills) or 5 (<= 96 registers, a few
 // spilled values; pays off only when the launch has more than 16 warps per SM to offer, i.e. B > ~4700)
-template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
+// VIRT = candidate launch (dto_kkt_args::virt): outputs and regularisation indexed by slot. A separate instantiation: as a
+// run-time switch its extra live index cost the default path registers and spills (acrobot, 64 problems: 0.275 vs 0.204 ms)
+template <int W, int BW, int MINB = (W == 16 ? 4 : 2), bool VIRT = false>
 __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args a)
 {
     constexpr int G = W;
@@ -223,24 +232,31 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     const bool valid = b0 < a.B;
     const int64_t bs = valid ? b0 : a.B - 1;         // idle groups shadow the last slot, stores masked
     const int64_t b = a.pidx ? (int64_t)a.pidx[bs] : bs;   // subset launch: slot -> problem
+    const int64_t bo = VIRT ? bs : b;                // candidate launch: regularisation, factor, solution, pivot count by slot
     const double* Hb = a.H + b * a.nnz_H;
     const double* Jb = a.J + b * a.nnz_J - a.nnz_H;  // see load_rows
     const double* hb = a.rhs + b * a.dim;
     const int nblk = a.nblk;
-    double* Lg = a.L + (size_t)b * a.factor_stride;  // [nblk*W][LW]: slot 0 = pivot d_j, slot q = L(j+q, j)
+    double* Lg = a.L + (size_t)bo * a.factor_stride; // [nblk*W][LW]: slot 0 = pivot d_j, slot q = L(j+q, j)
     double* Yg = Lg + (size_t)nblk * W * LW;         // [nblk*W]: D^-1 L^-1 h
     unsigned char* gsm = kkt_smem + (size_t)(wib * SM::NG + grp) * SM::PER_GROUP;
     double* stage = reinterpret_cast<double*>(gsm);                              // forward: rows of block blk+2, [w][i]
     double (*lcol)[W] = reinterpret_cast<double (*)[W]>(gsm + SM::RING * SM::SLOT);  // un-scaled column, double-buffered
 
+    // right-hand-side entry of original row ip; a candidate launch always finds it in the rhs array (nothing it depends
+    // on changed since the launch that wrote it), which also keeps the problem index out of the loop's live registers
+    auto rhs_at = [&](int32_t ip) -> double {
+        if (VIRT || !DTO_KKT_FUSE) return ip < 0 ? 0.0 : hb[ip];
+        return rhs_entry(a, b, ip, hb, valid);
+    };
     double A[W], Bv[W];
     double ra, rb = 0.0, rc = 0.0, regc = 0.0;
     int32_t nidx[W];                                  // gather indices of the rows two blocks ahead
-    load_rows<W>(a, Hb, Jb, 0, i, A, b);
-    ra = rhs_entry(a, b, a.iperm[i], hb, valid);
+    load_rows<W>(a, Hb, Jb, 0, i, A, bo);
+    ra = rhs_at(a.iperm[i]);
     if (nblk > 1) {
-        load_rows<W>(a, Hb, Jb, 1, i, Bv, b);
-        rb = rhs_entry(a, b, a.iperm[W + i], hb, valid);
+        load_rows<W>(a, Hb, Jb, 1, i, Bv, bo);
+        rb = rhs_at(a.iperm[W + i]);
     } else {
 #pragma unroll
         for (int w = 0; w < W; ++w) Bv[w] = 0.0;
@@ -253,6 +269,22 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
         }
     };
     load_idx(2);
+    // Static per-row values of the block two ahead (source row of the right-hand side, diagonal shift, pinned flag) are
+    // fetched one block early and consumed without branches: a table load followed by a dependent branch or load inside
+    // the block loop was a quarter of the time of a launch too small to hide it (profiles/ncu_kkt_latency_r02.txt)
+#if DTO_KKT_PREFETCH
+    const double prim = a.preg != nullptr ? a.preg[bo] : a.primal_reg;   // diagonal shift of this slot's variable rows
+    int32_t ipn = -1;
+    bool fixn = false;
+    auto load_static = [&](int blk) {
+        if (blk < nblk) {
+            const size_t row = (size_t)blk * W + i;
+            ipn = a.iperm[row];
+            fixn = a.rowfixed != nullptr && a.rowfixed[row];
+        }
+    };
+    load_static(2);
+#endif
 
     // ---------------- factor (right-looking) + forward solve ----------------
     // Step j = blk*W + s. v_r = A(r, j) (un-scaled column), l_r = v_r / d_j. The trailing update
@@ -271,9 +303,21 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
                 cp_async8_zfill(stage + w * W + i, sx >= 0 ? (const void*)(bp + sx) : (const void*)Hb, sx >= 0 ? 8 : 0);
             }
             cp_async_commit();
-            rc = rhs_entry(a, b, a.iperm[(size_t)(blk + 2) * W + i], hb, valid);
-            regc = row_shift(a, (size_t)(blk + 2) * W + i, b);
+#if DTO_KKT_PREFETCH
+            if (a.fuse_rhs) {
+                rc = rhs_at(ipn);
+            } else {
+                rc = 0.0;
+                if (ipn >= 0) rc = hb[ipn];
+            }
+            regc = (fixn || ipn < 0) ? 1.0 : (ipn < a.N_z ? prim : -a.dual_reg);   // = row_shift(): the values of the dreg table
             load_idx(blk + 3);
+            load_static(blk + 3);
+#else
+            rc = rhs_at(a.iperm[(size_t)(blk + 2) * W + i]);
+            regc = row_shift(a, (size_t)(blk + 2) * W + i, bo);
+            load_idx(blk + 3);
+#endif
         }
         double* LA = Lg + (size_t)blk * W * LW + i;  // + s*LW + (row - j) with immediates
 #pragma unroll
@@ -334,7 +378,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     __syncwarp();
     __threadfence_block();
 
-    kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, b);
+    kkt_backward<W, BW>(a, gsm, Lg, Yg, nblk, i, valid, bo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,8 +559,16 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_resolve_kernel(con
     issue(2);
     double ra = rhs_entry(a, b, a.iperm[i], hb, valid);
     double rb = nblk > 1 ? rhs_entry(a, b, a.iperm[W + i], hb, valid) : 0.0;
+    int32_t ipn = nblk > 2 ? a.iperm[2 * W + i] : -1;   // source row of the block two ahead, fetched one block early
     for (int blk = 0; blk < nblk; ++blk) {
-        const double rc = blk + 2 < nblk ? rhs_entry(a, b, a.iperm[(size_t)(blk + 2) * W + i], hb, valid) : 0.0;
+        double rc = 0.0;
+        if (blk + 2 < nblk) {
+            if (a.fuse_rhs)
+                rc = rhs_entry(a, b, ipn, hb, valid);
+            else if (ipn >= 0)
+                rc = hb[ipn];
+        }
+        if (blk + 3 < nblk) ipn = a.iperm[(size_t)(blk + 3) * W + i];
         cp_async_wait<2>();
         __syncwarp();
         const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
@@ -594,18 +646,24 @@ extern "C" int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream)
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
-static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
+template <int W, int BW, int MINB, bool VIRT>
+static cudaError_t launch_band_v(const dto_kkt_args* a, cudaStream_t st)
 {
     const int64_t per_block = 4 * (32 / W);
     // the opt-in is per device and a batch may span several: set it on every launch (a cheap driver call
     // next to a >= 100 us kernel) instead of caching it per process
     if (KktSmem<W, BW>::BYTES > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB, VIRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
         if (e != cudaSuccess) return e;
     }
-    kkt_band_kernel<W, BW, MINB><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
+    kkt_band_kernel<W, BW, MINB, VIRT><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
     return cudaGetLastError();
+}
+template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
+static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
+{
+    if (MINB == (W == 16 ? 4 : 2) && a->virt) return launch_band_v<W, BW, (W == 16 ? 4 : 2), true>(a, st);
+    return launch_band_v<W, BW, MINB, false>(a, st);
 }
 
 template <int W, int BW, int M>
@@ -628,10 +686,10 @@ extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
     const int bound = dto_kkt_bw_bound(a->W, a->bw);
-    const bool two = a->variant != 2;
+    const bool two = a->variant != 2 || a->virt;   // candidate launches (slot-indexed outputs) exist in the default kernel only
     // experiment (DTO_KKT_VARIANT=occ5): 5 CTAs per SM, 96 registers, a few spills -- measured slower on every
     // shape (cartpole 0.485 vs 0.346 ms, car 3.09 vs 2.35 ms; profiles/kkt_r01_history.jsonl tags v8 / v8occ5)
-    if (a->variant == 3 && a->W == 16 && (bound == 9 || bound == 15)) {
+    if (a->variant == 3 && !a->virt && a->W == 16 && (bound == 9 || bound == 15)) {
         e = bound == 9 ? launch_band_t<16, 9, 5>(a, st) : launch_band_t<16, 15, 5>(a, st);
         return e == cudaSuccess ? 1 : -(int)e;
     }

@@ -47,6 +47,11 @@ typedef struct dto_kkt_args {
     /* subset launch (a solver re-factorising only the problems whose inertia was wrong): when non-NULL, slot s of
      * the launch works on problem pidx[s] and B is the number of slots; every array above stays indexed by problem */
     const int32_t* pidx; /* [B] or NULL                                                        */
+    /* candidate launch (several regularisations of the same problem tried at once): with virt = 1 and pidx given, slot s
+     * READS problem pidx[s] (H, J, rhs) but its regularisation preg[s], factor L[s], solution sol[s] and pivot count
+     * nneg[s] are indexed by the SLOT: the caller passes scratch arrays there and keeps the candidate it wants */
+    int32_t virt;
+    double primal_reg, dual_reg;   /* the scalars behind the dreg table (+primal_reg on variable rows, -dual_reg on constraint rows) */
     /* variables pinned by equal lower/upper bounds (Bound(state_lower = x1, state_upper = x1), test/solve.jl): their
      * rows and columns of K are replaced by the identity (the gather table carries structural zeros there) and their
      * right-hand-side entries by 0, so their step is exactly 0 and the others get the reduced Newton step */

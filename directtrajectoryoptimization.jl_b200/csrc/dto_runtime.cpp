@@ -25,6 +25,7 @@
 #include <new>
 #include <string>
 #include <utility>
+#include <chrono>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a tool (nsys / ncu --nvtx) is attached

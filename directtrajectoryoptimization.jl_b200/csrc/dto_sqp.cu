@@ -22,13 +22,66 @@ __device__ __forceinline__ double wsum(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-// max |x| that propagates NaN like a comparison-free maximum would not: a row with a NaN is "not finite" separately
-__device__ __forceinline__ double absmax_row(const double* __restrict__ r, int n, int lane)
+// Row helpers: one warp walks a problem's row with stride 32. A single warp per row means few loads in flight unless
+// they are issued in batches, so every helper loads four strided elements before it uses the first (out-of-range
+// slots read nothing and contribute a neutral value); sums keep the order i = lane, lane + 32, ... of a plain loop.
+#define ROW4(n, lane, i) for (int i = (lane); i < (n); i += 128)
+__device__ __forceinline__ void ld4(const double* p, int i, int n, double (&v)[4], double fill)
+{
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + 32 * u < n) ? p[i + 32 * u] : fill;
+}
+__device__ __forceinline__ void st4(double* p, int i, int n, const double (&v)[4])
+{
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < n) p[i + 32 * u] = v[u];
+}
+__device__ __forceinline__ void row_copy(double* __restrict__ dst, const double* __restrict__ src, int n, int lane)
+{
+    ROW4(n, lane, i) {
+        double v[4];
+        ld4(src, i, n, v, 0.0);
+        st4(dst, i, n, v);
+    }
+}
+// dst = x + alpha * y (alpha is 1, -1 or a power of two in every caller: the product is exact, fused or not). dst may
+// be x or y (in-place updates): the four loads of a batch precede its stores in program order, nothing is restrict here
+__device__ __forceinline__ void row_axpy(double* dst, const double* x, double alpha, const double* y, int n, int lane)
+{
+    ROW4(n, lane, i) {
+        double vx[4], vy[4];
+        ld4(x, i, n, vx, 0.0);
+        ld4(y, i, n, vy, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vx[u] = vx[u] + alpha * vy[u];
+        st4(dst, i, n, vx);
+    }
+}
+__device__ __forceinline__ double row_sum_abs(const double* __restrict__ p, int n, int lane)
+{
+    double acc = 0.0;
+    ROW4(n, lane, i) {
+        double v[4];
+        ld4(p, i, n, v, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += fabs(v[u]);
+    }
+    return wsum(acc);
+}
+// max |x|; a NaN, once seen, is kept (torch's amax propagates NaN): a row with a NaN never passes a tolerance test
+__device__ __forceinline__ double absmax_row(const double* __restrict__ r, int n, int lane, const double* __restrict__ mask = nullptr)
 {
     double m = 0.0;
-    for (int i = lane; i < n; i += 32) {
-        const double v = fabs(r[i]);
-        m = (v > m || v != v) ? v : m;   // keep a NaN once seen (torch's amax propagates NaN)
+    ROW4(n, lane, i) {
+        double v[4], k[4];
+        ld4(r, i, n, v, 0.0);
+        if (mask) ld4(mask, i, n, k, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double x = fabs(mask ? v[u] * k[u] : v[u]);
+            m = (x > m || x != x) ? x : m;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -40,7 +93,12 @@ __device__ __forceinline__ double absmax_row(const double* __restrict__ r, int n
 __device__ __forceinline__ bool finite_row(const double* __restrict__ r, int n, int lane)
 {
     bool ok = true;
-    for (int i = lane; i < n; i += 32) ok = ok && isfinite(r[i]);
+    ROW4(n, lane, i) {
+        double v[4];
+        ld4(r, i, n, v, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ok = ok && isfinite(v[u]);
+    }
     return __all_sync(FULL, ok);
 }
 
@@ -54,8 +112,18 @@ __global__ void k_begin(const dto_sqp_args a)
 {
     WARP_PROBLEM();
     const double ex = a.exact[b];
-    for (int i = lane; i < a.N_z; i += 32) a.bz[b * a.N_z + i] = a.z[b * a.N_z + i];
-    for (int i = lane; i < a.N_c; i += 32) a.blam[b * a.N_c + i] = a.lam[b * a.N_c + i] * ex;
+    row_copy(a.bz + b * a.N_z, a.z + b * a.N_z, a.N_z, lane);
+    {
+        const double* __restrict__ src = a.lam + b * a.N_c;
+        double* __restrict__ dst = a.blam + b * a.N_c;
+        ROW4(a.N_c, lane, i) {
+            double v[4];
+            ld4(src, i, a.N_c, v, 0.0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] *= ex;
+            st4(dst, i, a.N_c, v);
+        }
+    }
     if (lane == 0) {
         const double d = a.lm[b];
         a.delta[b] = d;
@@ -66,7 +134,7 @@ __global__ void k_begin(const dto_sqp_args a)
 __global__ void k_set_lam(const dto_sqp_args a)
 {
     WARP_PROBLEM();
-    for (int i = lane; i < a.N_c; i += 32) a.blam[b * a.N_c + i] = a.lam[b * a.N_c + i];
+    row_copy(a.blam + b * a.N_c, a.lam + b * a.N_c, a.N_c, lane);
 }
 
 // ---- after the callbacks and the first factorisation of the iteration
@@ -74,19 +142,9 @@ __global__ void k_after_first(const dto_sqp_args a)
 {
     WARP_PROBLEM();
     const double* c = a.bc + b * a.N_c;
-    const double* rz = a.rhs + b * a.dim;
-    double dr = 0.0;
-    for (int i = lane; i < a.N_z; i += 32) {
-        const double v = fabs(rz[i] * a.free[i]);
-        dr = (v > dr || v != v) ? v : dr;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double w = __shfl_xor_sync(FULL, dr, o);
-        dr = (w > dr || w != w) ? w : dr;
-    }
+    const double dr = absmax_row(a.rhs + b * a.dim, a.N_z, lane, a.free);   // ||(g + J'lam) * free||_inf
     const double cv = absmax_row(c, a.N_c, lane);
-    for (int i = lane; i < a.N_c; i += 32) a.ckeep[b * a.N_c + i] = c[i];
+    row_copy(a.ckeep + b * a.N_c, c, a.N_c, lane);
     const bool fin = finite_row(a.sol + b * a.dim, a.dim, lane);
     if (lane == 0) {
         a.cv[b] = cv;
@@ -143,17 +201,46 @@ __global__ void k_direction(const dto_sqp_args a)
     const double* g = a.bg + b * a.N_z;
     const double* ck = a.ckeep + b * a.N_c;
     double gd = 0.0, c1 = 0.0, cl = 0.0;
-    for (int i = lane; i < a.N_z; i += 32) {
-        const double d = -sol[i] * a.free[i];
-        a.dz[b * a.N_z + i] = d;
-        gd += g[i] * d;
-        a.bz[b * a.N_z + i] = a.z[b * a.N_z + i] + 1.0 * d;   // first trial: alpha = 1
-    }
-    for (int i = lane; i < a.N_c; i += 32) {
-        const double dl = -sol[a.N_z + i];
-        a.dlam[b * a.N_c + i] = dl;
-        c1 += fabs(ck[i]);
-        cl += ck[i] * (a.lam[b * a.N_c + i] + dl);
+    {
+        const double* __restrict__ fr = a.free;
+        const double* __restrict__ zc = a.z + b * a.N_z;
+        double* __restrict__ dz = a.dz + b * a.N_z;
+        double* __restrict__ bz = a.bz + b * a.N_z;
+        ROW4(a.N_z, lane, i) {
+            double vs[4], vf[4], vg[4], vz[4];
+            ld4(sol, i, a.N_z, vs, 0.0);
+            ld4(fr, i, a.N_z, vf, 0.0);
+            ld4(g, i, a.N_z, vg, 0.0);
+            ld4(zc, i, a.N_z, vz, 0.0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double d = -vs[u] * vf[u];
+                vs[u] = d;
+                if (i + 32 * u < a.N_z) gd += vg[u] * d;      // (guarded: 0 * inf of a padded slot would be NaN)
+                vz[u] = vz[u] + 1.0 * d;                      // first trial: alpha = 1
+            }
+            st4(dz, i, a.N_z, vs);
+            st4(bz, i, a.N_z, vz);
+        }
+        const double* __restrict__ sl = sol + a.N_z;
+        const double* __restrict__ lam = a.lam + b * a.N_c;
+        double* __restrict__ dlam = a.dlam + b * a.N_c;
+        ROW4(a.N_c, lane, i) {
+            double vs[4], vc[4], vl[4];
+            ld4(sl, i, a.N_c, vs, 0.0);
+            ld4(ck, i, a.N_c, vc, 0.0);
+            ld4(lam, i, a.N_c, vl, 0.0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double dl = -vs[u];
+                vs[u] = dl;
+                if (i + 32 * u < a.N_c) {
+                    c1 += fabs(vc[u]);
+                    cl += vc[u] * (vl[u] + dl);
+                }
+            }
+            st4(dlam, i, a.N_c, vs);
+        }
     }
     gd = wsum(gd);
     c1 = wsum(c1);
@@ -178,24 +265,21 @@ __global__ void k_ls_round(const dto_sqp_args a, int32_t round)
 {
     WARP_PROBLEM();
     const double* ct = a.bc + b * a.N_c;
-    double ct1 = 0.0;
-    for (int i = lane; i < a.N_c; i += 32) ct1 += fabs(ct[i]);
-    ct1 = wsum(ct1);
+    const double ct1 = row_sum_abs(ct, a.N_c, lane);
     bool accepted = a.accepted[b] != 0;
     double alpha = a.alpha[b];
     const double nu = a.nu[b];
     const double phit = a.bf[b] + nu * ct1;
     const bool ok = (phit <= a.phi0[b] + a.p.armijo * alpha * a.slope[b]) && !accepted;
     if (ok) {
-        for (int i = lane; i < a.N_z; i += 32) a.z[b * a.N_z + i] = a.bz[b * a.N_z + i];
-        for (int i = lane; i < a.N_c; i += 32) a.lam[b * a.N_c + i] += alpha * a.dlam[b * a.N_c + i];
+        row_copy(a.z + b * a.N_z, a.bz + b * a.N_z, a.N_z, lane);
+        row_axpy(a.lam + b * a.N_c, a.lam + b * a.N_c, alpha, a.dlam + b * a.N_c, a.N_c, lane);
     }
     accepted = accepted || ok;
     if (round == 0 && a.p.soc) {
         // second-order correction candidates: rejected full steps that did not even reduce the constraint violation
         const bool need = !accepted && ct1 >= a.c1[b];
-        if (need)
-            for (int i = lane; i < a.N_c; i += 32) a.bc[b * a.N_c + i] = a.ckeep[b * a.N_c + i] + ct[i];   // c(z) + c(z + dz)
+        if (need) row_axpy(a.bc + b * a.N_c, a.ckeep + b * a.N_c, 1.0, ct, a.N_c, lane);   // c(z) + c(z + dz)
         if (lane == 0) {
             a.need[b] = need ? 1 : 0;
             if (need) a.idx[atomicAdd(a.counters + DTO_SQP_N_NEED, 1)] = (int32_t)b;
@@ -203,11 +287,11 @@ __global__ void k_ls_round(const dto_sqp_args a, int32_t round)
     }
     if (!accepted) alpha = 0.5 * alpha;
     __syncwarp();
-    for (int i = lane; i < a.N_z; i += 32) a.bz[b * a.N_z + i] = a.z[b * a.N_z + i] + alpha * a.dz[b * a.N_z + i];   // next trial
+    row_axpy(a.bz + b * a.N_z, a.z + b * a.N_z, alpha, a.dz + b * a.N_z, a.N_z, lane);   // next trial
     if (lane == 0) {
         a.accepted[b] = accepted ? 1 : 0;
         a.alpha[b] = alpha;
-        if (!accepted) atomicAdd(a.counters + DTO_SQP_N_OPEN, 1);   // the host stops the search when no problem is open
+        if (!accepted) a.oidx[atomicAdd(a.counters + DTO_SQP_N_OPEN, 1)] = (int32_t)b;   // the host stops the search when no problem is open
     }
 }
 
@@ -218,7 +302,18 @@ __global__ void k_soc_trial(const dto_sqp_args a, int32_t count)
     if (k >= count) return;
     const int64_t b = a.idx[k];
     const double* sol = a.sol + b * a.dim;
-    for (int i = lane; i < a.N_z; i += 32) a.bz[b * a.N_z + i] = a.z[b * a.N_z + i] + (-sol[i] * a.free[i]);
+    const double* __restrict__ zc = a.z + b * a.N_z;
+    const double* __restrict__ fr = a.free;
+    double* __restrict__ bz = a.bz + b * a.N_z;
+    ROW4(a.N_z, lane, i) {
+        double vs[4], vf[4], vz[4];
+        ld4(sol, i, a.N_z, vs, 0.0);
+        ld4(fr, i, a.N_z, vf, 0.0);
+        ld4(zc, i, a.N_z, vz, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vz[u] = vz[u] + (-vs[u] * vf[u]);
+        st4(bz, i, a.N_z, vz);
+    }
 }
 
 __global__ void k_soc_accept(const dto_sqp_args a, int32_t count)
@@ -229,19 +324,17 @@ __global__ void k_soc_accept(const dto_sqp_args a, int32_t count)
     const int64_t b = a.idx[k];
     const double* cs = a.bc + b * a.N_c;
     const double* sol = a.sol + b * a.dim;
-    double cs1 = 0.0;
-    for (int i = lane; i < a.N_c; i += 32) cs1 += fabs(cs[i]);
-    cs1 = wsum(cs1);
+    const double cs1 = row_sum_abs(cs, a.N_c, lane);
     const bool fin = finite_row(sol, a.dim, lane);
     const bool oks = (a.bf[b] + a.nu[b] * cs1 <= a.phi0[b] + a.p.armijo * a.slope[b]) && fin;
     double alpha = a.alpha[b];
     if (oks) {
-        for (int i = lane; i < a.N_z; i += 32) a.z[b * a.N_z + i] = a.bz[b * a.N_z + i];
-        for (int i = lane; i < a.N_c; i += 32) a.lam[b * a.N_c + i] -= sol[a.N_z + i];
+        row_copy(a.z + b * a.N_z, a.bz + b * a.N_z, a.N_z, lane);
+        row_axpy(a.lam + b * a.N_c, a.lam + b * a.N_c, -1.0, sol + a.N_z, a.N_c, lane);   // lam - sol_lambda
         alpha = 1.0;   // the full (corrected) step was taken: round 0 had already halved alpha for this problem
     }
     __syncwarp();
-    for (int i = lane; i < a.N_z; i += 32) a.bz[b * a.N_z + i] = a.z[b * a.N_z + i] + alpha * a.dz[b * a.N_z + i];   // trial of round 1
+    row_axpy(a.bz + b * a.N_z, a.z + b * a.N_z, alpha, a.dz + b * a.N_z, a.N_z, lane);   // trial of round 1
     if (lane == 0) {
         if (oks) {
             a.accepted[b] = 1;
@@ -258,7 +351,7 @@ __global__ void k_end(const dto_sqp_args a)
     if (a.p.lam_max > 0.0) {
         const double m = absmax_row(a.lam + b * a.N_c, a.N_c, lane);
         if (m > a.p.lam_max)
-            for (int i = lane; i < a.N_c; i += 32) a.lam[b * a.N_c + i] = 0.0;
+            for (int i = lane; i < a.N_c; i += 32) a.lam[b * a.N_c + i] = 0.0;   // (stores only)
     }
     if (lane == 0) {
         const bool accepted = a.accepted[b] != 0, done = a.done[b] != 0, bad = a.bad[b] != 0;
@@ -270,6 +363,124 @@ __global__ void k_end(const dto_sqp_args a)
         if (lm < a.p.lm_zero) lm = 0.0;
         a.lm[b] = lm;
         if (!accepted || bad) a.delta_last[b] = fmax(a.p.reg_first, a.p.reg_inc * fmax(a.delta_last[b], delta));
+    }
+}
+
+// ---- the remaining backtracking rounds of the open problems in one pass: R sequential rounds would try
+// alpha, alpha/2, .., alpha/2^(R-1) one after the other and take the first that passes; here every such trial point
+// gets a slot of the trial arrays, the objective and constraint kernels run once over the slots, and k_multi_pick
+// takes the first passing one in the same order (same trial points, same kernels, same test: same result)
+__global__ void k_multi_trial(const dto_sqp_args a, int32_t count, int32_t R)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= (int64_t)count * R) return;
+    const int64_t k = s / R;
+    const int j = (int)(s - k * R);
+    const int64_t b = a.oidx[k];
+    double alpha = a.alpha[b];
+    for (int q = 0; q < j; ++q) alpha = 0.5 * alpha;
+    row_axpy(a.tz + s * a.N_z, a.z + b * a.N_z, alpha, a.dz + b * a.N_z, a.N_z, lane);
+    if (a.N_w > 0) row_copy(a.tw + s * a.N_w, a.w + b * a.N_w, a.N_w, lane);
+}
+
+__global__ void k_multi_pick(const dto_sqp_args a, int32_t count, int32_t R)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= count) return;
+    const int64_t b = a.oidx[k];
+    if (a.accepted[b]) return;            // taken by the second-order correction after the list was written
+    double alpha = a.alpha[b];
+    const double nu = a.nu[b], phi0 = a.phi0[b], slope = a.slope[b];
+    bool taken = false;
+    for (int j = 0; j < R && !taken; ++j) {
+        const int64_t s = k * R + j;
+        const double* ct = a.tc + s * a.N_c;
+        const double ct1 = row_sum_abs(ct, a.N_c, lane);
+        const double phit = a.tf[s] + nu * ct1;
+        if (phit <= phi0 + a.p.armijo * alpha * slope) {
+            row_copy(a.z + b * a.N_z, a.tz + s * a.N_z, a.N_z, lane);
+            row_axpy(a.lam + b * a.N_c, a.lam + b * a.N_c, alpha, a.dlam + b * a.N_c, a.N_c, lane);
+            taken = true;
+        } else {
+            alpha = 0.5 * alpha;
+        }
+    }
+    if (lane == 0) {
+        a.alpha[b] = alpha;
+        if (taken) a.accepted[b] = 1;
+    }
+}
+
+// ---- inertia correction, m tries at once: sequential tries would factorise a bad problem with nxt_1, look at the
+// pivot count, then with nxt_2 = grow * nxt_1, ... Each try costs the full latency of a banded factorisation however
+// few problems take part, so the next m values of the ladder are factorised side by side in candidate slots and the
+// first one that works is kept: the same regularisation, factor and step the sequential tries end with.
+__global__ void k_reg_ladder(const dto_sqp_args a, int32_t m)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B || !a.bad[b]) return;
+    const double dl = a.delta_last[b];
+    const double start = dl == 0.0 ? a.p.reg_first : fmax(a.p.reg_min, a.p.reg_dec * dl);
+    const double grow = dl == 0.0 ? a.p.reg_inc_first : a.p.reg_inc;
+    double d = a.delta[b];
+    bool first = a.first[b] != 0;
+    const int64_t k = atomicAdd(a.counters + DTO_SQP_N_IDX, 1);
+    a.idx[k] = (int32_t)b;
+    for (int j = 0; j < m; ++j) {
+        d = first ? fmax(start, 2.0 * d) : fmin(a.p.reg_max, grow * d);
+        first = false;
+        a.vreg[k * m + j] = d;
+        a.vidx[k * m + j] = (int32_t)b;
+    }
+    a.first[b] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_reg_pick(const dto_sqp_args a, int32_t count, int32_t m)
+{
+    __shared__ int s_pick, s_good;
+    const int64_t k = blockIdx.x;
+    const int64_t b = a.idx[k];
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int pick = m - 1, good = 0;
+        for (int j = 0; j < m; ++j) {
+            const int64_t v = k * m + j;
+            const bool fin = finite_row(a.vsol + v * a.dim, a.dim, lane);
+            if (a.vnneg[v] == a.N_c && fin) {
+                pick = j;
+                good = 1;
+                break;
+            }
+        }
+        if (lane == 0) {
+            s_pick = pick;
+            s_good = good;
+            const int64_t v = k * m + pick;
+            a.delta[b] = a.vreg[v];      // a failed ladder leaves the last value tried, as sequential tries do
+            a.preg[b] = a.vreg[v];
+            a.nneg_w[b] = a.vnneg[v];
+            a.bad[b] = good ? 0 : 1;
+            if (!good) atomicAdd(a.counters + DTO_SQP_N_BAD, 1);
+        }
+    }
+    __syncthreads();
+    const int64_t v = k * m + s_pick;
+    for (int i = threadIdx.x; i < a.dim; i += blockDim.x) a.sol_w[b * a.dim + i] = a.vsol[v * a.dim + i];
+    if (s_good) {   // the factor is read again by a second-order correction
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(a.vL + (size_t)v * a.factor_stride);
+        double2* __restrict__ dst = reinterpret_cast<double2*>(a.L + (size_t)b * a.factor_stride);
+        const int64_t n2 = a.factor_stride / 2, step = blockDim.x;
+        for (int64_t i = threadIdx.x; i < n2; i += 4 * step) {
+            double2 v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * step < n2) v4[u] = src[i + u * step];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * step < n2) dst[i + u * step] = v4[u];
+        }
     }
 }
 
@@ -300,3 +511,22 @@ extern "C" int dto_sqp_k_ls_round(const dto_sqp_args* a, int32_t round, void* s)
 extern "C" int dto_sqp_k_soc_trial(const dto_sqp_args* a, int32_t count, void* s) { return launch_warp_per(k_soc_trial, count, s, *a, count); }
 extern "C" int dto_sqp_k_soc_accept(const dto_sqp_args* a, int32_t count, void* s) { return launch_warp_per(k_soc_accept, count, s, *a, count); }
 extern "C" int dto_sqp_k_end(const dto_sqp_args* a, void* s) { return launch_warp_per(k_end, a->B, s, *a); }
+extern "C" int dto_sqp_k_multi_trial(const dto_sqp_args* a, int32_t count, int32_t R, void* s)
+{
+    return launch_warp_per(k_multi_trial, (int64_t)count * R, s, *a, count, R);
+}
+extern "C" int dto_sqp_k_multi_pick(const dto_sqp_args* a, int32_t count, int32_t R, void* s) { return launch_warp_per(k_multi_pick, count, s, *a, count, R); }
+extern "C" int dto_sqp_k_reg_ladder(const dto_sqp_args* a, int32_t m, void* s)
+{
+    if (a->B <= 0) return 0;
+    k_reg_ladder<<<(unsigned)((a->B + 127) / 128), 128, 0, (cudaStream_t)s>>>(*a, m);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+extern "C" int dto_sqp_k_reg_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* s)
+{
+    if (count <= 0) return 0;
+    k_reg_pick<<<(unsigned)count, 256, 0, (cudaStream_t)s>>>(*a, count, m);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}

@@ -45,6 +45,21 @@ typedef struct dto_sqp_args {
     const double* free;   /* [N_z] 1 = free variable, 0 = pinned by equal bounds               */
     int32_t* counters;    /* [DTO_SQP_N_COUNTERS]                                              */
     int32_t* idx;         /* [B] problem list of a subset launch                               */
+    int32_t* oidx;        /* [B] problems whose line search is still open after a round        */
+    /* trial slots: the remaining step lengths of the open problems evaluated in one pass */
+    int32_t N_w;
+    const double* w;      /* [B][N_w] per-problem parameters of the batch                      */
+    double *tz, *tw, *tf, *tc;   /* [cap][N_z], [cap][N_w], [cap], [cap][N_c]                  */
+    /* candidate slots of the inertia correction: several regularisations of a problem factorised at once */
+    int32_t* vidx;        /* [V] problem of candidate slot v                                   */
+    double* vreg;         /* [V] its regularisation                                            */
+    double* vsol;         /* [V][dim]                                                          */
+    int32_t* vnneg;       /* [V]                                                               */
+    double* vL;           /* [V][factor_stride]                                                */
+    double* L;            /* [B][factor_stride] the batch's factors (the chosen candidate's is copied here) */
+    double* sol_w;        /* = sol, writable                                                   */
+    int32_t* nneg_w;      /* = nneg, writable                                                  */
+    int64_t factor_stride;
 } dto_sqp_args;
 
 /* each returns 0 or -(cudaError_t) */
@@ -58,6 +73,14 @@ int dto_sqp_k_ls_round(const dto_sqp_args* a, int32_t round, void* stream);
 int dto_sqp_k_soc_trial(const dto_sqp_args* a, int32_t count, void* stream);
 int dto_sqp_k_soc_accept(const dto_sqp_args* a, int32_t count, void* stream);
 int dto_sqp_k_end(const dto_sqp_args* a, void* stream);
+/* the next m regularisations of every bad problem (the values m sequential tries would use) into candidate slots k*m + j */
+int dto_sqp_k_reg_ladder(const dto_sqp_args* a, int32_t m, void* stream);
+/* per bad problem: the first candidate with the right inertia and a finite solution is kept (factor and solution copied) */
+int dto_sqp_k_reg_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* stream);
+/* slot k * R + j (k-th entry of oidx, j < R) <- z + alpha 2^-j dz and the problem's parameters */
+int dto_sqp_k_multi_trial(const dto_sqp_args* a, int32_t count, int32_t R, void* stream);
+/* per open problem: the first j whose trial passes the Armijo test is taken, as R sequential rounds would */
+int dto_sqp_k_multi_pick(const dto_sqp_args* a, int32_t count, int32_t R, void* stream);
 
 #ifdef __cplusplus
 }

@@ -414,10 +414,13 @@ class Solver:
 
     def solve(self, options: Optional[dict] = None, record_iterates: bool = False, method: str = "auto"):
         """solve!(solver) (src/solver.jl:45-47) for every problem of the batch. The reference's caller is
-        Ipopt, which is not available in this image. Two drivers stand in for it:
-          * "sqp" (default where it applies: exact Hessians, equality constraints, free variables): the
-            lock-step batched Newton-KKT solver of sqp.py -- callbacks, KKT assembly, factorisation and
-            line-search evaluations all on the device, no per-problem host solver (BASELINE config 3);
+        Ipopt, which is not available in this image. These drivers stand in for it:
+          * "native" (default where it applies: exact Hessians, equality constraints, variables free or pinned by
+            equal bounds): the lock-step batched Newton-KKT solver inside libdto.so (dto_sqp_solve) -- callbacks,
+            KKT assembly, factorisation, line-search evaluations and all bookkeeping on the device, no per-problem
+            host solver (BASELINE config 3);
+          * "sqp": the same algorithm with torch doing the bookkeeping (sqp.py `solve`; the statement of the algorithm
+            and the arm the oracle-driven twin mirrors; the only one that records iterates);
           * "broker": B per-problem host NLP solvers (SciPy trust-constr) running in lock step whose
             callbacks rendezvous into batched GPU calls (driver.py): the protocol an Ipopt-
             per-task driver would use.
@@ -428,7 +431,7 @@ class Solver:
             pinned = np.isfinite(lo) & (lo == up)
             ok = (self.nlp.hessian_lagrangian and not np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)
                   and np.array_equal(clo, cup) and self.nlp.num_shards == 1)
-            method = "sqp" if ok else "broker"
+            method = ("sqp" if record_iterates else "native") if ok else "broker"
         if method in ("sqp", "native"):
             from . import sqp
             o = sqp.SQPOptions()

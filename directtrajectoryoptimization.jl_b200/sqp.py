@@ -570,11 +570,14 @@ def solve_native(nlp, z0, lam0=None, options: Optional[SQPOptions] = None) -> SQ
     z, lam = np.empty((B, N_z)), np.empty((B, N_c))
     iters, done = np.empty(B, np.int32), np.empty(B, np.uint8)
     cv, dr, f = np.empty(B), np.empty(B), np.empty(B)
-    stats = np.zeros(8, np.int64)
+    stats = np.zeros(16, np.int64)
     ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
     _lib.check(L.dto_sqp_solve(nlp.handle, C.byref(co), ptr(z0), ptr(lam0), ptr(lo), ptr(up), ptr(z), ptr(lam), ptr(iters), ptr(done),
                                ptr(cv), ptr(dr), ptr(f), ptr(stats)))
     res = SQPResult(z, lam, iters.astype(np.float64), done.astype(bool), cv, dr, f, [])
     res.stats = dict(iterations=int(stats[0]), launches=int(stats[1]), factorisations=int(stats[2]), syncs=int(stats[3]),
-                     refactorisations=int(stats[4]), corrections=int(stats[5]), search_rounds=int(stats[6]))
+                     refactorisations=int(stats[4]), corrections=int(stats[5]), search_rounds=int(stats[6]), multi_trial_passes=int(stats[7]),
+                     phase_ms=dict(callbacks_first_factor=stats[8] / 1e3, inertia_correction=stats[9] / 1e3, line_search=stats[10] / 1e3,
+                                   of_which_corrections=stats[11] / 1e3, setup=stats[12] / 1e3, loop=stats[13] / 1e3,
+                                   results=stats[14] / 1e3))
     return res

@@ -44,7 +44,7 @@ def main(batch=64, T=101):
         xs, us = solver.get_trajectory(b)
         ok += int(np.linalg.norm(xs[0] - x1) < 1e-3 and np.linalg.norm(xs[-1] - xT) < 1e-3 and bool(res.converged[b]))
     print(f"{ok} of {batch} swing-ups solved (||x_1 - x1||, ||x_T - xT|| < 1e-3, KKT residuals converged); "
-          f"median iterations {float(res.iterations.median()):.0f}; kernels launched {solver.sqp_launches}")
+          f"median iterations {float(np.median(res.iterations)):.0f}; kernels launched {solver.sqp_launches}")
     xs, us = solver.get_trajectory(0)
     print("x_1 =", xs[0], " x_T =", xs[-1], " max |u| =", max(abs(u[0]) for u in us))
 

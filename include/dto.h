@@ -266,8 +266,11 @@ void dto_sqp_default_options(dto_sqp_options* o);
  * NULL: primal_bounds (src/data.jl:123-133); a variable with lower == upper is pinned to that value, any other finite
  * bound -> DTO_ERR_UNSUPPORTED, as are inequality constraint rows. Outputs (each may be NULL): z [B][N_z],
  * lambda [B][N_c], iterations [B] (max_iter where not converged), converged [B], constraint_violation [B] = ||c||_inf,
- * dual_residual [B], objective [B]; stats[8] = {iterations run, kernel launches, factorisation launches, host
- * synchronisations, inertia-correction factorisations, second-order-correction solves, line-search rounds, 0}. The final iterate stays resident as the batch's z (dto_get_last_x). */
+ * dual_residual [B], objective [B]; stats[16] = {iterations run, kernel launches, factorisation launches, host
+ * synchronisations, inertia-correction factorisations, second-order-correction solves, sequential line-search rounds,
+ * one-pass evaluations of all remaining step lengths, and host
+ * microseconds spent in: callbacks + first factorisation, inertia correction, line search (with corrections),
+ * second-order corrections; set-up (allocations, tables, host -> device), iteration loop, results (device -> host), 0}. The final iterate stays resident as the batch's z (dto_get_last_x). */
 int dto_sqp_solve(dto_batch* b, const dto_sqp_options* options, const double* z0, const double* lambda0, const double* lower,
                   const double* upper, double* z, double* lambda, int32_t* iterations, uint8_t* converged,
                   double* constraint_violation, double* dual_residual, double* objective, int64_t* stats);

@@ -312,6 +312,9 @@ struct Solver
     state_indices::Vector{Vector{Int}}
     action_indices::Vector{Vector{Int}}
     z::Vector{Float64}                          # host mirror for get_trajectory (src/solver.jl:41-43)
+    lower::Vector{Float64}                      # primal_bounds (src/data.jl:123-133): handed to dto_sqp_solve for batch > 1
+    upper::Vector{Float64}
+    z0::Matrix{Float64}                         # [n, batch] initial guesses of the batched solve (column b = problem b)
 end
 
 function Solver(dynamics, objective, constraints, bounds;
@@ -357,24 +360,80 @@ function Solver(dynamics, objective, constraints, bounds;
     end
     MOI.set(optimizer, MOI.NLPBlock(), block)
     MOI.set(optimizer, MOI.ObjectiveSense(), MOI.MIN_SENSE)
-    Solver(nlp, optimizer, z, xi, ui, zeros(n))
+    Solver(nlp, optimizer, z, xi, ui, zeros(n), lower, upper, zeros(n, batch))
 end
 
-# src/solver.jl:23-47, unchanged semantics (batch == 1; the lock-step driver for batch > 1 is INTEGRATION.md §4)
-function DTO.initialize_states!(solver::Solver, states)
+# src/solver.jl:23-47, unchanged semantics. batch == 1: the one Ipopt instance drives the callbacks (one problem per call).
+# batch > 1: every problem starts from the same guess unless `problem = b` is given, and solve! runs the whole batch in
+# lock step inside libdto.so (dto_sqp_solve below) -- no Ipopt, no per-problem host solver.
+function DTO.initialize_states!(solver::Solver, states; problem::Int=0)
     for (t, xt) in enumerate(states), i in eachindex(xt)
         MOI.set(solver.optimizer, MOI.VariablePrimalStart(), solver.variables[solver.state_indices[t][i]], xt[i])
     end
+    cols = problem == 0 ? (1:size(solver.z0, 2)) : (problem:problem)
+    for (t, xt) in enumerate(states), b in cols
+        solver.z0[solver.state_indices[t], b] = xt
+    end
 end
-function DTO.initialize_controls!(solver::Solver, actions)
+function DTO.initialize_controls!(solver::Solver, actions; problem::Int=0)
     for (t, ut) in enumerate(actions), j in eachindex(ut)
         MOI.set(solver.optimizer, MOI.VariablePrimalStart(), solver.variables[solver.action_indices[t][j]], ut[j])
     end
+    cols = problem == 0 ? (1:size(solver.z0, 2)) : (problem:problem)
+    for (t, ut) in enumerate(actions), b in cols
+        solver.z0[solver.action_indices[t], b] = ut
+    end
 end
-DTO.solve!(solver::Solver) = MOI.optimize!(solver.optimizer)
+
+# ---------------------------------------------------------------- batched solve (dto_sqp_solve, include/dto.h)
+"dto_sqp_options: same fields, same order (4 Int32 then 21 Float64)"
+Base.@kwdef struct SQPOptions
+    max_iter::Int32 = 200;  max_refactor::Int32 = 14;  max_backtrack::Int32 = 10;  soc::Int32 = 1
+    tol_constraint::Float64 = 1.0e-8;  tol_dual::Float64 = 1.0e-6;  dual_reg::Float64 = 1.0e-9
+    reg_first::Float64 = 1.0e-4;  reg_min::Float64 = 1.0e-20;  reg_max::Float64 = 1.0e10
+    reg_inc_first::Float64 = 100.0;  reg_inc::Float64 = 8.0;  reg_dec::Float64 = 1.0 / 3.0
+    armijo::Float64 = 1.0e-4;  merit_margin::Float64 = 1.1;  merit_rho::Float64 = 0.3;  merit_min::Float64 = 1.0
+    lm_first::Float64 = 1.0e-2;  lm_min::Float64 = 1.0e-4;  lm_grow::Float64 = 4.0;  lm_shrink::Float64 = 0.25
+    lm_grow_below::Float64 = 0.3;  lm_zero::Float64 = 1.0e-10
+    lam_max::Float64 = 1.0e4;  exact_below::Float64 = 1.0
+end
+
+"""
+    solve_batch(nlp, z0; lower, upper, options = SQPOptions(), lambda0 = nothing)
+
+All problems of a one-device batch from the guesses `z0[n, B]` (column b = problem b), in lock step on the GPU: the role
+Ipopt plays for one problem in `solve!(solver)` (src/solver.jl:45-47). Equality constraints; variables free or pinned by
+`lower[i] == upper[i]` (anything else throws with DTO_ERR_UNSUPPORTED). Returns a named tuple
+`(z, lambda, iterations, converged, constraint_violation, dual_residual, objective, stats)`.
+"""
+function solve_batch(nlp::BatchedNLPData, z0::Matrix{Float64}; lower=nothing, upper=nothing, options::SQPOptions=SQPOptions(), lambda0=nothing)
+    n, m = num_variables(nlp.shape), num_constraint(nlp.shape)
+    B = size(z0, 2)
+    size(z0, 1) == n || throw(DimensionMismatch("z0 must be [num_variables, batch]"))
+    z, lam = Matrix{Float64}(undef, n, B), Matrix{Float64}(undef, m, B)
+    its, conv = Vector{Int32}(undef, B), Vector{UInt8}(undef, B)
+    cv, dr, f = Vector{Float64}(undef, B), Vector{Float64}(undef, B), Vector{Float64}(undef, B)
+    stats = zeros(Int64, 16)
+    lo = lower === nothing ? Ptr{Float64}(C_NULL) : pointer(lower)
+    up = upper === nothing ? Ptr{Float64}(C_NULL) : pointer(upper)
+    l0 = lambda0 === nothing ? Ptr{Float64}(C_NULL) : pointer(lambda0)
+    GC.@preserve lower upper lambda0 begin
+        check(ccall((:dto_sqp_solve, libdto), Cint,
+                    (Ptr{Cvoid}, Ref{SQPOptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Int32}, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                    nlp.batch, Ref(options), z0, l0, lo, up, z, lam, its, conv, cv, dr, f, stats))
+    end
+    (z=z, lambda=lam, iterations=Int.(its), converged=conv .!= 0, constraint_violation=cv, dual_residual=dr, objective=f, stats=stats)
+end
+
+function DTO.solve!(solver::Solver)
+    size(solver.z0, 2) == 1 && return MOI.optimize!(solver.optimizer)
+    max_iter = Int32(get(solver.optimizer.options, "max_iter", 200))               # Options.max_iter (src/options.jl:9)
+    solve_batch(solver.nlp, solver.z0; lower=solver.lower, upper=solver.upper, options=SQPOptions(max_iter=max_iter))
+end
 "the last z any callback was handed (the reference returns its internal per-knot buffers, src/solver.jl:41-43)"
-function DTO.get_trajectory(solver::Solver)
-    check(ccall((:dto_get_last_x, libdto), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), solver.nlp.batch, 0, solver.z))
+function DTO.get_trajectory(solver::Solver; problem::Int=1)
+    check(ccall((:dto_get_last_x, libdto), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), solver.nlp.batch, problem - 1, solver.z))
     T = length(solver.state_indices)
     [solver.z[solver.state_indices[t]] for t in 1:T], [solver.z[solver.action_indices[t]] for t in 1:T-1]
 end

@@ -148,7 +148,7 @@ def test_reference_solve_tests_with_bound_pinned_end_points():
     rng = np.random.default_rng(4)
     for b in range(B):
         s.initialize_controls([rng.normal(size=1) for _ in range(100)], problem=b)
-    res = s.solve(options=dict(max_iter=300))
+    res = s.solve(options=dict(max_iter=300), method="sqp")
     ok = 0
     for b in range(B):
         xs, _ = s.get_trajectory(b)
@@ -234,3 +234,41 @@ def test_native_solver_full_solves_and_solver_api():
     assert ok >= 0.9 * B, ok
     assert s.sqp_launches > 100 and res.stats["syncs"] < res.stats["launches"]
     s.nlp.close()
+
+
+def test_native_one_pass_line_search_equals_sequential_rounds(monkeypatch):
+    """After the first round the native solver evaluates every remaining step length of the still-open problems in ONE
+    pass over trial slots and takes the first that passes -- which is what the sequential rounds do one host round trip
+    at a time (DTO_SQP_MULTI=0). Same trial points, same kernels, same test: the two must agree bit for bit, on a
+    batch whose searches do backtrack (acrobot swing-up from random controls)."""
+    ma = M.build_acrobot(D, T=101, stage_endpoint_constraints=False)
+    B = 48
+    pn = D.solver_from(ma, batch=B).nlp
+    z0 = _guess(ma, B, 12)
+    opts = sqp.SQPOptions(max_iter=60)
+    one = sqp.solve_native(pn, z0, options=opts)
+    monkeypatch.setenv("DTO_SQP_MULTI", "0")
+    seq = sqp.solve_native(pn, z0, options=opts)
+    assert one.stats["multi_trial_passes"] > 0 and seq.stats["multi_trial_passes"] == 0
+    assert seq.stats["search_rounds"] > one.stats["search_rounds"]          # the searches did go past the first round
+    assert np.array_equal(one.z, seq.z) and np.array_equal(one.lam, seq.lam)
+    assert np.array_equal(one.iterations, seq.iterations) and np.array_equal(one.constraint_violation, seq.constraint_violation)
+    pn.close()
+
+
+def test_native_inertia_ladder_equals_one_try_per_pass(monkeypatch):
+    """Inertia correction: the native solver factorises the next four regularisations of every bad problem side by side
+    (candidate slots of the factor kernel) and keeps the first that gives N_c negative pivots; DTO_SQP_LADDER=1 tries
+    them one factorisation pass at a time. Same ladder, same factor kernel: bit-identical iterates, fewer passes."""
+    ma = M.build_acrobot(D, T=101, stage_endpoint_constraints=False)
+    B = 48
+    pn = D.solver_from(ma, batch=B).nlp
+    z0 = _guess(ma, B, 12)
+    opts = sqp.SQPOptions(max_iter=60)
+    par = sqp.solve_native(pn, z0, options=opts)
+    monkeypatch.setenv("DTO_SQP_LADDER", "1")
+    seq = sqp.solve_native(pn, z0, options=opts)
+    assert 0 < par.stats["refactorisations"] < seq.stats["refactorisations"]
+    assert np.array_equal(par.z, seq.z) and np.array_equal(par.lam, seq.lam)
+    assert np.array_equal(par.iterations, seq.iterations) and np.array_equal(par.dual_residual, seq.dual_residual)
+    pn.close()
