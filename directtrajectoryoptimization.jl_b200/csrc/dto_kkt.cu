@@ -572,6 +572,9 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_resolve_kernel(con
         cp_async_wait<2>();
         __syncwarp();
         const double* sl = reinterpret_cast<const double*>(gsm + (blk % SM::RING) * SM::SLOT);
+        // y_j / d_j is applied by the lane that owns row j (i == s), to its own value: one reciprocal per lane and block
+        // (of the pivot of its own column) instead of one per step -- the same 1 / d_j the factor kernel multiplies by
+        const double dinv = 1.0 / sl[i * LW];
 #pragma unroll
         for (int s = 0; s < G; ++s) {
             const bool inA = i > s && i <= s + BW;
@@ -579,7 +582,6 @@ __global__ void __launch_bounds__(128, (W == 16 ? 4 : 2)) kkt_resolve_kernel(con
             const bool inB = hasB && (i <= s + BW - G);
             const double lA = inA ? sl[s * LW + (i - s)] : 0.0;
             const double lB = inB ? sl[s * LW + (i + G - s)] : 0.0;
-            const double dinv = 1.0 / sl[s * LW];
             const double yj = shfl_g<G>(ra, s);
             ra = fma(-lA, yj, ra);
             if (hasB) rb = fma(-lB, yj, rb);

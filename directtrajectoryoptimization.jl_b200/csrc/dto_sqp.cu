@@ -159,8 +159,12 @@ __global__ void k_after_first(const dto_sqp_args a)
         const bool bad = (a.nneg[b] != a.N_c || !fin) && !done;
         a.bad[b] = bad ? 1 : 0;
         a.first[b] = 1;
+        a.tries[b] = 0;
         if (done) atomicAdd(a.counters + DTO_SQP_N_DONE, 1);
-        if (bad) atomicAdd(a.counters + DTO_SQP_N_BAD, 1);
+        if (bad) {
+            a.pred_next[atomicAdd(a.counters + DTO_SQP_N_BAD, 1)] = (int32_t)b;   // likely to need the correction again next time
+            if (a.p.max_refactor > 0) atomicAdd(a.counters + DTO_SQP_N_RETRY, 1);
+        }
     }
 }
 
@@ -168,7 +172,7 @@ __global__ void k_after_first(const dto_sqp_args a)
 __global__ void k_reg_next(const dto_sqp_args a)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B || !a.bad[b]) return;
+    if (b >= a.B || !a.bad[b] || a.tries[b] >= a.p.max_refactor) return;
     const double dl = a.delta_last[b], d = a.delta[b];
     const double start = dl == 0.0 ? a.p.reg_first : fmax(a.p.reg_min, a.p.reg_dec * dl);
     const double grow = dl == 0.0 ? a.p.reg_inc_first : a.p.reg_inc;
@@ -176,6 +180,7 @@ __global__ void k_reg_next(const dto_sqp_args a)
     a.delta[b] = nxt;
     a.preg[b] = nxt;
     a.first[b] = 0;
+    a.tries[b] += 1;
     a.idx[atomicAdd(a.counters + DTO_SQP_N_IDX, 1)] = (int32_t)b;
 }
 
@@ -190,6 +195,7 @@ __global__ void k_recheck(const dto_sqp_args a, int32_t count)
         const bool bad = a.nneg[b] != a.N_c || !fin;   // (these problems are not done)
         a.bad[b] = bad ? 1 : 0;
         if (bad) atomicAdd(a.counters + DTO_SQP_N_BAD, 1);
+        if (bad && a.tries[b] < a.p.max_refactor) atomicAdd(a.counters + DTO_SQP_N_RETRY, 1);
     }
 }
 
@@ -279,7 +285,8 @@ __global__ void k_ls_round(const dto_sqp_args a, int32_t round)
     if (round == 0 && a.p.soc) {
         // second-order correction candidates: rejected full steps that did not even reduce the constraint violation
         const bool need = !accepted && ct1 >= a.c1[b];
-        if (need) row_axpy(a.bc + b * a.N_c, a.ckeep + b * a.N_c, 1.0, ct, a.N_c, lane);   // c(z) + c(z + dz)
+        // c(z) + c(z + dz), straight into the constraint part of the right-hand side [g + J'lam ; c] (the rest of it stays)
+        if (need) row_axpy(a.rhs + b * a.dim + a.N_z, a.ckeep + b * a.N_c, 1.0, ct, a.N_c, lane);
         if (lane == 0) {
             a.need[b] = need ? 1 : 0;
             if (need) a.idx[atomicAdd(a.counters + DTO_SQP_N_NEED, 1)] = (int32_t)b;
@@ -417,38 +424,64 @@ __global__ void k_multi_pick(const dto_sqp_args a, int32_t count, int32_t R)
 // pivot count, then with nxt_2 = grow * nxt_1, ... Each try costs the full latency of a banded factorisation however
 // few problems take part, so the next m values of the ladder are factorised side by side in candidate slots and the
 // first one that works is kept: the same regularisation, factor and step the sequential tries end with.
+// the next values of problem b's ladder from (d, first): what m sequential tries would use; entries past the problem's
+// remaining tries repeat the last value (a duplicate factorisation nobody prefers)
+__device__ __forceinline__ void ladder_values(const dto_sqp_args& a, int64_t b, double d, bool first, int32_t m, int32_t left, int64_t k,
+                                              double* __restrict__ vreg, int32_t* __restrict__ vidx)
+{
+    const double dl = a.delta_last[b];
+    const double start = dl == 0.0 ? a.p.reg_first : fmax(a.p.reg_min, a.p.reg_dec * dl);
+    const double grow = dl == 0.0 ? a.p.reg_inc_first : a.p.reg_inc;
+    for (int j = 0; j < m; ++j) {
+        if (j < left) d = first ? fmax(start, 2.0 * d) : fmin(a.p.reg_max, grow * d);
+        first = false;
+        vreg[k * m + j] = d;
+        vidx[k * m + j] = (int32_t)b;
+    }
+}
+
 __global__ void k_reg_ladder(const dto_sqp_args a, int32_t m)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B || !a.bad[b]) return;
-    const double dl = a.delta_last[b];
-    const double start = dl == 0.0 ? a.p.reg_first : fmax(a.p.reg_min, a.p.reg_dec * dl);
-    const double grow = dl == 0.0 ? a.p.reg_inc_first : a.p.reg_inc;
-    double d = a.delta[b];
-    bool first = a.first[b] != 0;
+    const int32_t left = a.p.max_refactor - a.tries[b];
+    if (left <= 0) return;
     const int64_t k = atomicAdd(a.counters + DTO_SQP_N_IDX, 1);
     a.idx[k] = (int32_t)b;
-    for (int j = 0; j < m; ++j) {
-        d = first ? fmax(start, 2.0 * d) : fmin(a.p.reg_max, grow * d);
-        first = false;
-        a.vreg[k * m + j] = d;
-        a.vidx[k * m + j] = (int32_t)b;
-    }
+    ladder_values(a, b, a.delta[b], a.first[b] != 0, m, left, k, a.vreg, a.vidx);
     a.first[b] = 0;
+    a.tries[b] += left < m ? left : m;
 }
 
-__global__ void __launch_bounds__(256) k_reg_pick(const dto_sqp_args a, int32_t count, int32_t m)
+// prediction (before this iteration's first factorisation is known): the ladder a listed problem WOULD climb if its
+// damping lm turns out not to be enough -- delta = lm and first = true are what k_reg_ladder would see after the check
+__global__ void k_pred_ladder(const dto_sqp_args a, int32_t count, int32_t m)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int64_t b = a.pred_cur[k];
+    ladder_values(a, b, a.delta[b], true, m, a.p.max_refactor, k, a.vreg2, a.vidx2);
+}
+
+// block per listed problem: the first candidate with N_c negative pivots and a finite solution is kept
+template <bool PRED>
+__global__ void __launch_bounds__(256) k_pick(const dto_sqp_args a, int32_t count, int32_t m)
 {
     __shared__ int s_pick, s_good;
     const int64_t k = blockIdx.x;
-    const int64_t b = a.idx[k];
+    const int64_t b = PRED ? a.pred_cur[k] : a.idx[k];
+    if (PRED && !a.bad[b]) return;        // the damping was enough after all: the candidates are dropped
+    const double* __restrict__ vreg = PRED ? a.vreg2 : a.vreg;
+    const double* __restrict__ vsol = PRED ? a.vsol2 : a.vsol;
+    const int32_t* __restrict__ vnneg = PRED ? a.vnneg2 : a.vnneg;
+    const double* __restrict__ vL = PRED ? a.vL2 : a.vL;
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         int pick = m - 1, good = 0;
         for (int j = 0; j < m; ++j) {
             const int64_t v = k * m + j;
-            const bool fin = finite_row(a.vsol + v * a.dim, a.dim, lane);
-            if (a.vnneg[v] == a.N_c && fin) {
+            const bool fin = finite_row(vsol + v * a.dim, a.dim, lane);
+            if (vnneg[v] == a.N_c && fin) {
                 pick = j;
                 good = 1;
                 break;
@@ -458,18 +491,26 @@ __global__ void __launch_bounds__(256) k_reg_pick(const dto_sqp_args a, int32_t 
             s_pick = pick;
             s_good = good;
             const int64_t v = k * m + pick;
-            a.delta[b] = a.vreg[v];      // a failed ladder leaves the last value tried, as sequential tries do
-            a.preg[b] = a.vreg[v];
-            a.nneg_w[b] = a.vnneg[v];
+            a.delta[b] = vreg[v];      // a failed ladder leaves the last value tried, as sequential tries do
+            a.preg[b] = vreg[v];
+            a.nneg_w[b] = vnneg[v];
             a.bad[b] = good ? 0 : 1;
-            if (!good) atomicAdd(a.counters + DTO_SQP_N_BAD, 1);
+            if (PRED) {
+                a.first[b] = 0;
+                a.tries[b] = m < a.p.max_refactor ? m : a.p.max_refactor;
+                // k_after_first counted this problem as bad with tries left: no longer, if repaired or out of tries
+                if (good || a.tries[b] >= a.p.max_refactor) atomicSub(a.counters + DTO_SQP_N_RETRY, 1);
+            } else {
+                if (!good) atomicAdd(a.counters + DTO_SQP_N_BAD, 1);
+                if (!good && a.tries[b] < a.p.max_refactor) atomicAdd(a.counters + DTO_SQP_N_RETRY, 1);
+            }
         }
     }
     __syncthreads();
     const int64_t v = k * m + s_pick;
-    for (int i = threadIdx.x; i < a.dim; i += blockDim.x) a.sol_w[b * a.dim + i] = a.vsol[v * a.dim + i];
+    for (int i = threadIdx.x; i < a.dim; i += blockDim.x) a.sol_w[b * a.dim + i] = vsol[v * a.dim + i];
     if (s_good) {   // the factor is read again by a second-order correction
-        const double2* __restrict__ src = reinterpret_cast<const double2*>(a.vL + (size_t)v * a.factor_stride);
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(vL + (size_t)v * a.factor_stride);
         double2* __restrict__ dst = reinterpret_cast<double2*>(a.L + (size_t)b * a.factor_stride);
         const int64_t n2 = a.factor_stride / 2, step = blockDim.x;
         for (int64_t i = threadIdx.x; i < n2; i += 4 * step) {
@@ -526,7 +567,21 @@ extern "C" int dto_sqp_k_reg_ladder(const dto_sqp_args* a, int32_t m, void* s)
 extern "C" int dto_sqp_k_reg_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* s)
 {
     if (count <= 0) return 0;
-    k_reg_pick<<<(unsigned)count, 256, 0, (cudaStream_t)s>>>(*a, count, m);
+    k_pick<false><<<(unsigned)count, 256, 0, (cudaStream_t)s>>>(*a, count, m);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+extern "C" int dto_sqp_k_pred_ladder(const dto_sqp_args* a, int32_t count, int32_t m, void* s)
+{
+    if (count <= 0) return 0;
+    k_pred_ladder<<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)s>>>(*a, count, m);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+extern "C" int dto_sqp_k_pred_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* s)
+{
+    if (count <= 0) return 0;
+    k_pick<true><<<(unsigned)count, 256, 0, (cudaStream_t)s>>>(*a, count, m);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }

@@ -18,10 +18,11 @@ typedef struct dto_sqp_params {   /* SQPOptions of sqp.py, same meaning */
     double lm_first, lm_min, lm_grow, lm_shrink, lm_grow_below, lm_zero;
     double exact_below, lam_max;
     int32_t soc;
+    int32_t max_refactor;   /* inertia-correction tries per problem and iteration */
 } dto_sqp_params;
 
 enum { DTO_SQP_N_DONE = 0, DTO_SQP_N_BAD = 1, DTO_SQP_N_IDX = 2, DTO_SQP_N_NEED = 3, DTO_SQP_N_OPEN = 4, DTO_SQP_N_SOC_OK = 5,
-       DTO_SQP_N_COUNTERS = 8 };
+       DTO_SQP_N_RETRY = 6 /* bad problems that still have tries left */, DTO_SQP_N_COUNTERS = 8 };
 
 typedef struct dto_sqp_args {
     int64_t B;
@@ -33,7 +34,7 @@ typedef struct dto_sqp_args {
     const double* bf;     /* [B]       objective                                               */
     const double* bg;     /* [B][N_z]  gradient                                                */
     double* bc;           /* [B][N_c]  constraint values (overwritten by trial evaluations)    */
-    const double* rhs;    /* [B][dim]  [g + J'lam ; c]                                         */
+    double* rhs;          /* [B][dim]  [g + J'lam ; c] (a second-order correction rewrites its c part) */
     const double* sol;    /* [B][dim]  K^-1 rhs                                                */
     double* preg;         /* [B]       per-problem primal regularisation read by the factor kernel */
     const int32_t* nneg;  /* [B]       negative pivots of the last factorisation              */
@@ -60,6 +61,16 @@ typedef struct dto_sqp_args {
     double* sol_w;        /* = sol, writable                                                   */
     int32_t* nneg_w;      /* = nneg, writable                                                  */
     int64_t factor_stride;
+    int32_t* tries;       /* [B] inertia-correction tries used by the problem in this iteration */
+    /* prediction: the problems whose first factorisation had the wrong inertia in the previous iteration get their ladder
+     * factorised in a second set of candidate slots WHILE the first factorisation of this iteration runs */
+    int32_t* pred_cur;    /* [B] list used in this iteration                                   */
+    int32_t* pred_next;   /* [B] list written by this iteration's first check                  */
+    int32_t* vidx2;       /* second candidate set, as above                                    */
+    double* vreg2;
+    double* vsol2;
+    int32_t* vnneg2;
+    double* vL2;
 } dto_sqp_args;
 
 /* each returns 0 or -(cudaError_t) */
@@ -77,6 +88,10 @@ int dto_sqp_k_end(const dto_sqp_args* a, void* stream);
 int dto_sqp_k_reg_ladder(const dto_sqp_args* a, int32_t m, void* stream);
 /* per bad problem: the first candidate with the right inertia and a finite solution is kept (factor and solution copied) */
 int dto_sqp_k_reg_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* stream);
+/* prediction: ladder of the first `count` problems of pred_cur from their damping (before the first factorisation is known) */
+int dto_sqp_k_pred_ladder(const dto_sqp_args* a, int32_t count, int32_t m, void* stream);
+/* after the first check: a predicted problem that did turn out bad takes the first working candidate of the second set */
+int dto_sqp_k_pred_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* stream);
 /* slot k * R + j (k-th entry of oidx, j < R) <- z + alpha 2^-j dz and the problem's parameters */
 int dto_sqp_k_multi_trial(const dto_sqp_args* a, int32_t count, int32_t R, void* stream);
 /* per open problem: the first j whose trial passes the Armijo test is taken, as R sequential rounds would */

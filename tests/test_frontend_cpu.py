@@ -108,7 +108,7 @@ def test_julia_glue_defines_what_it_uses():
             "zeros", "fill", "fill!", "first", "eachindex", "Symbol", "findnz", "dot", "string", "replace", "join", "tempname", "write",
             "strip", "read", "setenv", "haskey", "push!", "enumerate", "vcat", "repeat", "fieldnames", "typeof", "getfield", "String",
             "Int", "Int32", "Int64", "Cint", "Float64", "Vector", "Dict", "IdDict", "Ptr", "isempty", "in", "if", "for", "while",
-            "sizeof", "undef", "Tuple", "Matrix", "Cdouble", "Val", "convert",
+            "sizeof", "undef", "Tuple", "Matrix", "Cdouble", "Val", "convert", "throw", "size", "min", "max",
             "f", "empty"}  # (function-valued arguments)
     unknown = sorted(n for n in called - defined - base if not n[0].isupper() or n in ("Solver",))
     assert unknown == [] or unknown == ["Solver"], unknown

@@ -240,3 +240,35 @@ def test_lone_scaling_is_an_error():
     J = np.empty((1, s.nlp.num_jacobian))
     with pytest.raises(ValueError):
         s.nlp.eval_jacobian_hessian(J, H, None, scaling=2.0)
+
+
+def test_native_solver_options_agree_across_the_three_languages():
+    """dto_sqp_options (include/dto.h), SQPOptions (sqp.py) and SQPOptions (julia/DTOB200.jl) describe the same algorithm:
+    the C defaults (dto_sqp_default_options runs without a GPU) equal the python defaults field by field, the ctypes
+    mirror has the C struct's field order, and so has the Julia struct."""
+    import ctypes as C
+    import re
+    from dto_b200 import _lib, sqp
+    HERE = os.path.dirname(os.path.abspath(__file__))
+    hdr = open(os.path.join(os.path.dirname(HERE), "include", "dto.h")).read()
+    body = re.search(r"typedef struct dto_sqp_options \{(.*?)\} dto_sqp_options;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for decl in body.split(";"):
+        m = re.match(r"\s*(int32_t|double)\s+(.*)", decl.strip(), flags=re.S)
+        if m:
+            c_fields += [(n.strip(), m.group(1)) for n in m.group(2).split(",")]
+    assert [n for n, _ in c_fields] == [n for n, _ in _lib.SqpOptions._fields_]
+    assert all((t is C.c_int32) == (ct == "int32_t") for (_, ct), (_, t) in zip(c_fields, _lib.SqpOptions._fields_))
+    co = _lib.SqpOptions()
+    _lib.lib().dto_sqp_default_options(C.byref(co))
+    po = sqp.SQPOptions()
+    for name, _ in c_fields:
+        assert float(getattr(co, name)) == float(getattr(po, name)), name
+    jl = open(os.path.join(os.path.dirname(HERE), "julia", "DTOB200.jl")).read()
+    jbody = re.search(r"Base\.@kwdef struct SQPOptions(.*?)\nend", jl, flags=re.S).group(1)
+    j_fields = re.findall(r"(\w+)::(Int32|Float64)\s*=\s*([^;\n]+)", jbody)
+    assert [n for n, _, _ in j_fields] == [n for n, _ in c_fields]
+    assert all((jt == "Int32") == (ct == "int32_t") for (_, jt, _), (_, ct) in zip(j_fields, c_fields))
+    for name, _, val in j_fields:
+        assert abs(float(eval(val.strip())) - float(getattr(po, name))) <= 1e-15 * abs(float(getattr(po, name))), name

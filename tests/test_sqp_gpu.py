@@ -259,16 +259,23 @@ def test_native_one_pass_line_search_equals_sequential_rounds(monkeypatch):
 def test_native_inertia_ladder_equals_one_try_per_pass(monkeypatch):
     """Inertia correction: the native solver factorises the next four regularisations of every bad problem side by side
     (candidate slots of the factor kernel) and keeps the first that gives N_c negative pivots; DTO_SQP_LADDER=1 tries
-    them one factorisation pass at a time. Same ladder, same factor kernel: bit-identical iterates, fewer passes."""
+    the values one factorisation pass at a time; DTO_SQP_PREDICT=1 (an experiment, no faster) also factorises the ladder
+    of last iteration's bad problems on a side stream beside the first factorisation. Same ladder, same factor kernel:
+    bit-identical iterates in all three modes, fewer passes."""
     ma = M.build_acrobot(D, T=101, stage_endpoint_constraints=False)
     B = 48
     pn = D.solver_from(ma, batch=B).nlp
     z0 = _guess(ma, B, 12)
     opts = sqp.SQPOptions(max_iter=60)
+    lad = sqp.solve_native(pn, z0, options=opts)      # the default: ladder in candidate slots after the first check
+    monkeypatch.setenv("DTO_SQP_PREDICT", "1")        # experiment: + candidates of last iteration's bad problems beside the first factorisation
     par = sqp.solve_native(pn, z0, options=opts)
+    monkeypatch.delenv("DTO_SQP_PREDICT")
     monkeypatch.setenv("DTO_SQP_LADDER", "1")
     seq = sqp.solve_native(pn, z0, options=opts)
-    assert 0 < par.stats["refactorisations"] < seq.stats["refactorisations"]
-    assert np.array_equal(par.z, seq.z) and np.array_equal(par.lam, seq.lam)
-    assert np.array_equal(par.iterations, seq.iterations) and np.array_equal(par.dual_residual, seq.dual_residual)
+    assert par.stats["predicted_passes"] > 0 and lad.stats["predicted_passes"] == 0 and seq.stats["predicted_passes"] == 0
+    assert par.stats["refactorisations"] <= lad.stats["refactorisations"] < seq.stats["refactorisations"]
+    for other in (par, seq):
+        assert np.array_equal(lad.z, other.z) and np.array_equal(lad.lam, other.lam)
+        assert np.array_equal(lad.iterations, other.iterations) and np.array_equal(lad.dual_residual, other.dual_residual)
     pn.close()
