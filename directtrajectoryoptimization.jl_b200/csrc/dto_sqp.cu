@@ -161,6 +161,7 @@ __global__ void k_after_first(const dto_sqp_args a)
         a.first[b] = 1;
         a.tries[b] = 0;
         if (done) atomicAdd(a.counters + DTO_SQP_N_DONE, 1);
+        if (!done) a.alist[atomicAdd(a.counters + DTO_SQP_N_ACTIVE, 1)] = (int32_t)b;   // the next first factorisation skips the others
         if (bad) {
             a.pred_next[atomicAdd(a.counters + DTO_SQP_N_BAD, 1)] = (int32_t)b;   // likely to need the correction again next time
             if (a.p.max_refactor > 0) atomicAdd(a.counters + DTO_SQP_N_RETRY, 1);

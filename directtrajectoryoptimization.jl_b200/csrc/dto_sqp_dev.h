@@ -22,7 +22,8 @@ typedef struct dto_sqp_params {   /* SQPOptions of sqp.py, same meaning */
 } dto_sqp_params;
 
 enum { DTO_SQP_N_DONE = 0, DTO_SQP_N_BAD = 1, DTO_SQP_N_IDX = 2, DTO_SQP_N_NEED = 3, DTO_SQP_N_OPEN = 4, DTO_SQP_N_SOC_OK = 5,
-       DTO_SQP_N_RETRY = 6 /* bad problems that still have tries left */, DTO_SQP_N_COUNTERS = 8 };
+       DTO_SQP_N_RETRY = 6 /* bad problems that still have tries left */, DTO_SQP_N_ACTIVE = 7 /* not converged */,
+       DTO_SQP_N_COUNTERS = 8 };
 
 typedef struct dto_sqp_args {
     int64_t B;
@@ -62,6 +63,7 @@ typedef struct dto_sqp_args {
     int32_t* nneg_w;      /* = nneg, writable                                                  */
     int64_t factor_stride;
     int32_t* tries;       /* [B] inertia-correction tries used by the problem in this iteration */
+    int32_t* alist;       /* [B] problems that have not converged (written by the first check, for the next iteration) */
     /* prediction: the problems whose first factorisation had the wrong inertia in the previous iteration get their ladder
      * factorised in a second set of candidate slots WHILE the first factorisation of this iteration runs */
     int32_t* pred_cur;    /* [B] list used in this iteration                                   */

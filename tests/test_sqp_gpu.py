@@ -279,3 +279,22 @@ def test_native_inertia_ladder_equals_one_try_per_pass(monkeypatch):
         assert np.array_equal(lad.z, other.z) and np.array_equal(lad.lam, other.lam)
         assert np.array_equal(lad.iterations, other.iterations) and np.array_equal(lad.dual_residual, other.dual_residual)
     pn.close()
+
+
+def test_native_solver_leaves_converged_problems_out_of_the_factorisation(monkeypatch):
+    """Once half of the batch has converged, the first factorisation of an iteration runs over the list of problems that
+    have not (DTO_SQP_SKIP_DONE=0: always everything). A converged problem's step is never taken, so nothing may change:
+    iterates, iteration counts, residuals bit for bit -- on a batch whose problems converge at different iterations."""
+    ma = M.build_acrobot(D, T=101, stage_endpoint_constraints=False)
+    B = 32
+    pn = D.solver_from(ma, batch=B).nlp
+    z0 = _guess(ma, B, 12)
+    opts = sqp.SQPOptions(max_iter=260)
+    on = sqp.solve_native(pn, z0, options=opts)
+    monkeypatch.setenv("DTO_SQP_SKIP_DONE", "0")
+    off = sqp.solve_native(pn, z0, options=opts)
+    assert 2 * on.converged.sum() > B and len(set(on.iterations[on.converged].tolist())) >= 3
+    assert np.array_equal(on.z, off.z) and np.array_equal(on.lam, off.lam) and np.array_equal(on.iterations, off.iterations)
+    assert np.array_equal(on.constraint_violation, off.constraint_violation) and np.array_equal(on.dual_residual, off.dual_residual)
+    assert np.array_equal(on.objective, off.objective)
+    pn.close()
