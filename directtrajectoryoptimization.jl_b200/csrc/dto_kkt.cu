@@ -67,14 +67,19 @@ __device__ __forceinline__ void cp_async_wait()
 
 // band entries of row (blk*W + i): slot w holds the column c = w (mod W) of [row-W+1, row].
 // JbmH = (this problem's J) - nnz_H, so that a table entry s >= nnz_H addresses J[s - nnz_H].
-__device__ __forceinline__ double row_shift(const dto_kkt_args& a, size_t row, int64_t b)
+template <bool DIAG = false>
+__device__ __forceinline__ double row_shift(const dto_kkt_args& a, size_t row, int64_t b, int64_t bd = -1)
 {
-    // diagonal shift of permuted row `row`: +primal_reg (per problem when a.preg is given), -dual_reg, 1.0 on padding
-    double reg = a.dreg[row];
+    // diagonal shift of permuted row `row`: +primal_reg (per problem when a.preg is given), -dual_reg, 1.0 on padding;
+    // DIAG: + the barrier diagonal of problem bd (a candidate slot's regularisation is the slot's, its diagonal the problem's)
     if (a.rowfixed != nullptr && a.rowfixed[row]) return 1.0;   // pinned variable: identity row
-    if (a.preg != nullptr) {
+    double reg = a.dreg[row];
+    if (a.preg != nullptr || (DIAG && a.diag != nullptr)) {
         const int32_t ip = a.iperm[row];
-        if (ip >= 0 && ip < a.N_z) reg = a.preg[b];
+        if (ip >= 0 && ip < a.N_z) {
+            if (a.preg != nullptr) reg = a.preg[b];
+            if (DIAG && a.diag != nullptr) reg += a.diag[(bd >= 0 ? bd : b) * a.N_z + ip];
+        }
     }
     return reg;
 }
@@ -101,12 +106,12 @@ __device__ __forceinline__ double rhs_entry(const dto_kkt_args& a, int64_t b, in
     return h;
 }
 
-template <int W>
+template <int W, bool DIAG = false>
 __device__ __forceinline__ void load_rows(const dto_kkt_args& a, const double* __restrict__ Hb, const double* __restrict__ JbmH,
-                                          int blk, int i, double (&X)[W], int64_t b = 0)
+                                          int blk, int i, double (&X)[W], int64_t b = 0, int64_t bd = -1)
 {
     const int32_t* src = a.src + ((size_t)blk * W) * W + i;
-    const double reg = row_shift(a, (size_t)blk * W + i, b);
+    const double reg = row_shift<DIAG>(a, (size_t)blk * W + i, b, bd);
     int32_t sidx[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) sidx[w] = src[w * W];
@@ -218,7 +223,8 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
 // spilled values; pays off only when the launch has more than 16 warps per SM to offer, i.e. B > ~4700)
 // VIRT = candidate launch (dto_kkt_args::virt): outputs and regularisation indexed by slot. A separate instantiation: as a
 // run-time switch its extra live index cost the default path registers and spills (acrobot, 64 problems: 0.275 vs 0.204 ms)
-template <int W, int BW, int MINB = (W == 16 ? 4 : 2), bool VIRT = false>
+// DIAG = a per-problem, per-variable diagonal is added to the Hessian block (dto_kkt_args::diag); separate for the same reason
+template <int W, int BW, int MINB = (W == 16 ? 4 : 2), bool VIRT = false, bool DIAG = false>
 __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args a)
 {
     constexpr int G = W;
@@ -252,10 +258,10 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     double A[W], Bv[W];
     double ra, rb = 0.0, rc = 0.0, regc = 0.0;
     int32_t nidx[W];                                  // gather indices of the rows two blocks ahead
-    load_rows<W>(a, Hb, Jb, 0, i, A, bo);
+    load_rows<W, DIAG>(a, Hb, Jb, 0, i, A, bo, b);
     ra = rhs_at(a.iperm[i]);
     if (nblk > 1) {
-        load_rows<W>(a, Hb, Jb, 1, i, Bv, bo);
+        load_rows<W, DIAG>(a, Hb, Jb, 1, i, Bv, bo, b);
         rb = rhs_at(a.iperm[W + i]);
     } else {
 #pragma unroll
@@ -311,11 +317,12 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
                 if (ipn >= 0) rc = hb[ipn];
             }
             regc = (fixn || ipn < 0) ? 1.0 : (ipn < a.N_z ? prim : -a.dual_reg);   // = row_shift(): the values of the dreg table
+            if (DIAG && !fixn && ipn >= 0 && ipn < a.N_z) regc += a.diag[b * a.N_z + ipn];
             load_idx(blk + 3);
             load_static(blk + 3);
 #else
             rc = rhs_at(a.iperm[(size_t)(blk + 2) * W + i]);
-            regc = row_shift(a, (size_t)(blk + 2) * W + i, bo);
+            regc = row_shift<DIAG>(a, (size_t)(blk + 2) * W + i, bo, b);
             load_idx(blk + 3);
 #endif
         }
@@ -607,7 +614,7 @@ __global__ void kkt_assemble_kernel(const dto_kkt_args a, int64_t problem, doubl
     const double* Hb = a.H + problem * a.nnz_H;
     const double* Jb = a.J + problem * a.nnz_J - a.nnz_H;
     double X[W];
-    load_rows<W>(a, Hb, Jb, blk, i, X, problem);
+    load_rows<W, true>(a, Hb, Jb, blk, i, X, problem);
 #pragma unroll
     for (int w = 0; w < W; ++w) out[((size_t)blk * W + w) * W + i] = X[w];
 }
@@ -648,26 +655,29 @@ extern "C" int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream)
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-template <int W, int BW, int MINB, bool VIRT>
+template <int W, int BW, int MINB, bool VIRT, bool DIAG>
 static cudaError_t launch_band_v(const dto_kkt_args* a, cudaStream_t st)
 {
     const int64_t per_block = 4 * (32 / W);
     // the opt-in is per device and a batch may span several: set it on every launch (a cheap driver call
     // next to a >= 100 us kernel) instead of caching it per process
     if (KktSmem<W, BW>::BYTES > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB, VIRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB, VIRT, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
         if (e != cudaSuccess) return e;
     }
-    kkt_band_kernel<W, BW, MINB, VIRT><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
+    kkt_band_kernel<W, BW, MINB, VIRT, DIAG><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
     return cudaGetLastError();
 }
 template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
 static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
 {
-    if (MINB == (W == 16 ? 4 : 2) && a->virt) return launch_band_v<W, BW, (W == 16 ? 4 : 2), true>(a, st);
-    return launch_band_v<W, BW, MINB, false>(a, st);
+    constexpr int DEF = (W == 16 ? 4 : 2);
+    if (MINB == DEF || a->virt || a->diag) {   // candidate slots and the barrier diagonal exist for the default occupancy only
+        if (a->diag) return a->virt ? launch_band_v<W, BW, DEF, true, true>(a, st) : launch_band_v<W, BW, DEF, false, true>(a, st);
+        if (a->virt) return launch_band_v<W, BW, DEF, true, false>(a, st);
+    }
+    return launch_band_v<W, BW, MINB, false, false>(a, st);
 }
-
 template <int W, int BW, int M>
 static cudaError_t launch_band_s(const dto_kkt_args* a, cudaStream_t st)
 {
@@ -688,10 +698,10 @@ extern "C" int dto_kkt_launch_band(const dto_kkt_args* a, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
     const int bound = dto_kkt_bw_bound(a->W, a->bw);
-    const bool two = a->variant != 2 || a->virt;   // candidate launches (slot-indexed outputs) exist in the default kernel only
+    const bool two = a->variant != 2 || a->virt || a->diag;   // candidate slots / barrier diagonal: default kernel only
     // experiment (DTO_KKT_VARIANT=occ5): 5 CTAs per SM, 96 registers, a few spills -- measured slower on every
     // shape (cartpole 0.485 vs 0.346 ms, car 3.09 vs 2.35 ms; profiles/kkt_r01_history.jsonl tags v8 / v8occ5)
-    if (a->variant == 3 && !a->virt && a->W == 16 && (bound == 9 || bound == 15)) {
+    if (a->variant == 3 && !a->virt && !a->diag && a->W == 16 && (bound == 9 || bound == 15)) {
         e = bound == 9 ? launch_band_t<16, 9, 5>(a, st) : launch_band_t<16, 15, 5>(a, st);
         return e == cudaSuccess ? 1 : -(int)e;
     }

@@ -420,7 +420,9 @@ class Solver:
             KKT assembly, factorisation, line-search evaluations and all bookkeeping on the device, no per-problem
             host solver (BASELINE config 3);
           * "sqp": the same algorithm with torch doing the bookkeeping (sqp.py `solve`; the statement of the algorithm
-            and the arm the oracle-driven twin mirrors; the only one that records iterates);
+            and the arm the oracle-driven twin mirrors; the only one that records iterates. When asked for explicitly it
+            also takes inequality bounds on variables -- Bound(action_lower = ..., action_upper = ...) -- by a primal-dual
+            interior point on the same Newton-KKT kernels (no restoration phase: see the scope note in sqp.py));
           * "broker": B per-problem host NLP solvers (SciPy trust-constr) running in lock step whose
             callbacks rendezvous into batched GPU calls (driver.py): the protocol an Ipopt-
             per-task driver would use.
@@ -431,6 +433,8 @@ class Solver:
             pinned = np.isfinite(lo) & (lo == up)
             ok = (self.nlp.hessian_lagrangian and not np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)
                   and np.array_equal(clo, cup) and self.nlp.num_shards == 1)
+            # (inequality bounds on variables: method="sqp" has an interior-point mode, but without a feasibility-restoration
+            # phase it is not robust enough to be the default -- see sqp.py; the broker's per-problem solver is)
             method = ("sqp" if record_iterates else "native") if ok else "broker"
         if method in ("sqp", "native"):
             from . import sqp
@@ -448,7 +452,7 @@ class Solver:
             self.results, self.iterates, self.broker = res, [], None
             return res
         if method == "sqp":
-            be = sqp.DeviceBackend(self.nlp, dual_reg=o.dual_reg)
+            be = sqp.DeviceBackend(self.nlp, dual_reg=o.dual_reg, options=o)
             res = None
             try:
                 z0 = be.torch.as_tensor(self._initial, device=be.xp.device)

@@ -82,7 +82,9 @@ def pendulum_midpoint(y, x, u, w):
     return y - (x + h * pendulum(0.5 * (x + y), u, w))
 
 
-def build_pendulum(api, T=11, evaluate_hessian=True):
+def build_pendulum(api, T=11, evaluate_hessian=True, u_bnd=None):
+    """`u_bnd` (not in the example): |u| <= u_bnd as Bound(action_lower, action_upper) -- the unconstrained swing-up peaks at
+    |u| = 18.6, so e.g. 15 makes the bounds active. Bounds live on the host: the model library is the same."""
     n, m = 2, 1
     dt = api.Dynamics(pendulum_midpoint, n, n, m, num_parameter=0, evaluate_hessian=evaluate_hessian)
     x1 = np.array([0.0, 0.0])
@@ -101,7 +103,7 @@ def build_pendulum(api, T=11, evaluate_hessian=True):
         dynamics=[dt] * (T - 1),
         objective=[ct] * (T - 1) + [cT],
         constraints=[con1] + [api.Constraint() for _ in range(2, T)] + [conT],
-        bounds=[api.Bound(n, m)] * (T - 1) + [api.Bound(n, 0)],
+        bounds=[api.Bound(n, m) if u_bnd is None else api.Bound(n, m, action_lower=[-u_bnd], action_upper=[u_bnd])] * (T - 1) + [api.Bound(n, 0)],
         general=None, evaluate_hessian=evaluate_hessian, x1=x1, xT=xT,
     )
 

@@ -237,7 +237,9 @@ int dto_kkt_get(dto_kkt* k, int which, double* out);
 int dto_kkt_matrix(dto_kkt* k, int64_t problem, double* dense);
 int dto_kkt_factor(dto_kkt* k, int64_t problem, double* Lband, double* D);
 /* which = 0 h, 1 sol, 2 factor storage, 3 per-problem primal regularisation [shard size] (asking for it switches the
- * kernels to per-problem mode: the caller writes it on the device), 4 negative-pivot counts [shard size] int32 */
+ * kernels to per-problem mode: the caller writes it on the device), 4 negative-pivot counts [shard size] int32,
+ * 5 a per-problem, per-variable diagonal [shard size][num_variables] ADDED to the Hessian block from then on (zero at first:
+ * the barrier term Sigma = z_L / (x - l) + z_U / (u - x) of an interior-point solver handling Bound(...), src/bounds.jl) */
 void* dto_kkt_device_pointer(dto_kkt* k, int which, int shard);
 
 /* ---- batched solver: the caller of the callback path ----

@@ -37,7 +37,7 @@ def band_ldl_solve(K, h, perm, bw):
 
 
 class OracleBackend:
-    def __init__(self, osolver, B, dual_reg=1.0e-9, c_twin=None, perm=None, linear="qdldl", bw=None):
+    def __init__(self, osolver, B, dual_reg=1.0e-9, c_twin=None, perm=None, linear="qdldl", bw=None, options=None):
         self.bw = bw
         self.gauss_newton = False
         self.o = osolver.nlp
@@ -45,9 +45,11 @@ class OracleBackend:
         self.xp = _XP(np)
         lo, up = self.o.variable_bounds
         lo, up = np.asarray(lo, float), np.asarray(up, float)
-        self.fixed = np.isfinite(lo) & (lo == up)
+        from dto_b200.sqp import bound_arrays
+        self.fixed, self.bounds = bound_arrays(lo, up, options)
         self.free = (~self.fixed).astype(np.float64)
         self.pinned_value = np.where(self.fixed, lo, 0.0)
+        self.diag = None
         self.dual_reg = dual_reg
         self.co = c_twin
         self.perm = perm
@@ -86,9 +88,12 @@ class OracleBackend:
                 self.o.eval_hessian_lagrangian(out["H"][b], z[b], 1.0, lam[b])
         return out
 
-    def callbacks(self, z, lam, lam_hess, delta=None):
+    def callbacks(self, z, lam, lam_hess, delta=None, diag=None, gshift=None):
         self.cur = self._eval(z, lam_hess, 31)
         self.lam = lam.copy()
+        self.diag = None if diag is None else np.array(diag, copy=True)     # interior point: Sigma on H's diagonal,
+        if gshift is not None:                                              # barrier gradient in g
+            self.cur["g"] = self.cur["g"] + gshift
         return self.cur["f"].copy(), self.cur["g"].copy(), self.cur["c"].copy()
 
     def _assemble(self, b, delta):
@@ -99,6 +104,8 @@ class OracleBackend:
         K[n + jr, jc] = self.cur["J"][b]
         K[jc, n + jr] = self.cur["J"][b]
         K[np.arange(n), np.arange(n)] += delta
+        if self.diag is not None:
+            K[np.arange(n), np.arange(n)] += self.diag[b]
         K[n + np.arange(m), n + np.arange(m)] -= self.dual_reg
         Jd = np.zeros((m, n))
         Jd[jr, jc] = self.cur["J"][b]

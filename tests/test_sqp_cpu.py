@@ -117,3 +117,46 @@ def test_repacking_the_batch_changes_no_result():
     assert res[True].iterations[0] == 0 and res[True].iterations[1] > 0
     for k in ("z", "lam", "objective", "constraint_violation"):
         assert np.array_equal(getattr(res[True], k), getattr(res[False], k)), k
+
+
+def test_interior_point_mode_handles_active_bounds():
+    """Inequality bounds on variables (Bound(action_lower, action_upper), src/bounds.jl; Ipopt's barrier treatment of the
+    bounds MOI hands it, src/data.jl:240-248) in `sqp.solve`: pendulum swing-up with |u| <= 15, whose unconstrained
+    optimum peaks at |u| = 18.6. The result must be a KKT point of the BOUNDED problem, checked from scratch with the
+    oracle: feasibility, strict interior, and stationarity g + J'lam = z_L - z_U with z_L, z_U >= 0 supported only on
+    controls at their bound (complementarity) -- the multipliers are recovered from the residual, not taken from the
+    solver. Bounds that are never active must give back the unconstrained optimum."""
+    mo = M.build_pendulum(O, u_bnd=15.0)
+    osolver = O.solver_from(mo)
+    B = 2
+    opts = sqp.SQPOptions(max_iter=60)
+    be = OracleBackend(osolver, B, linear="dense", options=opts)
+    assert be.bounds is not None and not be.fixed.any()
+    res = sqp.solve(be, _guess(mo, B, 1) * 0.3, options=opts)
+    assert res.converged.all()
+    T, n, m = mo["T"], mo["n"], mo["m"]
+    isu = np.zeros(be.N_z, dtype=bool)
+    isu[[t * (n + m) + n for t in range(T - 1)]] = True
+    nlp = osolver.nlp
+    jr = np.array([r for r, _ in nlp.jacobian_structure()]) - 1
+    jc = np.array([c for _, c in nlp.jacobian_structure()]) - 1
+    for b in range(B):
+        z, lam = res.z[b], res.lam[b]
+        u = z[isu]
+        assert np.all(np.abs(u) < 15.0) and (np.abs(u) > 15.0 - 1e-5).sum() >= 2          # strictly inside, some AT the bound
+        c, g, J = np.zeros(be.N_c), np.zeros(be.N_z), np.zeros(len(jr))
+        nlp.eval_constraint(c, z); nlp.eval_objective_gradient(g, z); nlp.eval_constraint_jacobian(J, z)
+        assert np.max(np.abs(c)) < 1e-8
+        Jd = np.zeros((be.N_c, be.N_z)); Jd[jr, jc] = J
+        r = g + Jd.T @ lam                                    # = z_L - z_U at a KKT point
+        assert np.max(np.abs(r[~isu])) < 1e-5                 # states carry no bound: plain stationarity
+        at_lower, at_upper = u < -15.0 + 1e-4, u > 15.0 - 1e-4
+        ru = r[isu]
+        assert np.all(ru[at_lower] > -1e-5) and np.all(ru[at_upper] < 1e-5)               # signs of the bound multipliers
+        assert np.max(np.abs(ru[~(at_lower | at_upper)])) < 1e-4                          # complementarity: inactive => zero
+    loose = M.build_pendulum(O, u_bnd=1.0e3)
+    ol = O.solver_from(loose)
+    r_loose = sqp.solve(OracleBackend(ol, 1, linear="dense", options=opts), _guess(loose, 1, 1) * 0.3, options=opts)
+    r_free = sqp.solve(OracleBackend(O.solver_from(M.build_pendulum(O)), 1, linear="dense"), _guess(loose, 1, 1) * 0.3, options=opts)
+    assert r_loose.converged.all() and r_free.converged.all()
+    assert abs(r_loose.objective[0] - r_free.objective[0]) < 1e-5 * r_free.objective[0] < res.objective.min() - r_free.objective[0]
