@@ -25,10 +25,12 @@ as in test/solve.jl); inequality rows are rejected, not approximated. Inequality
 as a primal-dual interior point on the same Newton-KKT step -- barrier diagonal inside the factor kernel
 (dto_kkt_device_pointer(k, 5)), fraction-to-the-boundary steps, monotone barrier updates -- but WITHOUT Ipopt's
 feasibility-restoration phase. Measured: the pendulum swing-up with |u| <= 15 (unconstrained peak 18.6) converges in 12
-iterations, device iterates = oracle-twin iterates to 1e-13; cartpole T = 101 converges for bounds the solution does
-not touch (|u| <= 30: 91 % of 32 guesses) and does NOT for the example's |u| <= 3 from the example's guess (all
-controls run into their bounds while the dynamics are still violated, ||c||_inf ~ 0.6: the situation restoration exists
-for). `Solver.solve()` therefore keeps sending bounded problems to the broker unless method="sqp" is asked for. It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
+iterations, device iterates = oracle-twin iterates to 1e-13; the cartpole example (T = 101, the example's guess,
+tools/ip_cartpole.py, profiles/ip_cartpole_r02.jsonl) converges for every guess with |u| <= 30, 10 and 5 (the last in
+24 iterations with a quarter of the controls AT the bound) and does NOT with the example's |u| <= 3: the iterates settle
+at ||c||_inf ~ 0.013 with 96 % of the controls saturated -- a one-swing trajectory that actuator cannot complete; the
+multi-pump solution needs the globalisation (restoration) this solver does not have.
+`Solver.solve()` therefore keeps sending bounded problems to the broker unless method="sqp" is asked for. It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
 damping and Ipopt-style inertia correction of the primal regularisation; it is NOT Ipopt:
 iterate-for-iterate parity with the reference's Ipopt runs is unverifiable here and is not claimed.
 """
@@ -83,6 +85,7 @@ class SQPOptions:
     bound_push: float = 1.0e-2         # kappa_1 / kappa_2 of Ipopt's initial point push
     bound_frac: float = 1.0e-2
     kappa_sigma: float = 1.0e10        # z stays within [mu/(kappa s), kappa mu/s]
+    tiny_step: float = 1.0e-6          # relative step size under which the full (fraction-to-the-boundary) step is taken untested
 
 
 class SQPResult:
@@ -268,6 +271,11 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             # (interior point: Ipopt's relaxation of the test by 10 eps |phi| -- with mu -> 0 the predicted decrease of a
             # converging problem drops below the rounding error of phi itself)
             ok = (phit <= phi0 + o.armijo * alpha * slope + (2.2e-15 * abs(phi0) if ip else 0.0)) & ~accepted
+            if ip and ls == 0:
+                # tiny steps are taken without the test (Ipopt's tiny_step_tol idea, wider): right after mu was decreased the
+                # step mostly re-centres z_L, z_U (dz ~ 1e-7), need not be a descent direction of the NEW barrier function,
+                # and rejecting it would also reject the multiplier step it carries
+                ok = ok | ((xp.max_abs_rows(dz) <= o.tiny_step * (1.0 + xp.max_abs_rows(z))) & ~accepted)
             z = xp.where_rows(ok, zt, z)
             lam = xp.where_rows(ok, lam + alpha[:, None] * dlam, lam)
             if ip:

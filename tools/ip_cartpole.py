@@ -1,0 +1,41 @@
+"""Interior-point mode of sqp.solve on the cartpole example (examples/cartpole/cartpole.jl: T = 101, |u| <= u_bnd, the
+example's guess: states interpolated, controls 0.01 randn):   python tools/ip_cartpole.py [u_bnd] [B] [max_iter]  -> JSON line"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import dto_b200 as D  # noqa: E402
+from examples import models as M  # noqa: E402
+
+ub = float(sys.argv[1]) if len(sys.argv) > 1 else 3.0
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 400
+T = 101
+mc = M.build_cartpole(D, T=T)
+n, m = mc["n"], mc["m"]
+mc["bounds"] = [D.Bound(n, m, action_lower=[-ub], action_upper=[ub])] * (T - 1) + [D.Bound(n, 0)]   # host side: same model library
+s = D.solver_from(mc, batch=B)
+s.nlp.set_parameters(np.tile(np.concatenate([mc["x1"], mc["xT"]]), (B, 1)))      # w = [x1; xT] of every problem (BASELINE config 2 layout)
+s.initialize_states(D.linear_interpolation(mc["x1"], mc["xT"], T))
+rng = np.random.default_rng(7)
+for b in range(B):
+    s.initialize_controls([0.01 * rng.normal(size=1) for _ in range(T - 1)], problem=b)
+so = dict(max_iter=iters)
+so.update(json.loads(os.environ.get("DTO_SQP_OPTIONS", "{}")))
+t0 = time.perf_counter()
+res = s.solve(options=so, method="sqp")
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+it, conv = res.iterations.cpu().numpy(), res.converged.cpu().numpy()
+Z = res.z.cpu().numpy()
+U = np.stack([Z[:, t * (n + m) + n] for t in range(T - 1)], axis=1)
+print(json.dumps(dict(u_bnd=ub, options=so, T=T, B=B, seconds=dt, converged=float(conv.mean()), it_median=float(np.median(it)), it_max=float(it.max()),
+                      cv_max=float(res.constraint_violation.cpu().numpy().max()), dr_median=float(np.median(res.dual_residual.cpu().numpy())),
+                      u_max=float(np.abs(U).max()), end_error_max=float(np.abs(Z[:, -n:] - mc["xT"]).max()), at_bound=float((np.abs(U) > 0.997 * ub).mean()), f_median=float(np.median(res.objective.cpu().numpy())))))
+s.nlp.close()
