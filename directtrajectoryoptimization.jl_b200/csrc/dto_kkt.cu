@@ -36,9 +36,6 @@
 #ifndef DTO_KKT_PREFETCH
 #define DTO_KKT_PREFETCH 1
 #endif
-#ifndef DTO_KKT_FUSE
-#define DTO_KKT_FUSE 1
-#endif
 
 namespace {
 
@@ -224,7 +221,9 @@ __device__ __forceinline__ void kkt_backward(const dto_kkt_args& a, unsigned cha
 // VIRT = candidate launch (dto_kkt_args::virt): outputs and regularisation indexed by slot. A separate instantiation: as a
 // run-time switch its extra live index cost the default path registers and spills (acrobot, 64 problems: 0.275 vs 0.204 ms)
 // DIAG = a per-problem, per-variable diagonal is added to the Hessian block (dto_kkt_args::diag); separate for the same reason
-template <int W, int BW, int MINB = (W == 16 ? 4 : 2), bool VIRT = false, bool DIAG = false>
+// FUSE = the kernel computes the right-hand side itself (dto_kkt_args::fuse_rhs, an option measured slower): its own instantiation too --
+// carrying the code path costs the default kernel 4 % on cartpole (registers)
+template <int W, int BW, int MINB = (W == 16 ? 4 : 2), bool VIRT = false, bool DIAG = false, bool FUSE = false>
 __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args a)
 {
     constexpr int G = W;
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
     // right-hand-side entry of original row ip; a candidate launch always finds it in the rhs array (nothing it depends
     // on changed since the launch that wrote it), which also keeps the problem index out of the loop's live registers
     auto rhs_at = [&](int32_t ip) -> double {
-        if (VIRT || !DTO_KKT_FUSE) return ip < 0 ? 0.0 : hb[ip];
+        if (VIRT || !FUSE) return ip < 0 ? 0.0 : hb[ip];
         return rhs_entry(a, b, ip, hb, valid);
     };
     double A[W], Bv[W];
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
             }
             cp_async_commit();
 #if DTO_KKT_PREFETCH
-            if (a.fuse_rhs) {
+            if (FUSE) {
                 rc = rhs_at(ipn);
             } else {
                 rc = 0.0;
@@ -655,27 +654,27 @@ extern "C" int dto_kkt_launch_rhs(const dto_kkt_args* a, void* stream)
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-template <int W, int BW, int MINB, bool VIRT, bool DIAG>
+template <int W, int BW, int MINB, bool VIRT, bool DIAG, bool FUSE = false>
 static cudaError_t launch_band_v(const dto_kkt_args* a, cudaStream_t st)
 {
     const int64_t per_block = 4 * (32 / W);
     // the opt-in is per device and a batch may span several: set it on every launch (a cheap driver call
     // next to a >= 100 us kernel) instead of caching it per process
     if (KktSmem<W, BW>::BYTES > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB, VIRT, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(kkt_band_kernel<W, BW, MINB, VIRT, DIAG, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, KktSmem<W, BW>::BYTES);
         if (e != cudaSuccess) return e;
     }
-    kkt_band_kernel<W, BW, MINB, VIRT, DIAG><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
+    kkt_band_kernel<W, BW, MINB, VIRT, DIAG, FUSE><<<(unsigned)((a->B + per_block - 1) / per_block), 128, KktSmem<W, BW>::BYTES, st>>>(*a);
     return cudaGetLastError();
 }
 template <int W, int BW, int MINB = (W == 16 ? 4 : 2)>
 static cudaError_t launch_band_t(const dto_kkt_args* a, cudaStream_t st)
 {
     constexpr int DEF = (W == 16 ? 4 : 2);
-    if (MINB == DEF || a->virt || a->diag) {   // candidate slots and the barrier diagonal exist for the default occupancy only
-        if (a->diag) return a->virt ? launch_band_v<W, BW, DEF, true, true>(a, st) : launch_band_v<W, BW, DEF, false, true>(a, st);
-        if (a->virt) return launch_band_v<W, BW, DEF, true, false>(a, st);
-    }
+    // candidate slots, the barrier diagonal and the fused right-hand side exist for the default occupancy only
+    if (a->diag) return a->virt ? launch_band_v<W, BW, DEF, true, true>(a, st) : launch_band_v<W, BW, DEF, false, true>(a, st);
+    if (a->virt) return launch_band_v<W, BW, DEF, true, false>(a, st);
+    if (a->fuse_rhs) return launch_band_v<W, BW, DEF, false, false, true>(a, st);
     return launch_band_v<W, BW, MINB, false, false>(a, st);
 }
 template <int W, int BW, int M>

@@ -231,12 +231,26 @@ def test_kkt_factor_kernel_variants_agree(name, kw, B, config, monkeypatch):
         monkeypatch.setenv("DTO_KKT_VARIANT", variant)
         kkt = PK.KKTSystem(pn)
         sol = np.empty((B, kkt.dim))
+        l0 = pn.launch_count()
         kkt.solve(sol, variables=z, scaling=sigma, duals=lam)
+        launches = pn.launch_count() - l0
         Lm, Dv = kkt.factor(B - 1)
         outs.append((sol, Lm, Dv))
         kkt.close()
     assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[0][0], outs[1][0])
+    # the FUSE instantiation (DTO_KKT_FUSE_RHS=1: the factor kernel forms h = [g + J'y; c] itself, no kkt_rhs_kernel): the
+    # same additions in the same order, so the same bits -- right-hand side, factor and solution
+    monkeypatch.setenv("DTO_KKT_VARIANT", "")
+    monkeypatch.setenv("DTO_KKT_FUSE_RHS", "1")
+    kkt = PK.KKTSystem(pn)
+    sol = np.empty((B, kkt.dim))
+    l0 = pn.launch_count()
+    kkt.solve(sol, variables=z, scaling=sigma, duals=lam)
+    assert pn.launch_count() - l0 == launches - 1             # the callbacks + ONE KKT kernel instead of two
+    Lm, Dv = kkt.factor(B - 1)
+    assert np.array_equal(sol, outs[0][0]) and np.array_equal(Lm, outs[0][1]) and np.array_equal(Dv, outs[0][2])
+    kkt.close()
     pn.close()
 
 
