@@ -420,9 +420,9 @@ class Solver:
             KKT assembly, factorisation, line-search evaluations and all bookkeeping on the device, no per-problem
             host solver (BASELINE config 3);
           * "sqp": the same algorithm with torch doing the bookkeeping (sqp.py `solve`; the statement of the algorithm
-            and the arm the oracle-driven twin mirrors; the only one that records iterates. When asked for explicitly it
-            also takes inequality bounds on variables -- Bound(action_lower = ..., action_upper = ...) -- by a primal-dual
-            interior point on the same Newton-KKT kernels (no restoration phase: see the scope note in sqp.py));
+            and the arm the oracle-driven twin mirrors; the only one that records iterates, and the one that takes
+            inequality bounds on variables -- Bound(action_lower = ..., action_upper = ...), the cartpole example -- by a
+            primal-dual interior point on the same Newton-KKT kernels (no restoration phase: scope note in sqp.py);
           * "broker": B per-problem host NLP solvers (SciPy trust-constr) running in lock step whose
             callbacks rendezvous into batched GPU calls (driver.py): the protocol an Ipopt-
             per-task driver would use.
@@ -431,11 +431,10 @@ class Solver:
             lo, up = self.nlp.variable_bounds
             clo, cup = self.nlp.constraint_bounds
             pinned = np.isfinite(lo) & (lo == up)
-            ok = (self.nlp.hessian_lagrangian and not np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)
-                  and np.array_equal(clo, cup) and self.nlp.num_shards == 1)
-            # (inequality bounds on variables: method="sqp" has an interior-point mode, but without a feasibility-restoration
-            # phase it is not robust enough to be the default -- see sqp.py; the broker's per-problem solver is)
-            method = ("sqp" if record_iterates else "native") if ok else "broker"
+            ok = self.nlp.hessian_lagrangian and np.array_equal(clo, cup) and self.nlp.num_shards == 1
+            inequality_bounds = bool(np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned))
+            # inequality bounds on variables (Bound(action_lower = ..., ...)): the interior-point mode of the torch-glued arm
+            method = ("sqp" if (record_iterates or inequality_bounds) else "native") if ok else "broker"
         if method in ("sqp", "native"):
             from . import sqp
             o = sqp.SQPOptions()

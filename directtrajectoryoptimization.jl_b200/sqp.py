@@ -25,12 +25,13 @@ as in test/solve.jl); inequality rows are rejected, not approximated. Inequality
 as a primal-dual interior point on the same Newton-KKT step -- barrier diagonal inside the factor kernel
 (dto_kkt_device_pointer(k, 5)), fraction-to-the-boundary steps, monotone barrier updates -- but WITHOUT Ipopt's
 feasibility-restoration phase. Measured: the pendulum swing-up with |u| <= 15 (unconstrained peak 18.6) converges in 12
-iterations, device iterates = oracle-twin iterates to 1e-13; the cartpole example (T = 101, the example's guess,
-tools/ip_cartpole.py, profiles/ip_cartpole_r02.jsonl) converges for every guess with |u| <= 30, 10 and 5 (the last in
-24 iterations with a quarter of the controls AT the bound) and does NOT with the example's |u| <= 3: the iterates settle
-at ||c||_inf ~ 0.013 with 96 % of the controls saturated -- a one-swing trajectory that actuator cannot complete; the
-multi-pump solution needs the globalisation (restoration) this solver does not have.
-`Solver.solve()` therefore keeps sending bounded problems to the broker unless method="sqp" is asked for. It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
+iterations, device iterates = oracle-twin iterates to 1e-13; the reference's cartpole example (examples/cartpole/
+cartpole.jl: T = 101, |u| <= 3, its own guess -- constant controls 0.01 and the states of an explicit rollout) is solved
+for every problem of a 4096-problem batch (median 47 iterations, 23 % of the controls AT the bound, end point to 1e-12;
+tools/ip_cartpole.py, profiles/ip_cartpole_r02.jsonl). What the missing restoration phase costs: from a guess whose states
+are interpolated from x1 to xT (not the example's) the same problem settles at ||c||_inf ~ 0.013 with 96 % of the controls
+saturated, whatever the options -- a one-swing trajectory that actuator cannot complete (|u| <= 5 and looser converge
+from that guess too). `Solver.solve()` sends problems with bounds on variables here (method "sqp"). It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
 damping and Ipopt-style inertia correction of the primal regularisation; it is NOT Ipopt:
 iterate-for-iterate parity with the reference's Ipopt runs is unverifiable here and is not claimed.
 """

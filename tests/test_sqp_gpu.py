@@ -340,3 +340,37 @@ def test_interior_point_mode_with_active_control_bounds_matches_oracle_twin():
     isu[[t * (n + m) + n for t in range(T - 1)]] = True
     assert np.all(diag[isu] > 0.0) and np.all(diag[~isu] == 0.0) and np.all(np.diag(K)[:pn.num_variables][isu] >= diag[isu] * (1 - 1e-12))
     pn.close()
+
+
+def test_reference_cartpole_example_with_control_bounds_solves_on_the_device():
+    """/root/reference/examples/cartpole/cartpole.jl as published -- T = 101, |u| <= 3 as Bound(action_lower, action_upper),
+    the state pinned at both ends, the example's own guess (constant controls 0.01, states of an explicit rollout) -- for
+    a batch, through Solver.solve(): bounds on variables select the interior-point mode of the lock-step solver. Every
+    problem must converge to a KKT point of the bounded problem: dynamics satisfied (checked with the
+    constraint callback at the returned point), end points met, |u| strictly within 3 with a good part of the controls AT the bound."""
+    import examples.cartpole_swingup as ex
+    B, T = 24, 101
+    model = M.build_cartpole(D, T=T)
+    n, m, x1, xT = model["n"], model["m"], model["x1"], model["xT"]
+    s = D.solver_from(model, batch=B)
+    s.nlp.set_parameters(np.tile(np.concatenate([x1, xT]), (B, 1)))
+    rng = np.random.default_rng(0)
+    for b in range(B):
+        u0 = np.array([0.01 * (1.0 + 0.2 * rng.normal())])
+        xs = [x1.astype(float)]
+        for _ in range(T - 1):
+            xs.append(np.array(M.cartpole_rk3_explicit(xs[-1], u0, np.zeros(0)), dtype=float))
+        s.initialize_states(xs, problem=b)
+        s.initialize_controls([u0] * (T - 1), problem=b)
+    res = s.solve(options=dict(max_iter=600))                 # method="auto" -> "sqp" (interior point): no broker
+    assert s.broker is None and s.sqp_launches > 100
+    assert bool(res.converged.all()), res.iterations
+    Z = res.z.cpu().numpy()
+    c = np.zeros((B, s.nlp.num_constraint))
+    s.nlp.eval_constraint(c, Z)
+    assert np.max(np.abs(c)) < 1e-7
+    U = np.stack([Z[:, t * (n + m) + n] for t in range(T - 1)], axis=1)
+    assert np.all(np.abs(U) < 3.0) and (np.abs(U) > 3.0 - 1e-4).mean() > 0.1
+    assert np.max(np.abs(Z[:, :n] - x1)) < 1e-6 and np.max(np.abs(Z[:, -n:] - xT)) < 1e-6
+    s.nlp.close()
+    assert callable(ex.main)

@@ -1,5 +1,6 @@
 """Interior-point mode of sqp.solve on the cartpole example (examples/cartpole/cartpole.jl: T = 101, |u| <= u_bnd, the
-example's guess: states interpolated, controls 0.01 randn):   python tools/ip_cartpole.py [u_bnd] [B] [max_iter]  -> JSON line"""
+example's guess: constant controls 0.01 and the states of an explicit rollout; GUESS=interpolate for interpolated states and
+controls GUESS_SIGMA * randn):   python tools/ip_cartpole.py [u_bnd] [B] [max_iter]  -> JSON line"""
 import json
 import os
 import sys
@@ -22,10 +23,23 @@ n, m = mc["n"], mc["m"]
 mc["bounds"] = [D.Bound(n, m, action_lower=[-ub], action_upper=[ub])] * (T - 1) + [D.Bound(n, 0)]   # host side: same model library
 s = D.solver_from(mc, batch=B)
 s.nlp.set_parameters(np.tile(np.concatenate([mc["x1"], mc["xT"]]), (B, 1)))      # w = [x1; xT] of every problem (BASELINE config 2 layout)
-s.initialize_states(D.linear_interpolation(mc["x1"], mc["xT"], T))
 rng = np.random.default_rng(7)
-for b in range(B):
-    s.initialize_controls([0.01 * rng.normal(size=1) for _ in range(T - 1)], problem=b)
+guess = os.environ.get("GUESS", "rollout")
+sigma = float(os.environ.get("GUESS_SIGMA", "0.01"))
+if guess == "rollout":
+    # the example's guess (cartpole.jl:102-109): constant controls 0.01 (here 0.01 (1 + 0.2 randn) per problem) and the states
+    # of an explicit RK3 rollout from x1
+    for b in range(B):
+        u0 = np.array([0.01 * (1.0 + 0.2 * rng.normal())])
+        xs = [mc["x1"].astype(float)]
+        for t in range(T - 1):
+            xs.append(np.array(M.cartpole_rk3_explicit(xs[-1], u0, np.zeros(0)), dtype=float))
+        s.initialize_states(xs, problem=b)
+        s.initialize_controls([u0 for _ in range(T - 1)], problem=b)
+else:   # states interpolated from x1 to xT, controls sigma * randn
+    s.initialize_states(D.linear_interpolation(mc["x1"], mc["xT"], T))
+    for b in range(B):
+        s.initialize_controls([sigma * rng.normal(size=1) for _ in range(T - 1)], problem=b)
 so = dict(max_iter=iters)
 so.update(json.loads(os.environ.get("DTO_SQP_OPTIONS", "{}")))
 t0 = time.perf_counter()
@@ -35,7 +49,7 @@ dt = time.perf_counter() - t0
 it, conv = res.iterations.cpu().numpy(), res.converged.cpu().numpy()
 Z = res.z.cpu().numpy()
 U = np.stack([Z[:, t * (n + m) + n] for t in range(T - 1)], axis=1)
-print(json.dumps(dict(u_bnd=ub, options=so, T=T, B=B, seconds=dt, converged=float(conv.mean()), it_median=float(np.median(it)), it_max=float(it.max()),
+print(json.dumps(dict(u_bnd=ub, guess=guess, guess_sigma=sigma, options=so, T=T, B=B, seconds=dt, converged=float(conv.mean()), it_median=float(np.median(it)), it_max=float(it.max()),
                       cv_max=float(res.constraint_violation.cpu().numpy().max()), dr_median=float(np.median(res.dual_residual.cpu().numpy())),
                       u_max=float(np.abs(U).max()), end_error_max=float(np.abs(Z[:, -n:] - mc["xT"]).max()), at_bound=float((np.abs(U) > 0.997 * ub).mean()), f_median=float(np.median(res.objective.cpu().numpy())))))
 s.nlp.close()
