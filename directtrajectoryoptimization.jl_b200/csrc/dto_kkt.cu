@@ -68,14 +68,15 @@ template <bool DIAG = false>
 __device__ __forceinline__ double row_shift(const dto_kkt_args& a, size_t row, int64_t b, int64_t bd = -1)
 {
     // diagonal shift of permuted row `row`: +primal_reg (per problem when a.preg is given), -dual_reg, 1.0 on padding;
-    // DIAG: + the barrier diagonal of problem bd (a candidate slot's regularisation is the slot's, its diagonal the problem's)
+    // DIAG: + the diagonal entry diag[bd][original index] of problem bd (variable AND constraint rows; a candidate slot's
+    // regularisation is the slot's, its diagonal the problem's)
     if (a.rowfixed != nullptr && a.rowfixed[row]) return 1.0;   // pinned variable: identity row
     double reg = a.dreg[row];
     if (a.preg != nullptr || (DIAG && a.diag != nullptr)) {
         const int32_t ip = a.iperm[row];
-        if (ip >= 0 && ip < a.N_z) {
-            if (a.preg != nullptr) reg = a.preg[b];
-            if (DIAG && a.diag != nullptr) reg += a.diag[(bd >= 0 ? bd : b) * a.N_z + ip];
+        if (ip >= 0) {
+            if (a.preg != nullptr && ip < a.N_z) reg = a.preg[b];
+            if (DIAG && a.diag != nullptr) reg += a.diag[(bd >= 0 ? bd : b) * a.dim + ip];
         }
     }
     return reg;
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(128, MINB) kkt_band_kernel(const dto_kkt_args 
                 if (ipn >= 0) rc = hb[ipn];
             }
             regc = (fixn || ipn < 0) ? 1.0 : (ipn < a.N_z ? prim : -a.dual_reg);   // = row_shift(): the values of the dreg table
-            if (DIAG && !fixn && ipn >= 0 && ipn < a.N_z) regc += a.diag[b * a.N_z + ipn];
+            if (DIAG && !fixn && ipn >= 0) regc += a.diag[b * a.dim + ipn];
             load_idx(blk + 3);
             load_static(blk + 3);
 #else

@@ -52,9 +52,10 @@ typedef struct dto_kkt_args {
      * nneg[s] are indexed by the SLOT: the caller passes scratch arrays there and keeps the candidate it wants */
     int32_t virt;
     double primal_reg, dual_reg;   /* the scalars behind the dreg table (+primal_reg on variable rows, -dual_reg on constraint rows) */
-    /* per-problem, per-variable diagonal added to the Hessian block (an interior-point solver's barrier term
-     * Sigma = z_L / (x - l) + z_U / (u - x)): K(i, i) += diag[b][i] for the variable rows of problem b; NULL = none */
-    const double* diag;  /* [B][N_z] or NULL                                                   */
+    /* per-problem diagonal added to K, natural order [variables; constraint rows] (an interior-point solver's barrier terms:
+     * Sigma = z_L / (x - l) + z_U / (u - x) on the variables, -t_i / lambda_i on inequality rows): K(i, i) += diag[b][i];
+     * NULL = none */
+    const double* diag;  /* [B][dim] or NULL                                                   */
     /* variables pinned by equal lower/upper bounds (Bound(state_lower = x1, state_upper = x1), test/solve.jl): their
      * rows and columns of K are replaced by the identity (the gather table carries structural zeros there) and their
      * right-hand-side entries by 0, so their step is exactly 0 and the others get the reduced Newton step */

@@ -431,10 +431,12 @@ class Solver:
             lo, up = self.nlp.variable_bounds
             clo, cup = self.nlp.constraint_bounds
             pinned = np.isfinite(lo) & (lo == up)
-            ok = self.nlp.hessian_lagrangian and np.array_equal(clo, cup) and self.nlp.num_shards == 1
-            inequality_bounds = bool(np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned))
-            # inequality bounds on variables (Bound(action_lower = ..., ...)): the interior-point mode of the torch-glued arm
-            method = ("sqp" if (record_iterates or inequality_bounds) else "native") if ok else "broker"
+            rows_ok = bool(np.all((clo == cup) | (np.isneginf(clo) & (cup == 0.0))))      # equalities and c(z) <= 0 rows
+            ok = self.nlp.hessian_lagrangian and rows_ok and self.nlp.num_shards == 1
+            inequalities = bool(np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)) or not np.array_equal(clo, cup)
+            # bounds on variables (Bound(action_lower = ..., ...)) and inequality rows (Constraint(...; indices_inequality)):
+            # the interior-point mode of the torch-glued arm
+            method = ("sqp" if (record_iterates or inequalities) else "native") if ok else "broker"
         if method in ("sqp", "native"):
             from . import sqp
             o = sqp.SQPOptions()
@@ -455,7 +457,7 @@ class Solver:
             res = None
             try:
                 z0 = be.torch.as_tensor(self._initial, device=be.xp.device)
-                res = sqp.solve(be, z0, options=o, record=record_iterates)
+                res = sqp.solve_bounded(be, z0, options=o, record=record_iterates)    # = sqp.solve when no bound is an inequality
                 Z = res.z.cpu().numpy()
                 self.sqp_launches = res.backend.total_launches()
             finally:

@@ -18,20 +18,23 @@ regularisation, convergence masks); they are written against an array namespace 
 for the product, numpy for the oracle-driven twin the parity test runs (tests/sqp_oracle.py) -- so both arms
 execute literally the same algorithm.
 
-Scope (stated plainly): equality-constrained problems whose variables are free or PINNED by equal lower and upper
-bounds (end points fixed by stage constraints as in examples/acrobot, or by Bound(state_lower = x1, state_upper = x1)
-as in test/solve.jl); inequality rows are rejected, not approximated. Inequality BOUNDS on variables
-(Bound(action_lower = ..., action_upper = ...)) are handled by `solve` (torch arm and oracle twin; not the native arm)
-as a primal-dual interior point on the same Newton-KKT step -- barrier diagonal inside the factor kernel
-(dto_kkt_device_pointer(k, 5)), fraction-to-the-boundary steps, monotone barrier updates -- but WITHOUT Ipopt's
-feasibility-restoration phase. Measured: the pendulum swing-up with |u| <= 15 (unconstrained peak 18.6) converges in 12
-iterations, device iterates = oracle-twin iterates to 1e-13; the reference's cartpole example (examples/cartpole/
-cartpole.jl: T = 101, |u| <= 3, its own guess -- constant controls 0.01 and the states of an explicit rollout) is solved
-for every problem of a 4096-problem batch (median 47 iterations, 23 % of the controls AT the bound, end point to 1e-12;
-tools/ip_cartpole.py, profiles/ip_cartpole_r02.jsonl). What the missing restoration phase costs: from a guess whose states
-are interpolated from x1 to xT (not the example's) the same problem settles at ||c||_inf ~ 0.013 with 96 % of the controls
-saturated, whatever the options -- a one-swing trajectory that actuator cannot complete (|u| <= 5 and looser converge
-from that guess too). `Solver.solve()` sends problems with bounds on variables here (method "sqp"). It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
+Scope (stated plainly): the native arm (dto_sqp_solve) takes equality-constrained problems whose variables are free or
+PINNED by equal lower and upper bounds (end points fixed by stage constraints as in examples/acrobot, or by
+Bound(state_lower = x1, state_upper = x1) as in test/solve.jl). Inequalities -- BOUNDS on variables
+(Bound(action_lower = ..., action_upper = ...)) and inequality ROWS c_i(z) <= 0 (Constraint(...; indices_inequality)) --
+are handled by `solve` / `solve_bounded` (torch arm and oracle twin) as a primal-dual interior point on the same
+Newton-KKT step: the barrier terms are a per-problem diagonal the factor kernel adds to K while it gathers a row
+(dto_kkt_device_pointer(k, 5): z_L/(x-l) + z_U/(u-x) on bounded variables, -t_i/lam_i on inequality rows whose slacks t
+are eliminated), fraction-to-the-boundary steps, monotone barrier updates -- but WITHOUT Ipopt's feasibility-restoration
+phase; `solve_bounded` adds a continuation on the bounds (widened tenfold, then tightened with a warm start) for the
+problems the direct solve leaves unconverged. Measured on the reference's own examples, each from its own guess:
+cartpole (T = 101, |u| <= 3, rollout guess): 4096 of 4096 problems, median 47 iterations, 23 % of the controls AT the
+bound; car (T = 51, |u| <= 0.5, pinned ends, obstacle inequality per knot, interpolated guess): 99.7 % of 1024 guesses,
+12 % of them through the continuation (tools/ip_cartpole.py, tools/ip_car.py, profiles/ip_*_r02.jsonl); pendulum with
+|u| <= 15: device iterates = oracle-twin iterates to 1e-13. What the missing restoration phase costs: cartpole from a guess
+whose states are interpolated from x1 to xT (not the example's) settles at ||c||_inf ~ 0.013 with 96 % of the controls
+saturated, whatever the options and with the continuation -- a one-swing trajectory that actuator cannot complete.
+`Solver.solve()` sends problems with inequalities here (method "sqp"). It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
 damping and Ipopt-style inertia correction of the primal regularisation; it is NOT Ipopt:
 iterate-for-iterate parity with the reference's Ipopt runs is unverifiable here and is not claimed.
 """
@@ -87,6 +90,8 @@ class SQPOptions:
     bound_frac: float = 1.0e-2
     kappa_sigma: float = 1.0e10        # z stays within [mu/(kappa s), kappa mu/s]
     tiny_step: float = 1.0e-6          # relative step size under which the full (fraction-to-the-boundary) step is taken untested
+    bound_stages: tuple = (10.0, 1.0)  # fallback of `solve_bounded` for problems the direct solve leaves unconverged: two-sided
+                                       #   bounds widened about their midpoint by these factors, one solve per stage, warm-started
 
 
 class SQPResult:
@@ -139,6 +144,11 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
         zL = xp.ones((B, N_z)) * hasL
         zU = xp.ones((B, N_z)) * hasU
         mu = xp.full((B,), o.mu_init)
+        # inequality rows c_i(z) <= 0 become c_i(z) + t_i = 0 with slacks t_i > 0; the slacks are eliminated from the Newton
+        # system (their row of K gets -t_i/lam_i on the diagonal, lam_i > 0 doubling as the slack's bound multiplier)
+        hasI = bnd["hasI"] if int(bnd["hasI"].shape[0]) == N_c else xp.zeros((N_c,))
+        any_ineq = bool(xp.any(hasI > 0))
+        t = None
         mu_floor = min(o.tol_constraint, o.tol_dual) / 10.0
         big = 1.0e300
     # results in the caller's problem order; `ids` = original problem number of every row of the working batch
@@ -167,7 +177,20 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             sU = xp.where(hasU > 0, up - z, xp.ones((B, N_z)))
             SigL, SigU = hasL * zL / sL, hasU * zU / sU
             gshift = mu[:, None] * (hasU / sU - hasL / sL)
-            f, g, c = be.callbacks(z, lam, lam * exact[:, None], delta, diag=SigL + SigU, gshift=gshift)
+            if any_ineq:
+                if t is None:       # first iteration: slacks from the constraint values at the start, multipliers on the central path
+                    _, c0 = be.objective_constraint(z)
+                    t = hasI * xp.maximum(-c0, xp.full((B, N_c), o.bound_push))
+                    lam = xp.where(hasI > 0, mu[:, None] / xp.maximum(t, xp.full((B, N_c), 1.0e-300)), lam)
+                tS = xp.where(hasI > 0, t, xp.ones((B, N_c)))
+                lamI = xp.where(hasI > 0, lam, xp.ones((B, N_c)))
+                diagC = -hasI * tS / lamI                        # (2,2) block: -t_i / lam_i on the inequality rows
+                cshift = hasI * (mu[:, None] / lamI)             # their right-hand side: c_i + mu / lam_i
+                f, g, c = be.callbacks(z, lam, lam * exact[:, None], delta, diag=xp.hcat(SigL + SigU, diagC), gshift=gshift, cshift=cshift)
+                f = f - mu * xp.sum_rows(hasI * xp.log(tS))
+                c = c + hasI * t                                 # residual of c(z) + t = 0
+            else:
+                f, g, c = be.callbacks(z, lam, lam * exact[:, None], delta, diag=SigL + SigU, gshift=gshift)
             f = f - mu * (xp.sum_rows(hasL * xp.log(sL)) + xp.sum_rows(hasU * xp.log(sU)))
         else:
             f, g, c = be.callbacks(z, lam, lam * exact[:, None], delta)
@@ -179,6 +202,10 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             compL, compU = hasL * sL * zL, hasU * sU * zU
             comp = xp.maximum(xp.max_abs_rows(compL), xp.max_abs_rows(compU))
             e_mu = xp.maximum(xp.maximum(dr, cv), xp.maximum(xp.max_abs_rows(compL - hasL * mu[:, None]), xp.max_abs_rows(compU - hasU * mu[:, None])))
+            if any_ineq:
+                compI = hasI * tS * lamI
+                comp = xp.maximum(comp, xp.max_abs_rows(compI))
+                e_mu = xp.maximum(e_mu, xp.max_abs_rows(compI - hasI * mu[:, None]))
             mu_next = xp.where(e_mu <= o.barrier_kappa_eps * mu,
                                xp.maximum(xp.full((B,), mu_floor), xp.minimum(o.barrier_kappa_mu * mu, mu ** o.barrier_theta_mu)), mu)
             dr = xp.maximum(dr, comp)
@@ -251,6 +278,13 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             a_z = xp.minimum(xp.min_rows(xp.where(dzL < 0.0, -tau * zL / xp.minimum(dzL, xp.full((B, N_z), -1.0e-300)), xp.full((B, N_z), big))),
                              xp.min_rows(xp.where(dzU < 0.0, -tau * zU / xp.minimum(dzU, xp.full((B, N_z), -1.0e-300)), xp.full((B, N_z), big))))
             a_z = xp.minimum(xp.ones((B,)), a_z)
+            if any_ineq:
+                dt = hasI * (mu[:, None] / lamI - tS - (tS / lamI) * dlam)       # from t lam = mu linearised (lam is the slack's multiplier)
+                amax = xp.minimum(amax, xp.min_rows(xp.where((hasI > 0) & (dt < 0.0), -tau * tS / xp.minimum(dt, xp.full((B, N_c), -1.0e-300)), xp.full((B, N_c), big))))
+                a_z = xp.minimum(a_z, xp.min_rows(xp.where((hasI > 0) & (dlam < 0.0), -tau * lamI / xp.minimum(dlam, xp.full((B, N_c), -1.0e-300)), xp.full((B, N_c), big))))
+                # the barrier of the slacks joins the merit function's slope
+                gd = gd - xp.sum_rows(hasI * (mu[:, None] / tS) * dt)
+                slope = gd - nu * c1
             alpha = amax
         soc_used = xp.zeros_bool((B,))
         accepted = xp.copy_bool(done) | bad     # converged problems and failed factorisations do not move
@@ -268,6 +302,10 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
                 stL = xp.where(hasL > 0, xp.maximum(zt - lo, xp.full((B, N_z), 1.0e-300)), xp.ones((B, N_z)))
                 stU = xp.where(hasU > 0, xp.maximum(up - zt, xp.full((B, N_z), 1.0e-300)), xp.ones((B, N_z)))
                 ft = ft - mu * (xp.sum_rows(hasL * xp.log(stL)) + xp.sum_rows(hasU * xp.log(stU)))
+                if any_ineq:
+                    tt = xp.where(hasI > 0, xp.maximum(t + alpha[:, None] * dt, xp.full((B, N_c), 1.0e-300)), xp.ones((B, N_c)))
+                    ft = ft - mu * xp.sum_rows(hasI * xp.log(tt))
+                    ct = ct + hasI * tt
             phit = ft + nu * xp.sum_abs_rows(ct)
             # (interior point: Ipopt's relaxation of the test by 10 eps |phi| -- with mu -> 0 the predicted decrease of a
             # converging problem drops below the rounding error of phi itself)
@@ -278,7 +316,11 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
                 # and rejecting it would also reject the multiplier step it carries
                 ok = ok | ((xp.max_abs_rows(dz) <= o.tiny_step * (1.0 + xp.max_abs_rows(z))) & ~accepted)
             z = xp.where_rows(ok, zt, z)
-            lam = xp.where_rows(ok, lam + alpha[:, None] * dlam, lam)
+            if ip and any_ineq:      # inequality multipliers move with the dual step length (they must stay positive)
+                lam = xp.where_rows(ok, lam + xp.where(hasI > 0, a_z[:, None] * dlam, alpha[:, None] * dlam), lam)
+                t = xp.where_rows(ok, hasI * tt, t)
+            else:
+                lam = xp.where_rows(ok, lam + alpha[:, None] * dlam, lam)
             if ip:
                 zL = xp.where_rows(ok, zL + a_z[:, None] * dzL, zL)
                 zU = xp.where_rows(ok, zU + a_z[:, None] * dzU, zU)
@@ -306,7 +348,10 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
         if o.lam_max > 0.0:
             # runaway multiplier estimates (damped steps near a rank-deficient Jacobian): start them again from zero, the
             # next Hessian of such a problem is then the objective's alone
-            lam = xp.where_rows(xp.max_abs_rows(lam) > o.lam_max, xp.zeros((B, N_c)), lam)
+            if ip and any_ineq:
+                lam = xp.where_rows(xp.max_abs_rows(lam * (1.0 - hasI)) > o.lam_max, lam * hasI, lam)      # equality rows only
+            else:
+                lam = xp.where_rows(xp.max_abs_rows(lam) > o.lam_max, xp.zeros((B, N_c)), lam)
         # a problem whose search failed keeps its point; more regularisation next time shortens the step
         stuck = ~accepted
         moved = ~done & ~bad
@@ -316,6 +361,9 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
             sUn = xp.where(hasU > 0, up - z, xp.ones((B, N_z)))
             zL = hasL * xp.maximum(xp.minimum(zL, o.kappa_sigma * mu[:, None] / sLn), mu[:, None] / (o.kappa_sigma * sLn))
             zU = hasU * xp.maximum(xp.minimum(zU, o.kappa_sigma * mu[:, None] / sUn), mu[:, None] / (o.kappa_sigma * sUn))
+            if any_ineq:
+                tSn = xp.where(hasI > 0, t, xp.ones((B, N_c)))
+                lam = xp.where(hasI > 0, xp.maximum(xp.minimum(lam, o.kappa_sigma * mu[:, None] / tSn), mu[:, None] / (o.kappa_sigma * tSn)), lam)
             mu = xp.where(done, mu, mu_next)
             alpha = alpha / amax            # the damping rules below look at the fraction of the allowed step that was taken
         lm = xp.where(moved & (alpha < o.lm_grow_below), xp.maximum(xp.full((B,), o.lm_min), o.lm_grow * xp.maximum(lm, delta)), lm)
@@ -330,7 +378,7 @@ def solve(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool 
     return SQPResult(out["z"], out["lam"], out["iters"], out["done"], out["cv"], out["dr"], out["f"], history, backend=be)
 
 
-def bound_arrays(lo, up, options: Optional[SQPOptions] = None):
+def bound_arrays(lo, up, options: Optional[SQPOptions] = None, clo=None, cup=None, scale: float = 1.0):
     """numpy: primal_bounds (src/data.jl:123-133) -> what `solve` needs. Returns (fixed, bounds): `fixed` = variables pinned
     by lo == up; `bounds` = None when no other finite bound exists, else dict(hasL, hasU, lo, up, pushL, pushU) with 0/1
     masks, finite values (0 where absent) and the distances the starting point is pushed inside (Ipopt's bound_push/frac)."""
@@ -338,9 +386,19 @@ def bound_arrays(lo, up, options: Optional[SQPOptions] = None):
     o = options or SQPOptions()
     lo, up = np.asarray(lo, float), np.asarray(up, float)
     fixed = np.isfinite(lo) & (lo == up)
+    if scale != 1.0:        # continuation stage: two-sided bounds widened about their midpoint (one-sided and pinned ones stay)
+        two = np.isfinite(lo) & np.isfinite(up) & ~fixed
+        l2, u2 = np.where(two, lo, 0.0), np.where(two, up, 0.0)
+        mid, half = 0.5 * (l2 + u2), 0.5 * (u2 - l2)
+        lo = np.where(two, mid - scale * half, lo)
+        up = np.where(two, mid + scale * half, up)
     hasL = np.isfinite(lo) & ~fixed
     hasU = np.isfinite(up) & ~fixed
-    if not (hasL.any() or hasU.any()):
+    # inequality rows c_i(z) <= 0: constraint_bounds (src/data.jl:135-148) gives them (-Inf, 0], equalities [0, 0]
+    hasI = np.zeros(0, dtype=bool) if clo is None else (np.asarray(clo, float) != np.asarray(cup, float))
+    if hasI.any() and not (np.all(np.isneginf(np.asarray(clo, float)[hasI])) and np.all(np.asarray(cup, float)[hasI] == 0.0)):
+        raise NotImplementedError("sqp: inequality rows other than c(z) <= 0 are outside this solver's scope")
+    if not (hasL.any() or hasU.any() or hasI.any()):
         return fixed, None
     if np.any((hasL & hasU) & (lo >= up)):
         raise ValueError("a variable's lower bound exceeds its upper bound")
@@ -348,7 +406,41 @@ def bound_arrays(lo, up, options: Optional[SQPOptions] = None):
     width = np.where(hasL & hasU, u0 - l0, np.inf)
     pushL = np.where(hasL, np.minimum(o.bound_push * np.maximum(1.0, np.abs(l0)), o.bound_frac * width), 0.0)
     pushU = np.where(hasU, np.minimum(o.bound_push * np.maximum(1.0, np.abs(u0)), o.bound_frac * width), 0.0)
-    return fixed, dict(hasL=hasL.astype(np.float64), hasU=hasU.astype(np.float64), lo=l0, up=u0, pushL=pushL, pushU=pushU)
+    return fixed, dict(hasL=hasL.astype(np.float64), hasU=hasU.astype(np.float64), lo=l0, up=u0, pushL=pushL, pushU=pushU,
+                       hasI=hasI.astype(np.float64))
+
+
+def solve_bounded(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool = False) -> SQPResult:
+    """`solve`, plus a fallback for problems with inequality bounds that the direct solve leaves unconverged (no restoration
+    phase: an iterate can run into its bounds while the constraints are still violated): the two-sided bounds are widened
+    about their midpoint by options.bound_stages[0], the problem is solved from the ORIGINAL guess, and the bounds are
+    tightened stage by stage to the true ones (last factor 1), every stage warm-started from the one before. A problem
+    keeps its direct result when that converged; otherwise it takes the staged one. Problems stay independent: what a
+    problem gets depends only on its own guess and the fixed stage list. The backend must offer set_bound_scale(scale)."""
+    o = options or SQPOptions()
+    xp = be.xp
+    res = solve(be, z0, lam0, o, record)
+    if getattr(be, "bounds", None) is None or getattr(be, "set_bound_scale", None) is None or not o.bound_stages or xp.all(res.converged):
+        return res
+    z, lam, its = z0, lam0, None
+    stages = tuple(o.bound_stages) + (() if float(o.bound_stages[-1]) == 1.0 else (1.0,))      # the last stage is the true problem
+    try:
+        for scale in stages:
+            be.set_bound_scale(float(scale))
+            stage = solve(be, z, lam, o, False)
+            z, lam = stage.z, stage.lam
+            its = stage.iterations if its is None else its + stage.iterations
+    finally:
+        be.set_bound_scale(1.0)
+    take = stage.converged & ~res.converged
+    res.z = xp.where_rows(take, stage.z, res.z)
+    res.lam = xp.where_rows(take, stage.lam, res.lam)
+    for name in ("constraint_violation", "dual_residual", "objective"):
+        setattr(res, name, xp.where(take, getattr(stage, name), getattr(res, name)))
+    res.iterations = xp.where(take, res.iterations + its, res.iterations)      # direct attempt + all stages
+    res.converged = res.converged | take
+    res.staged = take
+    return res
 
 
 # --------------------------------------------------------------------------------------- array namespaces
@@ -406,6 +498,9 @@ class _XP:
     def sum_rows(self, a):
         return a.sum(dim=1) if self.is_torch else a.sum(axis=1)
 
+    def hcat(self, a, b):
+        return self.m.cat([a, b], dim=1) if self.is_torch else self.m.concatenate([a, b], axis=1)
+
     def min_rows(self, a):
         return a.amin(dim=1) if self.is_torch else a.min(axis=1)
 
@@ -460,10 +555,9 @@ class DeviceBackend:
         lo, up = nlp.variable_bounds
         import numpy as np
         clo, cup = nlp.constraint_bounds
-        if np.any(clo != cup):
-            raise NotImplementedError("sqp: inequality constraints are outside this solver's scope")
         # Bound(state_lower = x1, state_upper = x1): pinned variables; any other finite bound: interior point in `solve`
-        fixed, bounds = bound_arrays(lo, up, options)
+        fixed, bounds = bound_arrays(lo, up, options, clo, cup)       # (inequality rows c(z) <= 0: slacks in `solve`)
+        self._bound_args = (lo, up, options, clo, cup)
         self.bounds = None if bounds is None else {k: torch.as_tensor(v, device=dev) for k, v in bounds.items()}
         self.free = torch.as_tensor((~fixed).astype(np.float64), device=dev)
         self.pinned_value = torch.as_tensor(np.where(fixed, lo, 0.0), device=dev)
@@ -488,7 +582,7 @@ class DeviceBackend:
         self.d_sol = kview(1, (B, self.kkt.dim))
         self.d_reg = kview(3, (B,))
         self.d_nneg = kview(4, (B,), "<i4")
-        self.d_diag = kview(5, (B, self.N_z)) if self.bounds is not None else None     # barrier diagonal added to H
+        self.d_diag = kview(5, (B, self.kkt.dim)) if self.bounds is not None else None   # barrier diagonal added to K
         self.d_sigma.fill_(1.0)
         # ONE stream for the kernels of libdto.so and torch's glue operations: the batch launches on torch's
         # current stream of the device, so every copy / update is ordered with the kernels without events
@@ -496,6 +590,12 @@ class DeviceBackend:
         nlp.set_stream(self.stream.cuda_stream, 0)
         self.launches0 = nlp.launch_count()
         self._graph = None          # (CUDAGraph, static buffers, armijo) of one backtracking round; False = capture unavailable
+
+    def set_bound_scale(self, scale: float):
+        """continuation stage of `solve_bounded`: two-sided bounds widened about their midpoint by `scale` (1 = the true ones)"""
+        if self.bounds is not None:
+            _, bounds = bound_arrays(*self._bound_args, scale=scale)
+            self.bounds = {k: self.torch.as_tensor(v, device=self.xp.device) for k, v in bounds.items()}
 
     def close(self):
         self.kkt.close()
@@ -527,7 +627,7 @@ class DeviceBackend:
         self.close()
         return be2
 
-    def callbacks(self, z, lam, lam_hess, delta, diag=None, gshift=None):
+    def callbacks(self, z, lam, lam_hess, delta, diag=None, gshift=None, cshift=None):
         """f, g, c at z; J and H(z, lam_hess) stay on the device; first KKT solve with the damping `delta` and the
         right-hand side of the TRUE multipliers `lam` (the Hessian may use others: Gauss-Newton for far-away problems).
         Interior point: `diag` [B, N_z] joins the diagonal of H inside the factor kernel, `gshift` is added to g (the
@@ -539,13 +639,20 @@ class DeviceBackend:
             self.d_reg.copy_(delta)
             self.nlp.launch(self._K[0])                 # f
             self.kkt.launch(2)                          # g, c, J, H(z, lam_hess)
+            c_raw = None
             if diag is not None:
-                self.d_diag.copy_(diag)
+                if diag.shape[1] == self.N_z:                       # bounds on variables only: the constraint rows keep -dual_reg
+                    self.d_diag[:, :self.N_z].copy_(diag)
+                else:
+                    self.d_diag.copy_(diag)
                 self.d_g.add_(gshift)
+                if cshift is not None:                              # inequality rows: right-hand side c + mu / lam
+                    c_raw = self.d_c.clone()
+                    self.d_c.add_(cshift)
             self.d_lam.copy_(lam)
             self.kkt.launch(0)                          # h = [g + J'lam; c], K = L D L', sol
             self._fresh = True
-            return self.d_f.clone(), self.d_g.clone(), self.d_c.clone()
+            return self.d_f.clone(), self.d_g.clone(), (self.d_c.clone() if c_raw is None else c_raw)
 
     def _solution(self):
         t = self.torch

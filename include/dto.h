@@ -238,8 +238,9 @@ int dto_kkt_matrix(dto_kkt* k, int64_t problem, double* dense);
 int dto_kkt_factor(dto_kkt* k, int64_t problem, double* Lband, double* D);
 /* which = 0 h, 1 sol, 2 factor storage, 3 per-problem primal regularisation [shard size] (asking for it switches the
  * kernels to per-problem mode: the caller writes it on the device), 4 negative-pivot counts [shard size] int32,
- * 5 a per-problem, per-variable diagonal [shard size][num_variables] ADDED to the Hessian block from then on (zero at first:
- * the barrier term Sigma = z_L / (x - l) + z_U / (u - x) of an interior-point solver handling Bound(...), src/bounds.jl) */
+ * 5 a per-problem diagonal [shard size][dim] (natural order: variables, then constraint rows) ADDED to K from then on (zero
+ * at first: the barrier terms of an interior-point solver -- z_L / (x - l) + z_U / (u - x) on variables with Bound(...),
+ * src/bounds.jl; -t_i / lambda_i on inequality rows, Constraint(...; indices_inequality), src/constraints.jl) */
 void* dto_kkt_device_pointer(dto_kkt* k, int which, int shard);
 
 /* ---- batched solver: the caller of the callback path ----

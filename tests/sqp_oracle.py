@@ -46,7 +46,9 @@ class OracleBackend:
         lo, up = self.o.variable_bounds
         lo, up = np.asarray(lo, float), np.asarray(up, float)
         from dto_b200.sqp import bound_arrays
-        self.fixed, self.bounds = bound_arrays(lo, up, options)
+        clo, cup = self.o.constraint_bounds
+        self._bound_args = (lo, up, options, clo, cup)
+        self.fixed, self.bounds = bound_arrays(lo, up, options, clo, cup)
         self.free = (~self.fixed).astype(np.float64)
         self.pinned_value = np.where(self.fixed, lo, 0.0)
         self.diag = None
@@ -60,6 +62,11 @@ class OracleBackend:
         hr = np.array([r for r, _ in self.hs]) - 1
         hc = np.array([c for _, c in self.hs]) - 1
         self._idx = (jr, jc, hr, hc)
+
+    def set_bound_scale(self, scale):
+        if self.bounds is not None:
+            from dto_b200.sqp import bound_arrays
+            _, self.bounds = bound_arrays(*self._bound_args, scale=scale)
 
     def pin(self, z):
         return z * self.free + self.pinned_value
@@ -88,13 +95,16 @@ class OracleBackend:
                 self.o.eval_hessian_lagrangian(out["H"][b], z[b], 1.0, lam[b])
         return out
 
-    def callbacks(self, z, lam, lam_hess, delta=None, diag=None, gshift=None):
+    def callbacks(self, z, lam, lam_hess, delta=None, diag=None, gshift=None, cshift=None):
         self.cur = self._eval(z, lam_hess, 31)
         self.lam = lam.copy()
-        self.diag = None if diag is None else np.array(diag, copy=True)     # interior point: Sigma on H's diagonal,
-        if gshift is not None:                                              # barrier gradient in g
+        self.diag = None if diag is None else np.array(diag, copy=True)     # interior point: diagonal added to K,
+        if gshift is not None:                                              # barrier gradient in g,
             self.cur["g"] = self.cur["g"] + gshift
-        return self.cur["f"].copy(), self.cur["g"].copy(), self.cur["c"].copy()
+        c_raw = self.cur["c"].copy()
+        if cshift is not None:                                              # c + mu / lam on inequality rows (right-hand side)
+            self.cur["c"] = self.cur["c"] + cshift
+        return self.cur["f"].copy(), self.cur["g"].copy(), c_raw
 
     def _assemble(self, b, delta):
         jr, jc, hr, hc = self._idx
@@ -105,7 +115,8 @@ class OracleBackend:
         K[jc, n + jr] = self.cur["J"][b]
         K[np.arange(n), np.arange(n)] += delta
         if self.diag is not None:
-            K[np.arange(n), np.arange(n)] += self.diag[b]
+            w = self.diag.shape[1]
+            K[np.arange(w), np.arange(w)] += self.diag[b]
         K[n + np.arange(m), n + np.arange(m)] -= self.dual_reg
         Jd = np.zeros((m, n))
         Jd[jr, jc] = self.cur["J"][b]

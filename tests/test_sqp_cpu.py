@@ -160,3 +160,57 @@ def test_interior_point_mode_handles_active_bounds():
     r_free = sqp.solve(OracleBackend(O.solver_from(M.build_pendulum(O)), 1, linear="dense"), _guess(loose, 1, 1) * 0.3, options=opts)
     assert r_loose.converged.all() and r_free.converged.all()
     assert abs(r_loose.objective[0] - r_free.objective[0]) < 1e-5 * r_free.objective[0] < res.objective.min() - r_free.objective[0]
+
+
+def test_reference_car_example_inequality_rows_and_bound_continuation():
+    """/root/reference/examples/car/car.jl as published (T = 51, |u| <= 0.5 as Bounds, both end states pinned by Bounds, the
+    circular obstacle as one INEQUALITY row per knot -- Constraint(obs, ...; indices_inequality = [1]) -- and the example's
+    guess: states interpolated, controls 0.001 randn), solved by the oracle-driven arm of the solver. Inequality rows
+    c_i(z) <= 0 get slacks that are eliminated into a -t_i/lam_i diagonal of K's (2,2) block; the direct solve runs into
+    the control bounds while the dynamics are still violated (no restoration phase), `solve_bounded` then widens the bounds
+    tenfold, solves, and tightens back with a warm start. The result must be a KKT point of the TRUE problem, checked from
+    scratch: equalities, obstacle rows <= 0 with the active ones at 0, controls within +-0.5 and some at the bound,
+    multipliers of the inequality rows >= 0 and zero on inactive rows, stationarity in the free coordinates."""
+    T = 51
+    mo = M.build_car(O, T=T, obstacle="stage")
+    osolver = O.solver_from(mo)
+    n, m = mo["n"], mo["m"]
+    rng = np.random.default_rng(3)
+    z0 = np.zeros((1, T * n + (T - 1) * m))
+    for t in range(T):
+        o = t * (n + m)
+        z0[:, o:o + n] = mo["x1"] + (mo["xT"] - mo["x1"]) * t / (T - 1)
+        if t < T - 1:
+            z0[:, o + n:o + n + m] = 0.001 * rng.normal(size=(1, m))
+    opts = sqp.SQPOptions(max_iter=90)
+    be = OracleBackend(osolver, 1, linear="dense", options=opts)
+    hasI = be.bounds["hasI"] > 0
+    assert hasI.sum() == T and be.fixed.sum() == 2 * n and be.bounds["hasL"].sum() == (T - 1) * m
+    direct = sqp.solve(be, z0, options=opts)
+    assert not direct.converged.any()                                  # the situation the fallback exists for
+    res = sqp.solve_bounded(be, z0, options=opts)
+    assert res.converged.all() and res.staged.all()
+    z, lam = res.z[0], res.lam[0]
+    nlp = osolver.nlp
+    c, g = np.zeros(be.N_c), np.zeros(be.N_z)
+    nlp.eval_constraint(c, z); nlp.eval_objective_gradient(g, z)
+    js = nlp.jacobian_structure()
+    J = np.zeros(len(js)); nlp.eval_constraint_jacobian(J, z)
+    Jd = np.zeros((be.N_c, be.N_z)); Jd[[r - 1 for r, _ in js], [cc - 1 for _, cc in js]] = J
+    assert np.max(np.abs(c[~hasI])) < 1e-8 and np.max(c[hasI]) < 1e-8
+    active = c[hasI] > -1e-6
+    assert 1 <= active.sum() <= 6                                      # the path touches the obstacle at a few knots
+    lamI = lam[hasI]
+    assert np.all(lamI > 0.0) and np.max(lamI[~active]) < 1e-5 and np.min(lamI[active]) > 1e-3
+    isu = np.zeros(be.N_z, dtype=bool)
+    for t in range(T - 1):
+        isu[t * (n + m) + n: t * (n + m) + n + m] = True
+    u = z[isu]
+    assert np.all(np.abs(u) < 0.5) and (np.abs(u) > 0.5 - 1e-5).sum() >= 3
+    assert np.allclose(z[:n], mo["x1"]) and np.allclose(z[-n:], mo["xT"])   # pinned exactly
+    r = g + Jd.T @ lam                                                 # = z_L - z_U on bounded variables, anything on pinned ones
+    free_state = ~isu & ~be.fixed
+    assert np.max(np.abs(r[free_state])) < 1e-5
+    ru = r[isu]
+    inner = np.abs(u) < 0.5 - 1e-4
+    assert np.max(np.abs(ru[inner])) < 1e-4 and np.all(ru[u > 0.5 - 1e-5] < 1e-5) and np.all(ru[u < -0.5 + 1e-5] > -1e-5)

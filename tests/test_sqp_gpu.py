@@ -320,7 +320,8 @@ def test_interior_point_mode_with_active_control_bounds_matches_oracle_twin():
     assert be.bounds is not None and int(be.bounds["hasL"].sum()) == mp["T"] - 1
     got = sqp.solve(be, torch.as_tensor(z0, device=be.xp.device), options=opts, record=True)
     K = be.kkt.matrix(1)
-    diag = be.d_diag[1].cpu().numpy()
+    diag = be.d_diag[1, :pn.num_variables].cpu().numpy()      # (the array is [B, dim]: constraint rows carry the slack terms, none here)
+    assert float(be.d_diag[:, pn.num_variables:].abs().max()) == 0.0
     be.close()
     assert bool(got.converged.all()) and ref.converged.all() and len(got.history) == len(ref.history)
     for hg, hr in zip(got.history, ref.history):
@@ -374,3 +375,34 @@ def test_reference_cartpole_example_with_control_bounds_solves_on_the_device():
     assert np.max(np.abs(Z[:, :n] - x1)) < 1e-6 and np.max(np.abs(Z[:, -n:] - xT)) < 1e-6
     s.nlp.close()
     assert callable(ex.main)
+
+
+def test_reference_car_example_with_obstacle_inequalities_solves_on_the_device():
+    """/root/reference/examples/car/car.jl as published (T = 51, |u| <= 0.5, pinned end states, one obstacle INEQUALITY row
+    per knot, the example's guess) for a batch through Solver.solve(): inequality rows and bounds select the
+    interior-point mode; its (2,2)-block diagonal -t_i/lam_i is added inside the factor kernel like the bounds' Sigma. The
+    direct solve fails on some guesses (controls run into their bounds first); the bound continuation of `solve_bounded`
+    picks those up. Every converged problem: dynamics satisfied, obstacle rows <= 0 and touched, controls within the bounds and at them."""
+    B, T = 12, 51
+    model = M.build_car(D, T=T, obstacle="stage")
+    n, m, x1, xT = model["n"], model["m"], model["x1"], model["xT"]
+    s = D.solver_from(model, batch=B)
+    s.initialize_states(D.linear_interpolation(x1, xT, T))
+    rng = np.random.default_rng(2)
+    for b in range(B):
+        s.initialize_controls([0.001 * rng.normal(size=m) for _ in range(T - 1)], problem=b)
+    res = s.solve(options=dict(max_iter=300))
+    conv = res.converged.cpu().numpy()
+    assert s.broker is None and conv.sum() >= B - 1, conv          # (99.7 % of 1024 guesses: tools/ip_car.py)
+    Z = res.z.cpu().numpy()
+    c = np.zeros((B, s.nlp.num_constraint))
+    s.nlp.eval_constraint(c, Z)
+    clo, cup = s.nlp.constraint_bounds
+    ineq = clo != cup
+    Z, c = Z[conv], c[conv]
+    assert ineq.sum() == T and np.max(np.abs(c[:, ~ineq])) < 1e-7
+    assert np.max(c[:, ineq]) < 1e-7 and np.all((c[:, ineq] > -1e-5).sum(axis=1) >= 1)
+    U = np.concatenate([Z[:, t * (n + m) + n: t * (n + m) + n + m] for t in range(T - 1)], axis=1)
+    assert np.all(np.abs(U) < 0.5) and np.all((np.abs(U) > 0.5 - 1e-4).sum(axis=1) >= 3)
+    assert np.array_equal(Z[:, :n], np.tile(x1, (len(Z), 1))) and np.array_equal(Z[:, -n:], np.tile(xT, (len(Z), 1)))
+    s.nlp.close()
