@@ -406,3 +406,32 @@ def test_reference_car_example_with_obstacle_inequalities_solves_on_the_device()
     assert np.all(np.abs(U) < 0.5) and np.all((np.abs(U) > 0.5 - 1e-4).sum(axis=1) >= 3)
     assert np.array_equal(Z[:, :n], np.tile(x1, (len(Z), 1))) and np.array_equal(Z[:, -n:], np.tile(xT, (len(Z), 1)))
     s.nlp.close()
+
+
+def test_interior_point_inequality_rows_device_iterates_match_oracle_twin():
+    """Inequality rows in the interior-point mode: the -t_i/lam_i entries of K's (2,2) block and the shifted right-hand side
+    are applied on the device (factor kernel, DIAG instantiation; constraint array) and densely in the oracle-driven twin.
+    Car with obstacle rows, control bounds and pinned end states at the small test shape (T = 7; too short to reach the goal,
+    which is irrelevant here): the two arms must walk through the same iterates."""
+    import torch
+    kw = dict(T=7, obstacle="stage")
+    mo, mp = M.build_car(O, **kw), M.build_car(D, **kw)
+    B = 3
+    osolver, pn = O.solver_from(mo), D.solver_from(mp, batch=B).nlp
+    z0 = _guess(mp, B, 8) * 0.05
+    n, m, T = mp["n"], mp["m"], mp["T"]
+    for t in range(T):
+        z0[:, t * (n + m): t * (n + m) + n] = mp["x1"] + (mp["xT"] - mp["x1"]) * t / (T - 1)
+    perm, bw = PK.analyze(pn)
+    opts = sqp.SQPOptions(max_iter=12, dual_reg=1.0e-6)
+    ref = sqp.solve(OracleBackend(osolver, B, dual_reg=opts.dual_reg, perm=perm - 1, bw=bw, linear="band", options=opts), z0, options=opts, record=True)
+    be = sqp.DeviceBackend(pn, dual_reg=opts.dual_reg, options=opts)
+    assert int(be.bounds["hasI"].sum()) == T and int(be.bounds["hasL"].sum()) == (T - 1) * m
+    got = sqp.solve(be, torch.as_tensor(z0, device=be.xp.device), options=opts, record=True)
+    assert float(be.d_diag[:, pn.num_variables:].abs().max()) > 0.0          # the slack terms reached the kernel's array
+    be.close()
+    assert len(got.history) == len(ref.history) == 12
+    for hg, hr in zip(got.history, ref.history):
+        assert np.max(np.abs(hg["z"] - hr["z"]) / np.maximum(1.0, np.abs(hr["z"]))) < 1e-7, hg["it"]
+        assert np.allclose(hg["f"], hr["f"], rtol=1e-7, atol=1e-9), hg["it"]
+    pn.close()
