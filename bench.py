@@ -447,6 +447,12 @@ def run_ours(args):
                 line["solve"] = solve_config3.run(B=4096, T=101, max_iter=300, method="native")
                 t_arm = solve_config3.run(B=4096, T=101, max_iter=300, method="sqp")
                 line["solve"]["torch_glue_arm"] = {k: t_arm[k] for k in ("seconds", "solves_per_s", "accepted_frac", "gpu_launches")}
+                # the reference's cartpole example (BASELINE config 2's model, |u| <= 3 as bounds, its rollout guess): interior-point
+                # mode of the torch-glued arm, 4096 problems (64 distinct guesses)
+                import ip_cartpole
+                cp = ip_cartpole.run(3.0, 4096, 600, guess="rollout", distinct=64)
+                line["solve"]["cartpole_example_with_bounds"] = {k: cp[k] for k in ("seconds", "solves_per_s", "converged", "it_median", "it_max", "cv_max",
+                                                                                        "u_max", "at_bound", "end_error_max")}
             except Exception as e:  # noqa: BLE001
                 line["solve"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:
