@@ -35,7 +35,8 @@ class SqpOptions(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("max_refactor", C.c_int32), ("max_backtrack", C.c_int32), ("soc", C.c_int32)] + [
         (n, C.c_double) for n in ("tol_constraint", "tol_dual", "dual_reg", "reg_first", "reg_min", "reg_max", "reg_inc_first", "reg_inc",
                                   "reg_dec", "armijo", "merit_margin", "merit_rho", "merit_min", "lm_first", "lm_min", "lm_grow", "lm_shrink",
-                                  "lm_grow_below", "lm_zero", "lam_max", "exact_below")]
+                                  "lm_grow_below", "lm_zero", "lam_max", "exact_below", "mu_init", "barrier_kappa_eps", "barrier_kappa_mu",
+                                  "barrier_theta_mu", "tau_min", "bound_push", "bound_frac", "kappa_sigma", "tiny_step", "bound_relax")]
 
 
 _lib = None

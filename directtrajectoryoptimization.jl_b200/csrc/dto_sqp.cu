@@ -526,6 +526,300 @@ __global__ void __launch_bounds__(256) k_pick(const dto_sqp_args a, int32_t coun
     }
 }
 
+// =====================================================================================================================
+// Interior-point mode (sqp.py `solve`, the `ip` branches): inequality bounds on variables and inequality rows c_i(z) <= 0.
+// Barrier terms enter the SAME Newton-KKT step as a per-problem diagonal of K (Sigma = z_L/(x-l) + z_U/(u-x) on bounded
+// variables, -t_i/lam_i on inequality rows whose slacks t are eliminated), a shifted gradient and a shifted constraint
+// right-hand side. Separate kernels: the equality-only kernels above are what the parity tests pinned and stay untouched.
+// =====================================================================================================================
+__device__ __forceinline__ double wmin(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double wmaxnan(double m)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(FULL, m, o);
+        m = (w > m || w != w) ? w : m;
+    }
+    return m;
+}
+#define KEEPMAX(m, x)                     \
+    do {                                  \
+        const double x__ = fabs(x);       \
+        m = (x__ > m || x__ != x__) ? x__ : m; \
+    } while (0)
+
+// after the callbacks (g, c, J, H at z): diagonal of K, barrier gradient into g, shifted constraint right-hand side,
+// residual of c(z) + t = 0 into ckeep, barrier value; first iteration: slacks and their multipliers
+__global__ void k_ip_prepare(const dto_sqp_args a)
+{
+    WARP_PROBLEM();
+    const double mu = a.mu[b];
+    double accB = 0.0, accI = 0.0;
+    const double* z = a.z + b * a.N_z;
+    for (int i = lane; i < a.N_z; i += 32) {
+        const double hl = a.hasL[i], hu = a.hasU[i];
+        const double sL = hl > 0.0 ? z[i] - a.lo[i] : 1.0, sU = hu > 0.0 ? a.up[i] - z[i] : 1.0;
+        a.diag[b * a.dim + i] = hl * a.zL[b * a.N_z + i] / sL + hu * a.zU[b * a.N_z + i] / sU;
+        a.bg_w[b * a.N_z + i] += mu * (hu / sU - hl / sL);
+        accB += hl * log(sL) + hu * log(sU);
+    }
+    for (int j = lane; j < a.N_c; j += 32) {
+        const double c = a.bc[b * a.N_c + j];
+        if (a.p.any_ineq) {
+            const double hi = a.hasI[j];
+            double t = a.t[b * a.N_c + j], lam = a.lam[b * a.N_c + j];
+            if (a.it == 0) {   // slacks from the constraint values at the start, multipliers on the central path
+                t = hi * fmax(-c, a.p.bound_push);
+                if (hi > 0.0) lam = mu / fmax(t, 1.0e-300);
+                a.t[b * a.N_c + j] = t;
+                a.lam[b * a.N_c + j] = lam;
+            }
+            const double tS = hi > 0.0 ? t : 1.0, lamI = hi > 0.0 ? lam : 1.0;
+            a.diag[b * a.dim + a.N_z + j] = -hi * tS / lamI;
+            a.ckeep[b * a.N_c + j] = c + hi * t;                // residual of c(z) + t = 0
+            a.bc[b * a.N_c + j] = c + hi * (mu / lamI);         // right-hand side of the row
+            accI += hi * log(tS);
+        } else {
+            a.ckeep[b * a.N_c + j] = c;
+        }
+    }
+    accB = wsum(accB);
+    accI = wsum(accI);
+    if (lane == 0) a.fbar[b] = -mu * accI - mu * accB;
+}
+
+__global__ void k_ip_after_first(const dto_sqp_args a)
+{
+    WARP_PROBLEM();
+    const double mu = a.mu[b];
+    const double* z = a.z + b * a.N_z;
+    const double* rz = a.rhs + b * a.dim;
+    double dr = 0.0, comp = 0.0, emu = 0.0;
+    for (int i = lane; i < a.N_z; i += 32) {
+        const double hl = a.hasL[i], hu = a.hasU[i];
+        const double sL = hl > 0.0 ? z[i] - a.lo[i] : 1.0, sU = hu > 0.0 ? a.up[i] - z[i] : 1.0;
+        const double zL = a.zL[b * a.N_z + i], zU = a.zU[b * a.N_z + i];
+        const double gshift = mu * (hu / sU - hl / sL);
+        KEEPMAX(dr, (rz[i] - gshift - zL + zU) * a.free[i]);     // g + J'lam - z_L + z_U of the ORIGINAL problem
+        const double cL = hl * sL * zL, cU = hu * sU * zU;
+        KEEPMAX(comp, cL);
+        KEEPMAX(comp, cU);
+        KEEPMAX(emu, cL - hl * mu);
+        KEEPMAX(emu, cU - hu * mu);
+    }
+    if (a.p.any_ineq)
+        for (int j = lane; j < a.N_c; j += 32) {
+            const double hi = a.hasI[j];
+            const double cI = hi * (hi > 0.0 ? a.t[b * a.N_c + j] * a.lam[b * a.N_c + j] : 1.0);
+            KEEPMAX(comp, cI);
+            KEEPMAX(emu, cI - hi * mu);
+        }
+    dr = wmaxnan(dr);
+    comp = wmaxnan(comp);
+    emu = wmaxnan(emu);
+    const double cv = absmax_row(a.ckeep + b * a.N_c, a.N_c, lane);
+    const bool fin = finite_row(a.sol + b * a.dim, a.dim, lane);
+    if (lane == 0) {
+        double e = dr > cv ? dr : cv;
+        e = (emu > e || emu != emu) ? emu : e;
+        const double lower = fmin(a.p.kappa_mu * mu, pow(mu, a.p.theta_mu));
+        a.mu_next[b] = (e <= a.p.kappa_eps * mu) ? fmax(a.p.mu_floor, lower) : mu;
+        const double drc = (comp > dr || comp != comp) ? comp : dr;
+        a.cv[b] = cv;
+        a.dr[b] = drc;
+        a.fcur[b] = a.bf[b] + a.fbar[b];
+        a.exact[b] = cv <= a.p.exact_below ? 1.0 : 0.0;
+        bool done = a.done[b] != 0;
+        const bool newly = !done && cv <= a.p.tol_constraint && drc <= a.p.tol_dual;
+        if (newly) a.iters[b] = a.it;
+        done = done || newly;
+        a.done[b] = done ? 1 : 0;
+        const bool bad = (a.nneg[b] != a.N_c || !fin) && !done;
+        a.bad[b] = bad ? 1 : 0;
+        a.first[b] = 1;
+        a.tries[b] = 0;
+        if (done) atomicAdd(a.counters + DTO_SQP_N_DONE, 1);
+        if (!done) a.alist[atomicAdd(a.counters + DTO_SQP_N_ACTIVE, 1)] = (int32_t)b;
+        if (bad) {
+            a.pred_next[atomicAdd(a.counters + DTO_SQP_N_BAD, 1)] = (int32_t)b;
+            if (a.p.max_refactor > 0) atomicAdd(a.counters + DTO_SQP_N_RETRY, 1);
+        }
+    }
+}
+
+__global__ void k_ip_direction(const dto_sqp_args a)
+{
+    WARP_PROBLEM();
+    const double mu = a.mu[b];
+    const double tau = fmax(a.p.tau_min, 1.0 - mu);
+    const double* sol = a.sol + b * a.dim;
+    const double* z = a.z + b * a.N_z;
+    const double big = 1.0e300;
+    double gd = 0.0, c1 = 0.0, cl = 0.0, gdt = 0.0, amax = big, az = big;
+    for (int i = lane; i < a.N_z; i += 32) {
+        const double d = -sol[i] * a.free[i];
+        a.dz[b * a.N_z + i] = d;
+        gd += a.bg[b * a.N_z + i] * d;
+        const double hl = a.hasL[i], hu = a.hasU[i];
+        const double sL = hl > 0.0 ? z[i] - a.lo[i] : 1.0, sU = hu > 0.0 ? a.up[i] - z[i] : 1.0;
+        const double zL = a.zL[b * a.N_z + i], zU = a.zU[b * a.N_z + i];
+        const double dzL = hl * (mu / sL - zL - (hl * zL / sL) * d);
+        const double dzU = hu * (mu / sU - zU + (hu * zU / sU) * d);
+        a.dzL[b * a.N_z + i] = dzL;
+        a.dzU[b * a.N_z + i] = dzU;
+        if (hl > 0.0 && d < 0.0) amax = fmin(amax, -tau * sL / fmin(d, -1.0e-300));
+        if (hu > 0.0 && d > 0.0) amax = fmin(amax, tau * sU / fmax(d, 1.0e-300));
+        if (dzL < 0.0) az = fmin(az, -tau * zL / fmin(dzL, -1.0e-300));
+        if (dzU < 0.0) az = fmin(az, -tau * zU / fmin(dzU, -1.0e-300));
+    }
+    for (int j = lane; j < a.N_c; j += 32) {
+        const double dl = -sol[a.N_z + j];
+        a.dlam[b * a.N_c + j] = dl;
+        const double ck = a.ckeep[b * a.N_c + j], lam = a.lam[b * a.N_c + j];
+        c1 += fabs(ck);
+        cl += ck * (lam + dl);
+        if (a.p.any_ineq) {
+            const double hi = a.hasI[j];
+            const double tS = hi > 0.0 ? a.t[b * a.N_c + j] : 1.0, lamI = hi > 0.0 ? lam : 1.0;
+            const double dt = hi * (mu / lamI - tS - (tS / lamI) * dl);      // from t lam = mu, linearised
+            a.dt[b * a.N_c + j] = dt;
+            if (hi > 0.0 && dt < 0.0) amax = fmin(amax, -tau * tS / fmin(dt, -1.0e-300));
+            if (hi > 0.0 && dl < 0.0) az = fmin(az, -tau * lamI / fmin(dl, -1.0e-300));
+            gdt += hi * (mu / tS) * dt;
+        }
+    }
+    gd = wsum(gd);
+    c1 = wsum(c1);
+    cl = wsum(cl);
+    gdt = wsum(gdt);
+    amax = fmin(1.0, wmin(amax));
+    az = fmin(1.0, wmin(az));
+    {
+        double* bz = a.bz + b * a.N_z;
+        for (int i = lane; i < a.N_z; i += 32) bz[i] = z[i] + amax * a.dz[b * a.N_z + i];      // first trial: the longest allowed step
+    }
+    if (lane == 0) {
+        const double delta = a.delta[b], lm = a.lm[b];
+        if (delta > lm) a.delta_last[b] = delta;
+        const double curv = fmax(-gd + cl, 0.0);
+        const double nu_need = (gd + 0.5 * curv) / ((1.0 - a.p.merit_rho) * fmax(c1, 1.0e-300));
+        const double nu = fmax(a.p.merit_min, a.p.merit_margin * nu_need);
+        gd -= gdt;                                   // the barrier of the slacks joins the slope
+        a.nu[b] = nu;
+        a.c1[b] = c1;
+        a.slope[b] = gd - nu * c1;
+        a.phi0[b] = a.fcur[b] + nu * c1;
+        a.alpha[b] = amax;
+        a.amax[b] = amax;
+        a.a_z[b] = az;
+        a.accepted[b] = (a.done[b] || a.bad[b]) ? 1 : 0;
+    }
+}
+
+__global__ void k_ip_ls_round(const dto_sqp_args a, int32_t round)
+{
+    WARP_PROBLEM();
+    const double mu = a.mu[b];
+    double alpha = a.alpha[b];
+    const double az = a.a_z[b];
+    const double* bz = a.bz + b * a.N_z;
+    double barB = 0.0, barI = 0.0, ct1 = 0.0, mdz = 0.0, mz = 0.0;
+    for (int i = lane; i < a.N_z; i += 32) {
+        const double hl = a.hasL[i], hu = a.hasU[i];
+        const double sL = hl > 0.0 ? fmax(bz[i] - a.lo[i], 1.0e-300) : 1.0, sU = hu > 0.0 ? fmax(a.up[i] - bz[i], 1.0e-300) : 1.0;
+        barB += hl * log(sL) + hu * log(sU);
+        KEEPMAX(mdz, a.dz[b * a.N_z + i]);
+        KEEPMAX(mz, a.z[b * a.N_z + i]);
+    }
+    for (int j = lane; j < a.N_c; j += 32) {
+        double r = a.bc[b * a.N_c + j];
+        if (a.p.any_ineq) {
+            const double hi = a.hasI[j];
+            const double tt = hi > 0.0 ? fmax(a.t[b * a.N_c + j] + alpha * a.dt[b * a.N_c + j], 1.0e-300) : 1.0;
+            barI += hi * log(tt);
+            r += hi * tt;
+        }
+        ct1 += fabs(r);
+    }
+    barB = wsum(barB);
+    barI = wsum(barI);
+    ct1 = wsum(ct1);
+    mdz = wmaxnan(mdz);
+    mz = wmaxnan(mz);
+    bool accepted = a.accepted[b] != 0;
+    const double phi0 = a.phi0[b];
+    double ft = a.bf[b] - mu * barB;
+    ft = ft - mu * barI;
+    const double phit = ft + a.nu[b] * ct1;
+    bool ok = (phit <= phi0 + a.p.armijo * alpha * a.slope[b] + 2.2e-15 * fabs(phi0)) && !accepted;
+    if (round == 0) ok = ok || ((mdz <= a.p.tiny_step * (1.0 + mz)) && !accepted);      // tiny steps are taken untested
+    if (ok) {
+        for (int i = lane; i < a.N_z; i += 32) {
+            a.z[b * a.N_z + i] = bz[i];
+            a.zL[b * a.N_z + i] += az * a.dzL[b * a.N_z + i];
+            a.zU[b * a.N_z + i] += az * a.dzU[b * a.N_z + i];
+        }
+        for (int j = lane; j < a.N_c; j += 32) {
+            const double hi = a.p.any_ineq ? a.hasI[j] : 0.0;
+            a.lam[b * a.N_c + j] += (hi > 0.0 ? az : alpha) * a.dlam[b * a.N_c + j];
+            if (a.p.any_ineq) a.t[b * a.N_c + j] = hi * (hi > 0.0 ? fmax(a.t[b * a.N_c + j] + alpha * a.dt[b * a.N_c + j], 1.0e-300) : 1.0);
+        }
+    }
+    accepted = accepted || ok;
+    if (!accepted) alpha = 0.5 * alpha;
+    __syncwarp();
+    row_axpy(a.bz + b * a.N_z, a.z + b * a.N_z, alpha, a.dz + b * a.N_z, a.N_z, lane);   // next trial
+    if (lane == 0) {
+        a.accepted[b] = accepted ? 1 : 0;
+        a.alpha[b] = alpha;
+        if (!accepted) a.oidx[atomicAdd(a.counters + DTO_SQP_N_OPEN, 1)] = (int32_t)b;
+    }
+}
+
+__global__ void k_ip_end(const dto_sqp_args a)
+{
+    WARP_PROBLEM();
+    const double mu = a.mu[b];
+    if (a.p.lam_max > 0.0) {      // runaway multiplier estimates start again from zero -- equality rows only (lam_I > 0 is a barrier quantity)
+        double m = 0.0;
+        for (int j = lane; j < a.N_c; j += 32) KEEPMAX(m, a.lam[b * a.N_c + j] * (a.p.any_ineq ? 1.0 - a.hasI[j] : 1.0));
+        m = wmaxnan(m);
+        if (m > a.p.lam_max)
+            for (int j = lane; j < a.N_c; j += 32) a.lam[b * a.N_c + j] *= (a.p.any_ineq ? a.hasI[j] : 0.0);
+    }
+    const double ks = a.p.kappa_sigma;
+    for (int i = lane; i < a.N_z; i += 32) {      // z_L, z_U within [mu / (kappa s), kappa mu / s] of the new slacks
+        const double hl = a.hasL[i], hu = a.hasU[i];
+        const double zi = a.z[b * a.N_z + i];
+        const double sL = hl > 0.0 ? zi - a.lo[i] : 1.0, sU = hu > 0.0 ? a.up[i] - zi : 1.0;
+        a.zL[b * a.N_z + i] = hl * fmax(fmin(a.zL[b * a.N_z + i], ks * mu / sL), mu / (ks * sL));
+        a.zU[b * a.N_z + i] = hu * fmax(fmin(a.zU[b * a.N_z + i], ks * mu / sU), mu / (ks * sU));
+    }
+    if (a.p.any_ineq)
+        for (int j = lane; j < a.N_c; j += 32)
+            if (a.hasI[j] > 0.0) {
+                const double t = a.t[b * a.N_c + j];
+                a.lam[b * a.N_c + j] = fmax(fmin(a.lam[b * a.N_c + j], ks * mu / t), mu / (ks * t));
+            }
+    if (lane == 0) {
+        const bool accepted = a.accepted[b] != 0, done = a.done[b] != 0, bad = a.bad[b] != 0;
+        if (!done) a.mu[b] = a.mu_next[b];
+        const bool moved = !done && !bad;
+        const double alpha = a.alpha[b] / a.amax[b], delta = a.delta[b];     // fraction of the allowed step that was taken
+        double lm = a.lm[b];
+        if (moved && alpha < a.p.lm_grow_below) lm = fmax(a.p.lm_min, a.p.lm_grow * fmax(lm, delta));
+        if (moved && accepted && alpha >= 1.0) lm = a.p.lm_shrink * lm;
+        if (lm < a.p.lm_zero) lm = 0.0;
+        a.lm[b] = lm;
+        if (!accepted || bad) a.delta_last[b] = fmax(a.p.reg_first, a.p.reg_inc * fmax(a.delta_last[b], delta));
+    }
+}
+
 template <class K, class... Args>
 int launch_warp_per(K kernel, int64_t n, void* stream, Args... args)
 {
@@ -586,3 +880,8 @@ extern "C" int dto_sqp_k_pred_pick(const dto_sqp_args* a, int32_t count, int32_t
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e;
 }
+extern "C" int dto_sqp_k_ip_prepare(const dto_sqp_args* a, void* s) { return launch_warp_per(k_ip_prepare, a->B, s, *a); }
+extern "C" int dto_sqp_k_ip_after_first(const dto_sqp_args* a, void* s) { return launch_warp_per(k_ip_after_first, a->B, s, *a); }
+extern "C" int dto_sqp_k_ip_direction(const dto_sqp_args* a, void* s) { return launch_warp_per(k_ip_direction, a->B, s, *a); }
+extern "C" int dto_sqp_k_ip_ls_round(const dto_sqp_args* a, int32_t round, void* s) { return launch_warp_per(k_ip_ls_round, a->B, s, *a, round); }
+extern "C" int dto_sqp_k_ip_end(const dto_sqp_args* a, void* s) { return launch_warp_per(k_ip_end, a->B, s, *a); }

@@ -19,6 +19,9 @@ typedef struct dto_sqp_params {   /* SQPOptions of sqp.py, same meaning */
     double exact_below, lam_max;
     int32_t soc;
     int32_t max_refactor;   /* inertia-correction tries per problem and iteration */
+    /* interior-point mode (inequality bounds on variables, inequality rows c_i(z) <= 0) */
+    int32_t ip, any_ineq;
+    double mu_floor, kappa_eps, kappa_mu, theta_mu, tau_min, kappa_sigma, tiny_step, bound_push;
 } dto_sqp_params;
 
 enum { DTO_SQP_N_DONE = 0, DTO_SQP_N_BAD = 1, DTO_SQP_N_IDX = 2, DTO_SQP_N_NEED = 3, DTO_SQP_N_OPEN = 4, DTO_SQP_N_SOC_OK = 5,
@@ -73,6 +76,14 @@ typedef struct dto_sqp_args {
     double* vsol2;
     int32_t* vnneg2;
     double* vL2;
+    /* interior-point mode */
+    const double *hasL, *hasU, *lo, *up;   /* [N_z] 0/1 masks and finite bound values (0 where absent)        */
+    const double* hasI;                    /* [N_c] 1 = inequality row c_i(z) <= 0                              */
+    double *zL, *zU, *dzL, *dzU;           /* [B][N_z] bound multipliers and their steps                        */
+    double *t, *dt;                        /* [B][N_c] slacks of the inequality rows and their steps            */
+    double *mu, *mu_next, *amax, *a_z, *fbar;   /* [B] barrier parameter, step limits, barrier value at z      */
+    double* diag;                          /* [B][dim] the diagonal the factor kernel adds to K                 */
+    double* bg_w;                          /* = bg, writable (the barrier gradient is added to g)               */
 } dto_sqp_args;
 
 /* each returns 0 or -(cudaError_t) */
@@ -90,6 +101,12 @@ int dto_sqp_k_end(const dto_sqp_args* a, void* stream);
 int dto_sqp_k_reg_ladder(const dto_sqp_args* a, int32_t m, void* stream);
 /* per bad problem: the first candidate with the right inertia and a finite solution is kept (factor and solution copied) */
 int dto_sqp_k_reg_pick(const dto_sqp_args* a, int32_t count, int32_t m, void* stream);
+/* interior-point mode: the same iteration with barrier terms (separate kernels: the equality-only path above stays as it is) */
+int dto_sqp_k_ip_prepare(const dto_sqp_args* a, void* stream);      /* after the callbacks: diag, g += barrier gradient, c shifted, residual, barrier value */
+int dto_sqp_k_ip_after_first(const dto_sqp_args* a, void* stream);
+int dto_sqp_k_ip_direction(const dto_sqp_args* a, void* stream);
+int dto_sqp_k_ip_ls_round(const dto_sqp_args* a, int32_t round, void* stream);
+int dto_sqp_k_ip_end(const dto_sqp_args* a, void* stream);
 /* prediction: ladder of the first `count` problems of pred_cur from their damping (before the first factorisation is known) */
 int dto_sqp_k_pred_ladder(const dto_sqp_args* a, int32_t count, int32_t m, void* stream);
 /* after the first check: a predicted problem that did turn out bad takes the first working candidate of the second set */

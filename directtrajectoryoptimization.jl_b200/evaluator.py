@@ -433,10 +433,9 @@ class Solver:
             pinned = np.isfinite(lo) & (lo == up)
             rows_ok = bool(np.all((clo == cup) | (np.isneginf(clo) & (cup == 0.0))))      # equalities and c(z) <= 0 rows
             ok = self.nlp.hessian_lagrangian and rows_ok and self.nlp.num_shards == 1
-            inequalities = bool(np.any((np.isfinite(lo) | np.isfinite(up)) & ~pinned)) or not np.array_equal(clo, cup)
-            # bounds on variables (Bound(action_lower = ..., ...)) and inequality rows (Constraint(...; indices_inequality)):
-            # the interior-point mode of the torch-glued arm
-            method = ("sqp" if (record_iterates or inequalities) else "native") if ok else "broker"
+            # (bounds on variables (Bound(action_lower = ..., ...)) and inequality rows (Constraint(...; indices_inequality)): the
+            # interior-point mode, in both arms)
+            method = ("sqp" if record_iterates else "native") if ok else "broker"
         if method in ("sqp", "native"):
             from . import sqp
             o = sqp.SQPOptions()

@@ -18,11 +18,11 @@ regularisation, convergence masks); they are written against an array namespace 
 for the product, numpy for the oracle-driven twin the parity test runs (tests/sqp_oracle.py) -- so both arms
 execute literally the same algorithm.
 
-Scope (stated plainly): the native arm (dto_sqp_solve) takes equality-constrained problems whose variables are free or
-PINNED by equal lower and upper bounds (end points fixed by stage constraints as in examples/acrobot, or by
-Bound(state_lower = x1, state_upper = x1) as in test/solve.jl). Inequalities -- BOUNDS on variables
-(Bound(action_lower = ..., action_upper = ...)) and inequality ROWS c_i(z) <= 0 (Constraint(...; indices_inequality)) --
-are handled by `solve` / `solve_bounded` (torch arm and oracle twin) as a primal-dual interior point on the same
+Scope (stated plainly): equality rows, variables free or PINNED by equal lower and upper bounds (end points fixed by stage
+constraints as in examples/acrobot, or by Bound(state_lower = x1, state_upper = x1) as in test/solve.jl), and inequalities --
+BOUNDS on variables (Bound(action_lower = ..., action_upper = ...)) and inequality ROWS c_i(z) <= 0
+(Constraint(...; indices_inequality)) -- in all three arms (`solve` / `solve_bounded` here; dto_sqp_solve with the k_ip_*
+kernels). Inequalities are handled as a primal-dual interior point on the same
 Newton-KKT step: the barrier terms are a per-problem diagonal the factor kernel adds to K while it gathers a row
 (dto_kkt_device_pointer(k, 5): z_L/(x-l) + z_U/(u-x) on bounded variables, -t_i/lam_i on inequality rows whose slacks t
 are eliminated), fraction-to-the-boundary steps, monotone barrier updates -- but WITHOUT Ipopt's feasibility-restoration
@@ -34,7 +34,7 @@ bound; car (T = 51, |u| <= 0.5, pinned ends, obstacle inequality per knot, inter
 |u| <= 15: device iterates = oracle-twin iterates to 1e-13. What the missing restoration phase costs: cartpole from a guess
 whose states are interpolated from x1 to xT (not the example's) settles at ||c||_inf ~ 0.013 with 96 % of the controls
 saturated, whatever the options and with the continuation -- a one-swing trajectory that actuator cannot complete.
-`Solver.solve()` sends problems with inequalities here (method "sqp"). It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
+`Solver.solve()` runs the native arm for all of these (method "native"); "sqp" is this file's torch-glued arm. It is a line-search SQP with an l1 merit function, a second-order correction, Levenberg-Marquardt
 damping and Ipopt-style inertia correction of the primal regularisation; it is NOT Ipopt:
 iterate-for-iterate parity with the reference's Ipopt runs is unverifiable here and is not claimed.
 """
@@ -90,8 +90,8 @@ class SQPOptions:
     bound_frac: float = 1.0e-2
     kappa_sigma: float = 1.0e10        # z stays within [mu/(kappa s), kappa mu/s]
     tiny_step: float = 1.0e-6          # relative step size under which the full (fraction-to-the-boundary) step is taken untested
-    bound_stages: tuple = (10.0, 1.0)  # fallback of `solve_bounded` for problems the direct solve leaves unconverged: two-sided
-                                       #   bounds widened about their midpoint by these factors, one solve per stage, warm-started
+    bound_relax: float = 10.0          # fallback of `solve_bounded` for problems the direct solve leaves unconverged: two-sided bounds
+                                       #   widened about their midpoint by this factor, solved, then the true bounds warm-started (<= 1: off)
 
 
 class SQPResult:
@@ -413,17 +413,17 @@ def bound_arrays(lo, up, options: Optional[SQPOptions] = None, clo=None, cup=Non
 def solve_bounded(be, z0, lam0=None, options: Optional[SQPOptions] = None, record: bool = False) -> SQPResult:
     """`solve`, plus a fallback for problems with inequality bounds that the direct solve leaves unconverged (no restoration
     phase: an iterate can run into its bounds while the constraints are still violated): the two-sided bounds are widened
-    about their midpoint by options.bound_stages[0], the problem is solved from the ORIGINAL guess, and the bounds are
-    tightened stage by stage to the true ones (last factor 1), every stage warm-started from the one before. A problem
+    about their midpoint by options.bound_relax, the problem is solved from the ORIGINAL guess, and then the true bounds are
+    solved warm-started from there. A problem
     keeps its direct result when that converged; otherwise it takes the staged one. Problems stay independent: what a
     problem gets depends only on its own guess and the fixed stage list. The backend must offer set_bound_scale(scale)."""
     o = options or SQPOptions()
     xp = be.xp
     res = solve(be, z0, lam0, o, record)
-    if getattr(be, "bounds", None) is None or getattr(be, "set_bound_scale", None) is None or not o.bound_stages or xp.all(res.converged):
+    if getattr(be, "bounds", None) is None or getattr(be, "set_bound_scale", None) is None or o.bound_relax <= 1.0 or xp.all(res.converged):
         return res
     z, lam, its = z0, lam0, None
-    stages = tuple(o.bound_stages) + (() if float(o.bound_stages[-1]) == 1.0 else (1.0,))      # the last stage is the true problem
+    stages = (float(o.bound_relax), 1.0)      # the last stage is the true problem
     try:
         for scale in stages:
             be.set_bound_scale(float(scale))
@@ -804,6 +804,7 @@ def solve_native(nlp, z0, lam0=None, options: Optional[SQPOptions] = None) -> SQ
     _lib.check(L.dto_sqp_solve(nlp.handle, C.byref(co), ptr(z0), ptr(lam0), ptr(lo), ptr(up), ptr(z), ptr(lam), ptr(iters), ptr(done),
                                ptr(cv), ptr(dr), ptr(f), ptr(stats)))
     res = SQPResult(z, lam, iters.astype(np.float64), done.astype(bool), cv, dr, f, [])
+    res.staged = done == 2          # converged by the bound continuation (see solve_bounded)
     res.stats = dict(iterations=int(stats[0]), launches=int(stats[1]), factorisations=int(stats[2]), syncs=int(stats[3]),
                      refactorisations=int(stats[4]), corrections=int(stats[5]), search_rounds=int(stats[6]), multi_trial_passes=int(stats[7]), predicted_passes=int(stats[15]),
                      phase_ms=dict(callbacks_first_factor=stats[8] / 1e3, inertia_correction=stats[9] / 1e3, line_search=stats[10] / 1e3,

@@ -15,6 +15,11 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dto_b200 as D  # noqa: E402
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
 from examples import models as M  # noqa: E402
 
 
@@ -41,7 +46,7 @@ def main(batch=64, T=101):
         umax = max(umax, max(abs(u[0]) for u in us))
         ok += int(np.linalg.norm(xs[0] - x1) < 1e-3 and np.linalg.norm(xs[-1] - xT) < 1e-3 and bool(res.converged[b]))
     print(f"{ok} of {batch} swing-ups solved (||x_1 - x1||, ||x_T - xT|| < 1e-3, KKT residuals converged); max |u| = {umax:.6f} <= 3; "
-          f"median iterations {float(np.median(np.asarray(res.iterations.cpu()))):.0f}; kernels launched {solver.sqp_launches}")
+          f"median iterations {float(np.median(_np(res.iterations))):.0f}; kernels launched {solver.sqp_launches}")
     xs, us = solver.get_trajectory(0)
     print("x_1 =", xs[0], " x_T =", xs[-1])
     return ok

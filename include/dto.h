@@ -247,8 +247,10 @@ void* dto_kkt_device_pointer(dto_kkt* k, int which, int shard);
  * Replaces solve!(solver) (/root/reference/src/solver.jl:45-47: MOI.optimize! hands the five callbacks to Ipopt) for a
  * whole batch at once: a lock-step line-search Newton-KKT (SQP) method whose every step is a kernel of this library --
  * the callbacks above, the KKT consumer, and O(B N) bookkeeping kernels (csrc/dto_sqp.cu); only eight counters per
- * synchronisation cross PCIe during the iterations. It is NOT Ipopt (no inequality handling, l1 merit line search
- * instead of a filter); scope: equality constraints, variables free or pinned by equal bounds. The algorithm is stated
+ * synchronisation cross PCIe during the iterations. It is NOT Ipopt (l1 merit line search instead of a filter, no feasibility
+ * restoration). Scope: equality rows and inequality rows c_i(z) <= 0; variables free, pinned by equal bounds, or bounded --
+ * inequalities by a primal-dual interior point on the same Newton-KKT step (the barrier terms are a diagonal the factor kernel
+ * adds to K). The algorithm is stated
  * in directtrajectoryoptimization.jl_b200/sqp.py (`solve`); the fields below are that file's SQPOptions. */
 typedef struct dto_sqp_options {
     int32_t max_iter;        /* Options.max_iter (src/options.jl:9) */
@@ -263,12 +265,21 @@ typedef struct dto_sqp_options {
     double lm_first, lm_min, lm_grow, lm_shrink, lm_grow_below, lm_zero;   /* Levenberg-Marquardt damping of H */
     double lam_max;          /* multiplier estimates beyond this are reset to 0 (0 = off) */
     double exact_below;      /* ||c||_inf under which the Hessian of the Lagrangian is used (else the objective's: Gauss-Newton) */
+    /* interior-point mode: inequality bounds on variables and inequality rows c_i(z) <= 0 */
+    double mu_init;          /* first barrier parameter */
+    double barrier_kappa_eps, barrier_kappa_mu, barrier_theta_mu;   /* monotone barrier update (Waechter & Biegler 2006, eq. 7) */
+    double tau_min;          /* fraction to the boundary */
+    double bound_push, bound_frac;   /* the starting point is moved this far inside its bounds */
+    double kappa_sigma;      /* bound multipliers stay within [mu / (kappa s), kappa mu / s] */
+    double tiny_step;        /* relative step size under which a step is taken without the merit test */
+    double bound_relax;      /* > 1: problems left unconverged are solved again with two-sided bounds widened by this factor, then
+                                the true bounds warm-started from there (<= 1: no such fallback) */
 } dto_sqp_options;
 void dto_sqp_default_options(dto_sqp_options* o);
 /* Solves every problem of a one-shard batch from z0 [B][N_z] (lambda0 [B][N_c] or NULL = 0). lower / upper [N_z] or
  * NULL: primal_bounds (src/data.jl:123-133); a variable with lower == upper is pinned to that value, any other finite
- * bound -> DTO_ERR_UNSUPPORTED, as are inequality constraint rows. Outputs (each may be NULL): z [B][N_z],
- * lambda [B][N_c], iterations [B] (max_iter where not converged), converged [B], constraint_violation [B] = ||c||_inf,
+ * bound is an inequality (interior point). Constraint rows other than equalities and (-Inf, 0] -> DTO_ERR_UNSUPPORTED. Outputs (each may be NULL): z [B][N_z],
+ * lambda [B][N_c], iterations [B] (max_iter where not converged), converged [B] (1; 2 = by the bound continuation), constraint_violation [B] = ||c||_inf,
  * dual_residual [B], objective [B]; stats[16] = {iterations run, kernel launches, factorisation launches, host
  * synchronisations, inertia-correction factorisations, second-order-correction solves, sequential line-search rounds,
  * one-pass evaluations of all remaining step lengths, and host

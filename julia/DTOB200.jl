@@ -386,7 +386,7 @@ function DTO.initialize_controls!(solver::Solver, actions; problem::Int=0)
 end
 
 # ---------------------------------------------------------------- batched solve (dto_sqp_solve, include/dto.h)
-"dto_sqp_options: same fields, same order (4 Int32 then 21 Float64)"
+"dto_sqp_options: same fields, same order (4 Int32 then 31 Float64)"
 Base.@kwdef struct SQPOptions
     max_iter::Int32 = 200;  max_refactor::Int32 = 14;  max_backtrack::Int32 = 10;  soc::Int32 = 1
     tol_constraint::Float64 = 1.0e-8;  tol_dual::Float64 = 1.0e-6;  dual_reg::Float64 = 1.0e-9
@@ -396,14 +396,17 @@ Base.@kwdef struct SQPOptions
     lm_first::Float64 = 1.0e-2;  lm_min::Float64 = 1.0e-4;  lm_grow::Float64 = 4.0;  lm_shrink::Float64 = 0.25
     lm_grow_below::Float64 = 0.3;  lm_zero::Float64 = 1.0e-10
     lam_max::Float64 = 1.0e4;  exact_below::Float64 = 1.0
+    mu_init::Float64 = 0.1;  barrier_kappa_eps::Float64 = 10.0;  barrier_kappa_mu::Float64 = 0.2;  barrier_theta_mu::Float64 = 1.5
+    tau_min::Float64 = 0.99;  bound_push::Float64 = 1.0e-2;  bound_frac::Float64 = 1.0e-2;  kappa_sigma::Float64 = 1.0e10
+    tiny_step::Float64 = 1.0e-6;  bound_relax::Float64 = 10.0
 end
 
 """
     solve_batch(nlp, z0; lower, upper, options = SQPOptions(), lambda0 = nothing)
 
 All problems of a one-device batch from the guesses `z0[n, B]` (column b = problem b), in lock step on the GPU: the role
-Ipopt plays for one problem in `solve!(solver)` (src/solver.jl:45-47). Equality constraints; variables free or pinned by
-`lower[i] == upper[i]` (anything else throws with DTO_ERR_UNSUPPORTED). Returns a named tuple
+Ipopt plays for one problem in `solve!(solver)` (src/solver.jl:45-47). Equality rows and rows c(z) <= 0; variables free, pinned
+by `lower[i] == upper[i]`, or bounded (interior point). Returns a named tuple
 `(z, lambda, iterations, converged, constraint_violation, dual_residual, objective, stats)`.
 """
 function solve_batch(nlp::BatchedNLPData, z0::Matrix{Float64}; lower=nothing, upper=nothing, options::SQPOptions=SQPOptions(), lambda0=nothing)

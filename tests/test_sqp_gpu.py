@@ -18,6 +18,10 @@ from sqp_oracle import OracleBackend
 pytestmark = pytest.mark.gpu
 
 
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
 def _guess(model, B, seed):
     T, n, m = model["T"], model["n"], model["m"]
     rng = np.random.default_rng(seed)
@@ -190,8 +194,8 @@ def test_native_solver_walks_through_the_oracle_driven_iterates(name, kw, B, ite
 
 def test_native_solver_pinned_end_points_and_scope():
     """test/solve.jl:227-296 set-up (x1 pinned by equal bounds, xT by a GeneralConstraint) through dto_sqp_solve: same
-    result as the oracle-driven twin, pinned variables exactly at the bound; an inequality bound is refused with
-    DTO_ERR_UNSUPPORTED rather than approximated."""
+    result as the oracle-driven twin, pinned variables exactly at the bound; inequality bounds switch the native solver
+    to its interior-point mode (iterates strictly inside), inconsistent bounds are an argument error."""
     from dto_b200 import _lib
     kw = dict(reference_exact=True)
     mo, mp = M.build_linear_general(O, **kw), M.build_linear_general(D, **kw)
@@ -208,10 +212,19 @@ def test_native_solver_pinned_end_points_and_scope():
     assert np.array_equal(got.z[:, :n], np.tile(mp["x1"], (B, 1)))
     assert np.all(np.linalg.norm(got.z[:, -n:] - mp["xT"], axis=1) < 1e-3)
     pn.close()
-    pb = D.solver_from(M.build_cartpole(D, T=11), batch=2).nlp        # |u| <= u_bnd: inequality bounds on the controls
-    with pytest.raises(_lib.DtoError) as e:
-        sqp.solve_native(pb, np.zeros((2, pb.num_variables)))
-    assert e.value.status == -7 and "inequality bound" in str(e.value)
+    pb = D.solver_from(M.build_cartpole(D, T=11), batch=2).nlp        # |u| <= 3: inequality bounds -> interior-point mode
+    pb.set_parameters(np.tile(np.concatenate([np.zeros(4), [0.0, np.pi, 0.0, 0.0]]), (2, 1)))
+    rb = sqp.solve_native(pb, np.zeros((2, pb.num_variables)), options=sqp.SQPOptions(max_iter=15))
+    ub = np.stack([rb.z[:, t * 5 + 4] for t in range(10)], axis=1)
+    assert np.all(np.abs(ub) < 3.0) and np.all(np.isfinite(rb.z))      # (T = 11 is too short to swing up: only the bounds are checked)
+    with pytest.raises(_lib.DtoError) as e:                          # lower > upper is an argument error, not a scope question
+        lo, up = pb.variable_bounds
+        lo2 = lo.copy(); lo2[4] = 5.0
+        z0 = np.zeros((2, pb.num_variables))
+        out = [np.empty((2, pb.num_variables)), np.empty((2, pb.num_constraint))]
+        _lib.check(_lib.lib().dto_sqp_solve(pb.handle, None, z0.ctypes.data, None, lo2.ctypes.data, np.ascontiguousarray(up).ctypes.data,
+                                            out[0].ctypes.data, out[1].ctypes.data, None, None, None, None, None, None))
+    assert e.value.status == -1
     pb.close()
 
 
@@ -363,10 +376,10 @@ def test_reference_cartpole_example_with_control_bounds_solves_on_the_device():
             xs.append(np.array(M.cartpole_rk3_explicit(xs[-1], u0, np.zeros(0)), dtype=float))
         s.initialize_states(xs, problem=b)
         s.initialize_controls([u0] * (T - 1), problem=b)
-    res = s.solve(options=dict(max_iter=600))                 # method="auto" -> "sqp" (interior point): no broker
+    res = s.solve(options=dict(max_iter=600))                 # method="auto" -> the native solver's interior-point mode: no broker
     assert s.broker is None and s.sqp_launches > 100
-    assert bool(res.converged.all()), res.iterations
-    Z = res.z.cpu().numpy()
+    assert bool(_np(res.converged).all()), res.iterations
+    Z = _np(res.z)
     c = np.zeros((B, s.nlp.num_constraint))
     s.nlp.eval_constraint(c, Z)
     assert np.max(np.abs(c)) < 1e-7
@@ -392,9 +405,9 @@ def test_reference_car_example_with_obstacle_inequalities_solves_on_the_device()
     for b in range(B):
         s.initialize_controls([0.001 * rng.normal(size=m) for _ in range(T - 1)], problem=b)
     res = s.solve(options=dict(max_iter=300))
-    conv = res.converged.cpu().numpy()
+    conv = _np(res.converged)
     assert s.broker is None and conv.sum() >= B - 1, conv          # (99.7 % of 1024 guesses: tools/ip_car.py)
-    Z = res.z.cpu().numpy()
+    Z = _np(res.z)
     c = np.zeros((B, s.nlp.num_constraint))
     s.nlp.eval_constraint(c, Z)
     clo, cup = s.nlp.constraint_bounds
@@ -435,3 +448,44 @@ def test_interior_point_inequality_rows_device_iterates_match_oracle_twin():
         assert np.max(np.abs(hg["z"] - hr["z"]) / np.maximum(1.0, np.abs(hr["z"]))) < 1e-7, hg["it"]
         assert np.allclose(hg["f"], hr["f"], rtol=1e-7, atol=1e-9), hg["it"]
     pn.close()
+
+
+@pytest.mark.parametrize("case", ["pendulum_bounds", "cartpole_example", "car_example"])
+def test_native_interior_point_agrees_with_the_torch_glued_arm(case):
+    """The interior-point mode exists in both arms: `sqp.solve` (torch glue; equal to the oracle-driven twin iterate by
+    iterate, tests above) and dto_sqp_solve (kernels k_ip_* of csrc/dto_sqp.cu). Same algorithm, different summation
+    orders: the two must converge for the same problems, in (nearly) the same number of iterations, to the same points."""
+    import torch
+    if case == "pendulum_bounds":
+        model, B, iters = M.build_pendulum(D, u_bnd=15.0), 4, 60
+    elif case == "cartpole_example":
+        model, B, iters = M.build_cartpole(D, T=101), 8, 400
+    else:
+        model, B, iters = M.build_car(D, T=51, obstacle="stage"), 8, 300
+    n, m, T, x1, xT = model["n"], model["m"], model["T"], model["x1"], model["xT"]
+    s = D.solver_from(model, batch=B)
+    rng = np.random.default_rng(5)
+    if case == "cartpole_example":
+        s.nlp.set_parameters(np.tile(np.concatenate([x1, xT]), (B, 1)))
+        for b in range(B):
+            u0 = np.array([0.01 * (1.0 + 0.2 * rng.normal())])
+            xs = [x1.astype(float)]
+            for _ in range(T - 1):
+                xs.append(np.array(M.cartpole_rk3_explicit(xs[-1], u0, np.zeros(0)), dtype=float))
+            s.initialize_states(xs, problem=b)
+            s.initialize_controls([u0] * (T - 1), problem=b)
+    else:
+        s.initialize_states(D.linear_interpolation(x1, xT, T))
+        for b in range(B):
+            s.initialize_controls([(0.3 if case == "pendulum_bounds" else 0.001) * rng.normal(size=m) for _ in range(T - 1)], problem=b)
+    nat = s.solve(options=dict(max_iter=iters), method="native")
+    tor = s.solve(options=dict(max_iter=iters), method="sqp")
+    cn, ct = _np(nat.converged), _np(tor.converged)
+    assert cn.sum() >= B - 1 and ct.sum() >= B - 1
+    both = cn & ct
+    zn, zt = _np(nat.z)[both], _np(tor.z)[both]
+    assert np.max(np.abs(zn - zt) / np.maximum(1.0, np.abs(zt))) < 1e-5
+    assert np.allclose(_np(nat.objective)[both], _np(tor.objective)[both], rtol=1e-6, atol=1e-8)
+    direct = both & ~_np(getattr(nat, "staged", np.zeros(B, bool))) & ~_np(getattr(tor, "staged", torch.zeros(B, dtype=torch.bool)))
+    assert np.max(np.abs(_np(nat.iterations)[direct] - _np(tor.iterations)[direct])) <= 3
+    s.nlp.close()

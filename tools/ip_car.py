@@ -12,6 +12,11 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import dto_b200 as D  # noqa: E402
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
 from examples import models as M  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -30,15 +35,15 @@ t0 = time.perf_counter()
 res = s.solve(options=so)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-conv, it = res.converged.cpu().numpy(), res.iterations.cpu().numpy()
-Z = res.z.cpu().numpy()
+conv, it = _np(res.converged), _np(res.iterations)
+Z = _np(res.z)
 c = np.zeros((B, s.nlp.num_constraint))
 s.nlp.eval_constraint(c, Z)
 clo, cup = s.nlp.constraint_bounds
 ineq = clo != cup
 U = np.concatenate([Z[:, t * (n + m) + n: t * (n + m) + n + m] for t in range(T - 1)], axis=1)
-print(json.dumps(dict(options=so, T=T, B=B, seconds=dt, converged=float(conv.mean()), staged=float(res.staged.cpu().numpy().mean()) if hasattr(res, "staged") else 0.0,
+print(json.dumps(dict(options=so, T=T, B=B, seconds=dt, converged=float(conv.mean()), staged=float(_np(res.staged).mean()) if hasattr(res, "staged") else 0.0,
                       it_median=float(np.median(it)), it_max=float(it.max()), eq_violation_max_converged=float(np.abs(c[conv][:, ~ineq]).max()) if conv.any() else None,
                       obstacle_max_converged=float(c[conv][:, ineq].max()) if conv.any() else None, u_max=float(np.abs(U).max()),
-                      at_bound=float((np.abs(U) > 0.4999).mean()), f_median=float(np.median(res.objective.cpu().numpy())), launches=int(s.sqp_launches))))
+                      at_bound=float((np.abs(U) > 0.4999).mean()), f_median=float(np.median(_np(res.objective))), launches=int(s.sqp_launches))))
 s.nlp.close()

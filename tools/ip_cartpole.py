@@ -12,6 +12,11 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import dto_b200 as D  # noqa: E402
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
 from examples import models as M  # noqa: E402
 
 def run(ub=3.0, B=32, iters=400, guess=None, sigma=None, distinct=None):
@@ -46,15 +51,15 @@ def run(ub=3.0, B=32, iters=400, guess=None, sigma=None, distinct=None):
     so = dict(max_iter=iters)
     so.update(json.loads(os.environ.get("DTO_SQP_OPTIONS", "{}")))
     t0 = time.perf_counter()
-    res = s.solve(options=so, method="sqp")
+    res = s.solve(options=so, method=os.environ.get("METHOD", "auto"))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    it, conv = res.iterations.cpu().numpy(), res.converged.cpu().numpy()
-    Z = res.z.cpu().numpy()
+    it, conv = _np(res.iterations), _np(res.converged)
+    Z = _np(res.z)
     U = np.stack([Z[:, t * (n + m) + n] for t in range(T - 1)], axis=1)
     out = (dict(u_bnd=ub, guess=guess, guess_sigma=sigma, options=so, T=T, B=B, seconds=dt, converged=float(conv.mean()), it_median=float(np.median(it)), it_max=float(it.max()),
-                          cv_max=float(res.constraint_violation.cpu().numpy().max()), dr_median=float(np.median(res.dual_residual.cpu().numpy())),
-                          u_max=float(np.abs(U).max()), end_error_max=float(np.abs(Z[:, -n:] - mc["xT"]).max()), at_bound=float((np.abs(U) > 0.997 * ub).mean()), f_median=float(np.median(res.objective.cpu().numpy()))))
+                          cv_max=float(_np(res.constraint_violation).max()), dr_median=float(np.median(_np(res.dual_residual))),
+                          u_max=float(np.abs(U).max()), end_error_max=float(np.abs(Z[:, -n:] - mc["xT"]).max()), at_bound=float((np.abs(U) > 0.997 * ub).mean()), f_median=float(np.median(_np(res.objective)))))
     s.nlp.close()
     out["solves_per_s"] = B / dt
     return out
