@@ -214,3 +214,25 @@ def test_reference_car_example_inequality_rows_and_bound_continuation():
     ru = r[isu]
     inner = np.abs(u) < 0.5 - 1e-4
     assert np.max(np.abs(ru[inner])) < 1e-4 and np.all(ru[u > 0.5 - 1e-5] < 1e-5) and np.all(ru[u < -0.5 + 1e-5] > -1e-5)
+
+
+def test_bound_arrays_classify_and_scale_bounds():
+    """primal_bounds (src/data.jl:123-133) -> solver masks: lower == upper pins a variable, any other finite bound is an
+    inequality; a continuation stage widens TWO-SIDED bounds about their midpoint and leaves one-sided and pinned ones
+    alone; constraint rows with bounds (-Inf, 0] are inequality rows, anything else but equalities is refused."""
+    import pytest
+    inf = np.inf
+    lo = np.array([-inf, 0.0, 1.0, -2.0, -inf, 3.0])
+    up = np.array([inf, 0.0, 5.0, inf, 4.0, 3.0])
+    fixed, b = sqp.bound_arrays(lo, up, clo=np.array([0.0, -inf, 0.0]), cup=np.array([0.0, 0.0, 0.0]))
+    assert fixed.tolist() == [False, True, False, False, False, True]
+    assert b["hasL"].tolist() == [0, 0, 1, 1, 0, 0] and b["hasU"].tolist() == [0, 0, 1, 0, 1, 0] and b["hasI"].tolist() == [0, 1, 0]
+    assert b["lo"][2] == 1.0 and b["up"][2] == 5.0 and 0.0 < b["pushL"][2] <= 0.01 * 4.0
+    _, b10 = sqp.bound_arrays(lo, up, scale=10.0)
+    assert b10["lo"][2] == 3.0 - 20.0 and b10["up"][2] == 3.0 + 20.0            # two-sided: widened about the midpoint 3
+    assert b10["lo"][3] == -2.0 and b10["up"][4] == 4.0                          # one-sided: unchanged
+    assert sqp.bound_arrays(np.full(3, -inf), np.full(3, inf))[1] is None       # nothing to do: equality-only mode
+    with pytest.raises(NotImplementedError):
+        sqp.bound_arrays(lo, up, clo=np.array([-1.0]), cup=np.array([1.0]))     # a ranged row is outside the scope
+    with pytest.raises(ValueError):
+        sqp.bound_arrays(np.array([2.0]), np.array([1.0]))
