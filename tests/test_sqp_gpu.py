@@ -489,3 +489,29 @@ def test_native_interior_point_agrees_with_the_torch_glued_arm(case):
     direct = both & ~_np(getattr(nat, "staged", np.zeros(B, bool))) & ~_np(getattr(tor, "staged", torch.zeros(B, dtype=torch.bool)))
     assert np.max(np.abs(_np(nat.iterations)[direct] - _np(tor.iterations)[direct])) <= 3
     s.nlp.close()
+
+
+def test_one_sided_bounds_in_both_device_arms():
+    """A bound on one side only (Bound(action_lower = [-10]), no upper bound): the interior-point mode must treat the missing
+    side as absent (no barrier term, no push, never scaled by the continuation). Pendulum swing-up, whose unconstrained optimum
+    dips to u = -16.7: both device arms converge to the same point, u >= -10 strictly, the bound is active somewhere, and the
+    upper side is free to exceed +10."""
+    model = M.build_pendulum(D)
+    n, m, T = model["n"], model["m"], model["T"]
+    model["bounds"] = [D.Bound(n, m, action_lower=[-10.0])] * (T - 1) + [D.Bound(n, 0)]
+    B = 3
+    s = D.solver_from(model, batch=B)
+    lo, up = s.nlp.variable_bounds
+    assert np.isfinite(lo).sum() == T - 1 and not np.isfinite(up).any()
+    s.initialize_states(D.linear_interpolation(model["x1"], model["xT"], T))
+    rng = np.random.default_rng(3)
+    for b in range(B):
+        s.initialize_controls([0.3 * rng.normal(size=m) for _ in range(T - 1)], problem=b)
+    nat = s.solve(options=dict(max_iter=80), method="native")
+    tor = s.solve(options=dict(max_iter=80), method="sqp")
+    assert _np(nat.converged).all() and _np(tor.converged).all()
+    zn, zt = _np(nat.z), _np(tor.z)
+    assert np.max(np.abs(zn - zt) / np.maximum(1.0, np.abs(zt))) < 1e-5
+    U = np.stack([zn[:, t * (n + m) + n] for t in range(T - 1)], axis=1)
+    assert np.all(U > -10.0) and np.any(U < -10.0 + 1e-4) and np.any(U > 10.0)
+    s.nlp.close()
