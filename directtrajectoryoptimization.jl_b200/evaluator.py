@@ -200,6 +200,7 @@ class BatchedNLPData:
     def set_parameters(self, w):
         w = _f64(w, (self.batch, self.num_parameter), "parameters")
         _lib.check(_lib.lib().dto_set_parameters(self.handle, _p(w)))
+        self._w_host = w.copy()         # (a solve over several devices re-creates one batch per device: it needs them again)
 
     def set_x(self, z):
         z = _f64(z, (self.batch, self.num_variables), "variables")
@@ -432,7 +433,7 @@ class Solver:
             clo, cup = self.nlp.constraint_bounds
             pinned = np.isfinite(lo) & (lo == up)
             rows_ok = bool(np.all((clo == cup) | (np.isneginf(clo) & (cup == 0.0))))      # equalities and c(z) <= 0 rows
-            ok = self.nlp.hessian_lagrangian and rows_ok and self.nlp.num_shards == 1
+            ok = self.nlp.hessian_lagrangian and rows_ok        # (several devices: one native solve per device, side by side)
             # (bounds on variables (Bound(action_lower = ..., ...)) and inequality rows (Constraint(...; indices_inequality)): the
             # interior-point mode, in both arms)
             method = ("sqp" if record_iterates else "native") if ok else "broker"
@@ -447,7 +448,8 @@ class Solver:
         if method == "native":
             if record_iterates:
                 raise ValueError("solve: record_iterates needs method='sqp' (the native solver keeps no history)")
-            res = sqp.solve_native(self.nlp, self._initial, options=o)
+            res = sqp.solve_native(self.nlp, self._initial, options=o) if self.nlp.num_shards == 1 else \
+                sqp.solve_native_sharded(self.nlp, self._initial, options=o)
             self.sqp_launches = res.stats["launches"]
             self.results, self.iterates, self.broker = res, [], None
             return res

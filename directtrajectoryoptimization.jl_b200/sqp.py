@@ -811,3 +811,53 @@ def solve_native(nlp, z0, lam0=None, options: Optional[SQPOptions] = None) -> SQ
                                    of_which_corrections=stats[11] / 1e3, setup=stats[12] / 1e3, loop=stats[13] / 1e3,
                                    results=stats[14] / 1e3))
     return res
+
+
+def solve_native_sharded(nlp, z0, lam0=None, options: Optional[SQPOptions] = None) -> SQPResult:
+    """`solve_native` for a batch spread over several devices (row (e): problems are independent, contiguous shards, no
+    collective): dto_sqp_solve drives ONE device, so every shard gets its own one-device batch of the same shape (model library
+    and static tables shared, its slice of the per-problem parameters), the solves run side by side from one host thread each
+    (ctypes releases the GIL for the duration of the C call), and the results are put back in the caller's order; the final
+    iterate also becomes the resident z of the original batch (get_trajectory)."""
+    import threading
+
+    import numpy as np
+    B = nlp.batch
+    z0 = np.ascontiguousarray(z0, dtype=np.float64)
+    parts = [(nlp.shard_device(i),) + tuple(int(v) for v in nlp.shard_range(i)) for i in range(nlp.num_shards)]
+    w = getattr(nlp, "_w_host", None)
+    if nlp.num_parameter and w is None:
+        raise RuntimeError("solve_native_sharded: the per-problem parameters were not set through set_parameters")
+    results, errors = [None] * len(parts), []
+
+    def work(k, device, begin, size):
+        sub = None
+        try:
+            if size == 0:
+                return
+            sub = nlp.new_batch(batch=size, devices=[device])
+            if nlp.num_parameter:
+                sub.set_parameters(w[begin:begin + size])
+            results[k] = solve_native(sub, z0[begin:begin + size], None if lam0 is None else lam0[begin:begin + size], options)
+        except Exception as e:  # noqa: BLE001 - re-raised in the caller's thread
+            errors.append(e)
+        finally:
+            if sub is not None:
+                sub.close()
+
+    threads = [threading.Thread(target=work, args=(k,) + p) for k, p in enumerate(parts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    done = [r for r in results if r is not None]
+    cat = lambda name: np.concatenate([getattr(r, name) for r in done])  # noqa: E731
+    res = SQPResult(cat("z"), cat("lam"), cat("iterations"), cat("converged"), cat("constraint_violation"), cat("dual_residual"), cat("objective"), [])
+    res.staged = cat("staged")
+    res.stats = {k: (max if k == "iterations" else sum)(r.stats[k] for r in done) for k in done[0].stats if k != "phase_ms"}
+    res.stats["devices"] = [p[0] for p in parts]
+    assert res.z.shape[0] == B
+    nlp.set_x(res.z)
+    return res

@@ -515,3 +515,49 @@ def test_one_sided_bounds_in_both_device_arms():
     U = np.stack([zn[:, t * (n + m) + n] for t in range(T - 1)], axis=1)
     assert np.all(U > -10.0) and np.any(U < -10.0 + 1e-4) and np.any(U > 10.0)
     s.nlp.close()
+
+
+def test_solve_over_several_devices_equals_the_single_device_solve():
+    """Row (e) for the solver: a batch spread over all visible devices is solved by one dto_sqp_solve per device, side by side
+    (sqp.solve_native_sharded), no collective. Problems are independent and every kernel gives a problem the same bits wherever
+    it sits, so the result must equal the one-device solve bit for bit -- with per-problem parameters and bounds in play
+    (cartpole example) and without (pendulum). Needs >= 2 GPUs (`gpurun --gpus 2`)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    for case in ("pendulum", "cartpole"):
+        B = 2 * ndev + 1                                   # ragged shards
+        outs = []
+        for devices in ([0], list(range(ndev))):
+            if case == "pendulum":
+                model = M.build_pendulum(D)
+                s = D.solver_from(model, batch=B, devices=devices)
+                s.initialize_states(D.linear_interpolation(model["x1"], model["xT"], model["T"]))
+                for b in range(B):
+                    s.initialize_controls([np.array([0.05 * (b + 1)]) for _ in range(model["T"] - 1)], problem=b)
+                opts = dict(max_iter=60)
+            else:
+                model = M.build_cartpole(D, T=101)
+                T, x1, xT = 101, model["x1"], model["xT"]
+                s = D.solver_from(model, batch=B, devices=devices)
+                W = np.tile(np.concatenate([x1, xT]), (B, 1))
+                W[:, 5] += 0.01 * np.arange(B)             # per-problem goal angles: the parameter slices must follow the shards
+                s.nlp.set_parameters(W)
+                for b in range(B):
+                    u0 = np.array([0.01 * (1.0 + 0.1 * b)])
+                    xs = [x1.astype(float)]
+                    for _ in range(T - 1):
+                        xs.append(np.array(M.cartpole_rk3_explicit(xs[-1], u0, np.zeros(0)), dtype=float))
+                    s.initialize_states(xs, problem=b)
+                    s.initialize_controls([u0] * (T - 1), problem=b)
+                opts = dict(max_iter=300)
+            assert s.nlp.num_shards == len(devices)
+            res = s.solve(options=opts)
+            assert s.broker is None and _np(res.converged).all()
+            xs_last, _ = s.get_trajectory(B - 1)
+            outs.append((_np(res.z).copy(), _np(res.iterations).copy(), np.concatenate(xs_last)))
+            if len(devices) > 1:
+                assert res.stats["devices"] == devices
+            s.nlp.close()
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
