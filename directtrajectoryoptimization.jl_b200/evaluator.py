@@ -416,14 +416,13 @@ class Solver:
     def solve(self, options: Optional[dict] = None, record_iterates: bool = False, method: str = "auto"):
         """solve!(solver) (src/solver.jl:45-47) for every problem of the batch. The reference's caller is
         Ipopt, which is not available in this image. These drivers stand in for it:
-          * "native" (default where it applies: exact Hessians, equality constraints, variables free or pinned by
-            equal bounds): the lock-step batched Newton-KKT solver inside libdto.so (dto_sqp_solve) -- callbacks,
-            KKT assembly, factorisation, line-search evaluations and all bookkeeping on the device, no per-problem
-            host solver (BASELINE config 3);
-          * "sqp": the same algorithm with torch doing the bookkeeping (sqp.py `solve`; the statement of the algorithm
-            and the arm the oracle-driven twin mirrors; the only one that records iterates, and the one that takes
-            inequality bounds on variables -- Bound(action_lower = ..., action_upper = ...), the cartpole example -- by a
-            primal-dual interior point on the same Newton-KKT kernels (no restoration phase: scope note in sqp.py);
+          * "native" (default where it applies: exact Hessians; equality rows and rows c(z) <= 0; variables free, pinned
+            by equal bounds, or bounded): the lock-step batched Newton-KKT solver inside libdto.so (dto_sqp_solve) --
+            callbacks, KKT assembly, factorisation, line-search evaluations and all bookkeeping on the device, no
+            per-problem host solver; inequalities by a primal-dual interior point on the same kernels (no restoration
+            phase: scope note in sqp.py). A batch over several devices is solved one device per host thread;
+          * "sqp": the same algorithm with torch doing the bookkeeping (sqp.py `solve` / `solve_bounded`; the statement of
+            the algorithm and the arm the oracle-driven twin mirrors; the only one that records iterates; one device);
           * "broker": B per-problem host NLP solvers (SciPy trust-constr) running in lock step whose
             callbacks rendezvous into batched GPU calls (driver.py): the protocol an Ipopt-
             per-task driver would use.

@@ -276,7 +276,7 @@ typedef struct dto_sqp_options {
                                 the true bounds warm-started from there (<= 1: no such fallback) */
 } dto_sqp_options;
 void dto_sqp_default_options(dto_sqp_options* o);
-/* Solves every problem of a one-shard batch from z0 [B][N_z] (lambda0 [B][N_c] or NULL = 0). lower / upper [N_z] or
+/* Solves every problem of a one-shard batch (several devices: one batch and one host thread per device) from z0 [B][N_z] (lambda0 [B][N_c] or NULL = 0). lower / upper [N_z] or
  * NULL: primal_bounds (src/data.jl:123-133); a variable with lower == upper is pinned to that value, any other finite
  * bound is an inequality (interior point). Constraint rows other than equalities and (-Inf, 0] -> DTO_ERR_UNSUPPORTED. Outputs (each may be NULL): z [B][N_z],
  * lambda [B][N_c], iterations [B] (max_iter where not converged), converged [B] (1; 2 = by the bound continuation), constraint_violation [B] = ||c||_inf,
